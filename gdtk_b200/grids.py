@@ -1,0 +1,117 @@
+"""Small structured-grid generators for job scripts, tests and the benchmark.
+
+Grid generation is prep-stage host work in Eilmer (src/geom, src/eilmer/fbarray.lua) and
+outside the accelerated path; these helpers cover what the configurations of
+BASELINE.json need: boxes, straight-sided quadrilateral patches (Coons/TFI patch with
+straight edges = bilinear map) and splitting a grid into an array of blocks
+(``FBArray:new{grid=, nib=, njb=, nkb=}``).
+"""
+import numpy as np
+
+from . import _abi
+from .geometry import BlockGeometry, NG
+
+
+def box_grid_2d(x0, x1, y0, y1, nic, njc):
+    x = x0 + (x1 - x0) * (np.arange(nic + 1) / nic)
+    y = y0 + (y1 - y0) * (np.arange(njc + 1) / njc)
+    X, Y = np.meshgrid(x, y, indexing="xy")          # shape (njv, niv)
+    return X.copy(), Y.copy()
+
+
+def box_grid_3d(p0, p1, nic, njc, nkc):
+    x = p0[0] + (p1[0] - p0[0]) * (np.arange(nic + 1) / nic)
+    y = p0[1] + (p1[1] - p0[1]) * (np.arange(njc + 1) / njc)
+    z = p0[2] + (p1[2] - p0[2]) * (np.arange(nkc + 1) / nkc)
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")    # shape (nkv, njv, niv)
+    return X.copy(), Y.copy(), Z.copy()
+
+
+def quad_patch_grid(p00, p10, p11, p01, nic, njc):
+    """Straight-edged quadrilateral p00 (i=0,j=0), p10 (i=max,j=0), p11, p01; uniform
+    parameter distribution (makePatch with Line edges, default Coons patch)."""
+    r = (np.arange(nic + 1) / nic)[None, :]
+    s = (np.arange(njc + 1) / njc)[:, None]
+    out = []
+    for m in range(2):
+        out.append((1 - r) * (1 - s) * p00[m] + r * (1 - s) * p10[m] + r * s * p11[m] + (1 - r) * s * p01[m])
+    return out[0], out[1]
+
+
+def uniform_box_geometry(dims, nic, njc, nkc, dx, dy, dz=1.0):
+    """BlockGeometry of a uniform Cartesian block without touching vertices.
+
+    For spacings that are exactly representable (dyadic fractions) every formula of
+    geometry_2d/geometry_3d is exact, so the constants below are what those functions
+    return (tests/test_geometry.py checks this); this is the fast set-up route for the
+    large benchmark grids.
+    """
+    g = BlockGeometry(dims, nic, njc, nkc if dims == 3 else 1)
+    g.len[0][...] = dx
+    g.len[1][...] = dy
+    if dims == 3:
+        g.len[2][...] = dz
+        g.vol[...] = dx * dy * dz
+        frames = [((1, 0, 0), (0, 1, 0), (0, 0, 1), dy * dz),
+                  ((0, 1, 0), (0, 0, 1), (1, 0, 0), dx * dz),
+                  ((0, 0, 1), (1, 0, 0), (0, 1, 0), dx * dy)]
+    else:
+        g.vol[...] = dx * dy
+        g.areaxy[...] = dx * dy
+        # signed zeros as produced by FVInterface.update_2D_geometric_data
+        frames = [((1.0, -0.0, 0.0), (-0.0, -1.0, 0.0), (0, 0, 1), dy),
+                  ((0.0, 1.0, 0.0), (1.0, -0.0, 0.0), (0, 0, 1), dx)]
+    for d, (n, t1, t2, area) in enumerate(frames):
+        for m in range(3):
+            g.face[d][m][...] = n[m]
+            g.face[d][3 + m][...] = t1[m]
+            g.face[d][6 + m][...] = t2[m]
+        g.face[d][9][...] = area
+    return g
+
+
+def split_grid(grid, nib, njb, nkb=1):
+    """Cut a vertex grid into nib x njb x nkb sub-grids (FBArray); returns a list of
+    (ib, jb, kb, subgrid) in the reference's block order (i fastest? no: fbarray.lua
+    numbers blocks with k fastest, then j, then i)."""
+    P = [np.asarray(a) for a in grid]
+    dims = len(P)
+    if dims == 2:
+        njv, niv = P[0].shape
+        nkc = 1
+    else:
+        nkv, njv, niv = P[0].shape
+        nkc = nkv - 1
+    nic, njc = niv - 1, njv - 1
+
+    def cuts(n, nb):
+        base, extra = divmod(n, nb)
+        edges = [0]
+        for b in range(nb):
+            edges.append(edges[-1] + base + (1 if b < extra else 0))
+        return edges
+    ci, cj, ck = cuts(nic, nib), cuts(njc, njb), cuts(nkc, nkb) if dims == 3 else [0, 1]
+    out = []
+    for ib in range(nib):
+        for jb in range(njb):
+            for kb in range(nkb if dims == 3 else 1):
+                if dims == 2:
+                    sub = tuple(a[cj[jb]:cj[jb + 1] + 1, ci[ib]:ci[ib + 1] + 1].copy() for a in P)
+                else:
+                    sub = tuple(a[ck[kb]:ck[kb + 1] + 1, cj[jb]:cj[jb + 1] + 1, ci[ib]:ci[ib + 1] + 1].copy() for a in P)
+                out.append((ib, jb, kb, sub))
+    return out
+
+
+def connect_block_array(blocks_by_index, dims):
+    """Give every interior face of a regular block array its ExchangeBC_FullFace.
+    blocks_by_index: dict (ib, jb, kb) -> FluidBlock (with .id set)."""
+    from .sim import ExchangeBC_FullFace
+    for (ib, jb, kb), blk in blocks_by_index.items():
+        for d, (di, dj, dk) in enumerate(((1, 0, 0), (0, 1, 0), (0, 0, 1))):
+            if d >= dims:
+                continue
+            nb = blocks_by_index.get((ib + di, jb + dj, kb + dk))
+            if nb is not None:
+                blk.bcList[_abi.FACE_NAMES[2 * d + 1]] = ExchangeBC_FullFace(nb.id, 2 * d, 0)
+                nb.bcList[_abi.FACE_NAMES[2 * d]] = ExchangeBC_FullFace(blk.id, 2 * d + 1, 0)
