@@ -1,0 +1,197 @@
+"""Synthetic job descriptions for the configurations BASELINE.json names.
+
+Each factory returns (config, gmodel, blocks) ready for ``Simulation``; they play the
+role of the Lua job scripts under examples/eilmer in the reference:
+
+* cone20        examples/eilmer/2D/sharp-cone-20-degrees/sg/cone20.lua  (C1)
+* ffs           examples/eilmer/2D/forward-facing-step/ffs.lua          (C2)
+* box3d         3D ideal-air box / sheared ramp, N x N x N blocks        (C3, C4)
+* sod           examples/eilmer/3D/sod-shock-tube/sg (2D or 3D tube)
+* tpg_box3d     thermally-perfect 5-species air box                      (C5)
+"""
+import math
+import os
+
+import numpy as np
+
+from . import _abi
+from .gas import FlowState, IdealGas, set_gas_model
+from .grids import (box_grid_2d, box_grid_3d, quad_patch_grid, split_grid, connect_block_array,
+                    uniform_box_geometry)
+from .sim import (Config, FluidBlock, InFlowBC_Supersonic, OutFlowBC_Simple, OutFlowBC_SimpleExtrapolate,
+                  WallBC_WithSlip, identify_block_connections)
+from .geometry import NG, geometry_3d, geometry_2d
+
+
+def ideal_air():
+    """examples' ideal-air-gas-model.lua: mMass 0.02896, gamma 1.4."""
+    return IdealGas(mMass=0.02896, gamma=1.4, name="air")
+
+
+def cone20(flux_calculator="ausmdv", nx0=10, nx1=30, ny=40, **cfg_kw):
+    """Mach 1.5 flow over a 20-degree cone, 2D axisymmetric, 2 blocks (C1).
+
+    Geometry, states and settings of cone20.lua:26-66.  Differences, both forced by
+    scope: config.flux_calculator is set explicitly (the reference default is the
+    adaptive hanel/ausmdv blend) and the second patch uses the same
+    straight-edged Coons patch as the first one instead of gridType="ao"."""
+    gm = ideal_air()
+    cfg = Config(dimensions=2, axisymmetric=True, flux_calculator=flux_calculator,
+                 max_time=5.0e-3, max_step=3000, cfl_value=0.5, extrema_clipping=False)
+    for k, v in cfg_kw.items():
+        setattr(cfg, k, v)
+    initial = FlowState(gm, p=5955.0, T=304.0, velx=0.0)
+    inflow = FlowState(gm, p=95.84e3, T=1103.0, velx=1000.0)
+    a, b, c = (0.0, 0.0), (0.2, 0.0), (1.0, 0.29118)
+    d, e, f = (1.0, 1.0), (0.2, 1.0), (0.0, 1.0)
+    grid0 = quad_patch_grid(a, b, e, f, nx0, ny)
+    grid1 = quad_patch_grid(b, c, d, e, nx1, ny)
+    blk0 = FluidBlock(grid0, inflow, id=0)
+    blk1 = FluidBlock(grid1, initial, id=1)
+    identify_block_connections([blk0, blk1], 2)
+    blk0.bcList["west"] = InFlowBC_Supersonic(inflow)
+    blk1.bcList["east"] = OutFlowBC_Simple()
+    return cfg, gm, [blk0, blk1]
+
+
+def sod(dims=3, ncells=100, nj=2, nk=2, flux_calculator="ausmdv", nblocks=1, **cfg_kw):
+    """Sod's shock tube along x (examples/eilmer/3D/sod-shock-tube/sg/sod.lua: L=1.0,
+    high p=1e5,T=348.4 | low p=1e4,T=278.8, ideal air, t=0.6 ms)."""
+    gm = ideal_air()
+    cfg = Config(dimensions=dims, flux_calculator=flux_calculator, max_time=0.6e-3, max_step=5000,
+                 dt_init=1.0e-6, cfl_value=0.5)
+    for k, v in cfg_kw.items():
+        setattr(cfg, k, v)
+    hi = FlowState(gm, p=1.0e5, T=348.4)
+    lo = FlowState(gm, p=1.0e4, T=278.8)
+
+    def init(x, y, z):
+        return hi if x < 0.5 else lo
+    if dims == 3:
+        grid = box_grid_3d((0.0, 0.0, 0.0), (1.0, 0.1, 0.1), ncells, nj, nk)
+        parts = split_grid(grid, nblocks, 1, 1)
+    else:
+        grid = box_grid_2d(0.0, 1.0, 0.0, 0.1, ncells, nj)
+        parts = split_grid(grid, nblocks, 1)
+    blocks = {}
+    for n, (ib, jb, kb, sub) in enumerate(parts):
+        blocks[(ib, jb, kb)] = FluidBlock(sub, init, id=n)
+    connect_block_array(blocks, dims)
+    return cfg, gm, list(blocks.values())
+
+
+def _perturbed_prims(gm, geom, base, seed, amplitude=1.0e-3, noise=1.0e-6):
+    """Padded primitive arrays: base FlowState with rho and (consistently) p perturbed by
+    d(rho)/rho = 1e-3 sin(2 pi x) sin(2 pi y) sin(2 pi z) plus seeded noise 1e-6."""
+    shp = (geom.NK, geom.NJ, geom.NI)
+    vals = base.as_prims()
+    prims = [np.full(shp, v) for v in vals]
+    x, y, z = geom.pos
+    pert = amplitude * np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y) * (np.sin(2 * np.pi * z) if geom.dims == 3 else 1.0)
+    rng = np.random.default_rng(seed)
+    pert = pert + noise * (rng.random(shp) - 0.5)
+    fac = 1.0 + pert
+    prims[0] = prims[0] * fac
+    prims[2] = prims[2] * fac      # p = rho R T at unchanged T and u
+    nsp = base.nsp
+    if nsp > 1:
+        for i in range(nsp):
+            prims[8 + nsp + i] = prims[8 + nsp + i] * fac   # rho_s = massf * rho
+    return prims
+
+
+def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True, seed=1234,
+          gmodel=None, inflow=None, **cfg_kw):
+    """3D ideal-air box (C3/C4): unit cube, n^3 cells in nb^3 blocks; inflow west, simple
+    outflow east, slip walls elsewhere; initial state = inflow + smooth perturbation.
+    sheared=True tilts the k-lines by 10 degrees (general-metric path, cf.
+    examples/eilmer/3D/simple-ramp)."""
+    gm = gmodel or ideal_air()
+    cfg = Config(dimensions=3, flux_calculator=flux_calculator, max_step=10, max_time=1.0,
+                 dt_init=1.0e-3, cfl_value=0.5)
+    for k, v in cfg_kw.items():
+        setattr(cfg, k, v)
+    inflow = inflow or FlowState(gm, p=95.84e3, T=1103.0, velx=1000.0)
+    if n % nb:
+        raise ValueError("n must be divisible by nb")
+    m = n // nb
+    h = 1.0 / n
+    blocks = {}
+    bid = 0
+    for ib in range(nb):
+        for jb in range(nb):
+            for kb in range(nb):
+                x0, y0, z0 = ib * m * h, jb * m * h, kb * m * h
+                if sheared or not uniform_fast:
+                    X, Y, Z = box_grid_3d((x0, y0, z0), (x0 + m * h, y0 + m * h, z0 + m * h), m, m, m)
+                    if sheared:
+                        X = X + math.tan(math.radians(10.0)) * Z
+                    geom = geometry_3d(X, Y, Z)
+                else:
+                    geom = uniform_box_geometry(3, m, m, m, h, h, h)
+                    ii = (np.arange(geom.NI) - NG + 0.5) * h + x0
+                    jj = (np.arange(geom.NJ) - NG + 0.5) * h + y0
+                    kk = (np.arange(geom.NK) - NG + 0.5) * h + z0
+                    geom.pos[0][...] = ii[None, None, :]
+                    geom.pos[1][...] = jj[None, :, None]
+                    geom.pos[2][...] = kk[:, None, None]
+                prims = _perturbed_prims(gm, geom, inflow, seed + bid)
+                blk = FluidBlock(geom, prims, id=bid)
+                blocks[(ib, jb, kb)] = blk
+                bid += 1
+    connect_block_array(blocks, 3)
+    for (ib, jb, kb), blk in blocks.items():
+        if ib == 0:
+            blk.bcList["west"] = InFlowBC_Supersonic(inflow)
+        if ib == nb - 1:
+            blk.bcList["east"] = OutFlowBC_Simple()
+    return cfg, gm, list(blocks.values())
+
+
+def tpg_box3d(n=32, nb=2, gas_file=None, **kw):
+    """C5: thermally-perfect 5-species air (N2, O2, NO, N, O), frozen chemistry, T = 3000 K."""
+    gas_file = gas_file or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                        "tests", "golden", "gas", "therm-perf-5-species-air.json")
+    gm = set_gas_model(gas_file)
+    massf = {"N2": 0.767 * 0.99, "O2": 0.233 * 0.99, "NO": 0.004, "N": 0.003, "O": 0.003}
+    inflow = FlowState(gm, p=95.84e3, T=3000.0, velx=3000.0, massf=massf)
+    return box3d(n=n, nb=nb, gmodel=gm, inflow=inflow, **kw)
+
+
+def ffs(nx=384, ny=128, flux_calculator="ausmdv", uniform_fast=True, **cfg_kw):
+    """Mach-3 forward-facing step (C2): domain [0,3]x[0,1], step at x=0.6, height 0.2
+    (examples/eilmer/2D/forward-facing-step/ffs.lua:21-32), three blocks like the example:
+    blk0 [0,0.6]x[0,0.2], blk1 [0,0.6]x[0.2,1], blk2 [0.6,3]x[0.2,1].  nx, ny are the cell
+    counts of the bounding grid (4096 x 1024 for the benchmark); dx = 3/nx, dy = 1/ny."""
+    gm = ideal_air()
+    cfg = Config(dimensions=2, flux_calculator=flux_calculator, max_step=10, max_time=1.0,
+                 dt_init=1.0e-3, cfl_value=0.5)
+    for k, v in cfg_kw.items():
+        setattr(cfg, k, v)
+    T0 = 300.0
+    a0 = math.sqrt(gm.gamma * gm.Rgas * T0)
+    inflow = FlowState(gm, p=101.325e3, T=T0, velx=3.0 * a0)
+    dx, dy = 3.0 / nx, 1.0 / ny
+    i_step, j_step = int(round(0.6 / dx)), int(round(0.2 / dy))
+    specs = [(0, i_step, 0, j_step), (0, i_step, j_step, ny), (i_step, nx, j_step, ny)]
+    blocks = []
+    for bid, (i0, i1, j0, j1) in enumerate(specs):
+        if uniform_fast:
+            geom = uniform_box_geometry(2, i1 - i0, j1 - j0, 1, dx, dy)
+            ii = (np.arange(geom.NI) - NG + 0.5 + i0) * dx
+            jj = (np.arange(geom.NJ) - NG + 0.5 + j0) * dy
+            geom.pos[0][...] = ii[None, None, :]
+            geom.pos[1][...] = jj[None, :, None]
+        else:
+            X, Y = box_grid_2d(i0 * dx, i1 * dx, j0 * dy, j1 * dy, i1 - i0, j1 - j0)
+            geom = geometry_2d(X, Y)
+        blocks.append(FluidBlock(geom, inflow, id=bid))
+    from .sim import ExchangeBC_FullFace
+    blocks[0].bcList["north"] = ExchangeBC_FullFace(1, _abi.SOUTH)
+    blocks[1].bcList["south"] = ExchangeBC_FullFace(0, _abi.NORTH)
+    blocks[1].bcList["east"] = ExchangeBC_FullFace(2, _abi.WEST)
+    blocks[2].bcList["west"] = ExchangeBC_FullFace(1, _abi.EAST)
+    blocks[0].bcList["west"] = InFlowBC_Supersonic(inflow)
+    blocks[1].bcList["west"] = InFlowBC_Supersonic(inflow)
+    blocks[2].bcList["east"] = OutFlowBC_Simple()
+    return cfg, gm, blocks

@@ -1,0 +1,951 @@
+// eb200.cu -- host runtime behind the C ABI of include/eb200.h.
+//
+// Owns the device arena (SoA fields of all local blocks), the block table, the ghost-cell
+// work lists and the stage loop of gasdynamic_explicit_increment_with_fixed_grid
+// (reference src/eilmer/simcore_gasdynamic_step.d:906-1575).  Every numerical operation
+// of a time step runs in the CUDA kernels of this directory; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "eb200_internal.h"
+
+#ifndef EB_TILE_Y
+#define EB_TILE_Y 8
+#endif
+
+namespace {
+
+thread_local char g_err[1024] = "";
+void set_err(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+
+#define CUDA_OK(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            set_err("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,   \
+                    cudaGetErrorString(e_));                                                   \
+            return -100;                                                                       \
+        }                                                                                      \
+    } while (0)
+
+struct BC {
+    int kind = EB200_BC_WALL_WITH_SLIP, other_blk = -1, other_face = -1, orientation = 0;
+    std::vector<double> params;
+    int param_index = -1;
+};
+
+struct Block {
+    int id = 0, nic = 0, njc = 0, nkc = 0, owner = 0;
+    bool local = false;
+    int NI = 0, NJ = 0, NK = 0, kg = 0;
+    long long ncp = 0, cell0 = -1, stride[3] = {0, 0, 0};
+    int local_index = -1;
+    bool has_geometry = false, cartesian = false;
+    std::vector<double> vol, areaxy, len[3], face[3];
+    BC bc[6];
+    long long cidx(int i, int j, int k) const { return ((long long)(k + kg) * NJ + (j + EB_NG)) * NI + (i + EB_NG); }
+};
+
+struct Peer {
+    int rank = -1;
+    std::vector<int> send_idx, recv_idx;      // arena indices
+    int *d_send_idx = nullptr, *d_recv_idx = nullptr;
+    double *d_send = nullptr, *d_recv = nullptr;
+};
+
+struct Sim {
+    eb200_config cfg;
+    EbParams P;
+    EbGas hgas;
+    EbGas* d_gas = nullptr;
+    int n_stages = 0, threeD = 0, nfaces = 4;
+    std::vector<std::unique_ptr<Block>> blocks;
+    std::vector<Block*> local;
+    bool committed = false;
+    EbArena A;
+    std::vector<void*> allocs;
+    std::vector<EbBlockDesc> hdesc;
+    EbBlockDesc* d_desc = nullptr;
+    long long ncta = 0;
+    int which = 0;
+    EbCopyItem* d_copy = nullptr; long long ncopy = 0;
+    EbReflectItem* d_refl = nullptr; long long nrefl = 0;
+    EbFillItem* d_fill = nullptr; long long nfill = 0;
+    double* d_params = nullptr;
+    std::vector<Peer> peers;
+    eb200_exchange_fn exchange = nullptr; void* exchange_user = nullptr;
+    int* d_status = nullptr; int* h_status = nullptr;
+    unsigned long long* d_red = nullptr; double* d_last = nullptr;
+    cudaStream_t stream = nullptr;
+    int cur = 0;                              // index of the primitive buffer holding the current state
+    int U0 = 0;                               // index of the U level that currently plays U[0]
+    std::vector<int> Ulev;                    // permutation of U levels (swap at the end of a step)
+    long long launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    double flux_ms_acc = 0.0; long long flux_launches = 0;
+};
+
+std::vector<std::unique_ptr<Sim>> g_sims;
+
+Sim* get_sim(int h)
+{
+    if (h < 0 || h >= (int)g_sims.size() || !g_sims[h]) { set_err("invalid sim handle %d", h); return nullptr; }
+    return g_sims[h].get();
+}
+Block* get_blk(Sim* s, int id)
+{
+    for (auto& b : s->blocks) if (b->id == id) return b.get();
+    set_err("unknown block id %d", id);
+    return nullptr;
+}
+
+int n_stages_for(int scheme)
+{
+    switch (scheme) {
+    case EB200_UPDATE_EULER: return 1;
+    case EB200_UPDATE_PC: case EB200_UPDATE_MIDPOINT: return 2;
+    case EB200_UPDATE_CLASSIC_RK3: case EB200_UPDATE_TVD_RK3: return 3;
+    }
+    return 0;
+}
+// gamma tables of simcore_gasdynamic_step.d:1235-1395
+void stage_gammas(int scheme, int stage, double g[3])
+{
+    g[0] = g[1] = g[2] = 0.0;
+    if (stage == 1) {
+        switch (scheme) {
+        case EB200_UPDATE_EULER: case EB200_UPDATE_PC: case EB200_UPDATE_TVD_RK3: g[0] = 1.0; break;
+        case EB200_UPDATE_MIDPOINT: case EB200_UPDATE_CLASSIC_RK3: g[0] = 0.5; break;
+        }
+    } else if (stage == 2) {
+        switch (scheme) {
+        case EB200_UPDATE_PC: g[0] = 0.5; g[1] = 0.5; break;
+        case EB200_UPDATE_MIDPOINT: g[0] = 0.0; g[1] = 1.0; break;
+        case EB200_UPDATE_CLASSIC_RK3: g[0] = -1.0; g[1] = 2.0; break;
+        case EB200_UPDATE_TVD_RK3: g[0] = 0.25; g[1] = 0.25; break;
+        }
+    } else {
+        switch (scheme) {
+        case EB200_UPDATE_CLASSIC_RK3: g[0] = 1.0 / 6.0; g[1] = 4.0 / 6.0; g[2] = 1.0 / 6.0; break;
+        case EB200_UPDATE_TVD_RK3: g[0] = 1.0 / 6.0; g[1] = 1.0 / 6.0; g[2] = 4.0 / 6.0; break;
+        }
+    }
+}
+
+// --- host copies of the curve evaluation, used once to fill the constants of EbCurve --------
+bool h_coeffs(const EbCurve& c, double T, double a[9])
+{
+    int nb = c.nbreaks;
+    if (c.nseg == 1 || T < (c.T_breaks[1] - 0.5 * c.T_blends[0])) { memcpy(a, c.coeffs[0], 72); return true; }
+    if (T > (c.T_breaks[nb - 2] + 0.5 * c.T_blends[c.nseg - 2])) { memcpy(a, c.coeffs[c.nseg - 1], 72); return true; }
+    for (int i = 1; i < nb - 1; ++i) {
+        double lo = c.T_breaks[i] - 0.5 * c.T_blends[i - 1], hi = c.T_breaks[i] + 0.5 * c.T_blends[i - 1];
+        if (T >= lo && T <= hi) {
+            double wB = (1. / c.T_blends[i - 1]) * (T - lo), wA = 1.0 - wB;
+            for (int j = 0; j < 9; ++j) a[j] = wA * c.coeffs[i - 1][j] + wB * c.coeffs[i][j];
+            return true;
+        }
+        if (T > hi && T < (c.T_breaks[i + 1] - 0.5 * c.T_blends[i])) { memcpy(a, c.coeffs[i], 72); return true; }
+    }
+    return false;
+}
+double h_Cp(const EbCurve& c, double T)
+{
+    double a[9]; h_coeffs(c, T, a);
+    double Cp_on_R = a[0] / (T * T) + a[1] / T + a[2] + a[3] * T;
+    Cp_on_R += a[4] * T * T + a[5] * T * T * T + a[6] * T * T * T * T;
+    return c.R * Cp_on_R;
+}
+double h_h(const EbCurve& c, double T)
+{
+    double a[9]; h_coeffs(c, T, a);
+    double logT = std::log(T);
+    double h_on_RT = -a[0] / T + a[1] * logT + a[2] * T + a[3] * T * T / 2.0;
+    h_on_RT += a[4] * T * T * T / 3.0 + a[5] * T * T * T * T / 4.0 + a[6] * T * T * T * T * T / 5.0 + a[7];
+    return c.R * h_on_RT;
+}
+
+template <class T>
+int dev_alloc(Sim* s, T** p, size_t count, bool zero = true)
+{
+    void* q = nullptr;
+    CUDA_OK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    if (zero) CUDA_OK(cudaMemsetAsync(q, 0, std::max<size_t>(count, 1) * sizeof(T), s->stream));
+    s->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+template <class T>
+int dev_upload(Sim* s, T** p, const std::vector<T>& v)
+{
+    if (dev_alloc(s, p, v.size(), false)) return -100;
+    if (!v.empty()) CUDA_OK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+// Is the block uniform-Cartesian?  All face frames of a direction identical and axis-aligned
+// (signed permutation), all lengths / areas / volumes identical bit for bit.  If so, fill the
+// constants of the descriptor.
+bool detect_cartesian(const Sim* s, const Block* b, EbBlockDesc& D)
+{
+    if (s->cfg.axisymmetric) return false;
+    if (s->cfg.reserved_i[0]) return false;        // testing knob: force the general-metric path
+    const int dims = s->cfg.dimensions;
+    const int n[3] = { b->nic, b->njc, b->nkc };
+    // volumes
+    const double v0 = b->vol[b->cidx(0, 0, 0)];
+    for (int k = 0; k < n[2]; ++k) for (int j = 0; j < n[1]; ++j) for (int i = 0; i < n[0]; ++i)
+        if (b->vol[b->cidx(i, j, k)] != v0) return false;
+    D.vol = v0; D.vol_inv = 1.0 / v0; D.areaxy = (dims == 2) ? b->areaxy[b->cidx(0, 0, 0)] : 0.0;
+    for (int d = 0; d < 3; ++d) { D.len[d] = 1.0; D.area[d] = 0.0; }
+    for (int d = 0; d < dims; ++d) {
+        // lengths: interior cells plus the two ghost layers either side along d
+        int lo[3] = { 0, 0, 0 }, hi[3] = { n[0], n[1], n[2] };
+        lo[d] = -EB_NG; hi[d] = n[d] + EB_NG;
+        const double l0 = b->len[d][b->cidx(0, 0, 0)];
+        for (int k = lo[2]; k < hi[2]; ++k) for (int j = lo[1]; j < hi[1]; ++j) for (int i = lo[0]; i < hi[0]; ++i)
+            if (b->len[d][b->cidx(i, j, k)] != l0) return false;
+        D.len[d] = l0;
+        // faces: index range [0, n[d]] along d
+        int fhi[3] = { n[0], n[1], n[2] }; fhi[d] = n[d] + 1;
+        double f0[10];
+        const long long c0 = b->cidx(0, 0, 0);
+        for (int m = 0; m < 10; ++m) f0[m] = b->face[d][(long long)m * b->ncp + c0];
+        for (int k = 0; k < fhi[2]; ++k) for (int j = 0; j < fhi[1]; ++j) for (int i = 0; i < fhi[0]; ++i) {
+            const long long c = b->cidx(i, j, k);
+            for (int m = 0; m < 10; ++m) if (b->face[d][(long long)m * b->ncp + c] != f0[m]) return false;
+        }
+        // axis aligned?
+        for (int v = 0; v < 3; ++v) {
+            int nz = 0, which = -1;
+            for (int m = 0; m < 3; ++m) {
+                double x = f0[3 * v + m];
+                if (x != 0.0) { ++nz; which = m; if (std::fabs(x) != 1.0) return false; }
+            }
+            if (nz != 1) return false;
+            D.fr[d].perm[v] = which;
+            D.fr[d].neg[v] = f0[3 * v + which] < 0.0 ? 1 : 0;
+        }
+        if (D.fr[d].perm[0] == D.fr[d].perm[1] || D.fr[d].perm[0] == D.fr[d].perm[2] || D.fr[d].perm[1] == D.fr[d].perm[2]) return false;
+        for (int m = 0; m < 3; ++m) D.nvec[d][m] = f0[m];
+        D.area[d] = f0[9];
+        // l2r2_prepare on four equal lengths (onedinterp.d:338-354)
+        EbWeights& w = D.w[d];
+        const double l = l0;
+        w.lenL0 = l; w.lenR0 = l;
+        w.aL0 = 0.5 * l / (l + 2.0 * l + l);
+        w.aR0 = 0.5 * l / (l + 2.0 * l + l);
+        w.two_over_L0L1 = 2.0 / (l + l); w.two_over_R0L0 = 2.0 / (l + l); w.two_over_R1R0 = 2.0 / (l + l);
+        w.two_L0_plus_L1 = (2.0 * l + l); w.two_R0_plus_R1 = (2.0 * l + l);
+    }
+    if (dims == 2) {
+        D.fr[2].perm[0] = 2; D.fr[2].perm[1] = 0; D.fr[2].perm[2] = 1; D.fr[2].neg[0] = D.fr[2].neg[1] = D.fr[2].neg[2] = 0;
+        D.nvec[2][0] = 0; D.nvec[2][1] = 0; D.nvec[2][2] = 1; D.w[2] = D.w[0];
+    }
+    return true;
+}
+
+// full_face_copy.d:704-870 (2D) and :958-1014 (3D, orientation 0): interior cell (i,j,k) of `ot`
+// that feeds ghost layer `layer` behind the boundary-face cell (t1,t2) of face `face` of a block.
+int full_face_source(const Sim* s, int face, const Block* ot, int oface, int t1, int t2, int layer, int ijk[3])
+{
+    if (!s->threeD) {
+        const int t = t1;
+        const bool grpA = (face == EB200_NORTH || face == EB200_WEST);
+        const bool grpB = (oface == EB200_NORTH || oface == EB200_WEST);
+        const bool rev = (grpA == grpB);
+        switch (oface) {
+        case EB200_NORTH: ijk[0] = rev ? ot->nic - t - 1 : t; ijk[1] = ot->njc - 1 - layer; break;
+        case EB200_EAST: ijk[0] = ot->nic - 1 - layer; ijk[1] = rev ? ot->njc - t - 1 : t; break;
+        case EB200_SOUTH: ijk[0] = rev ? ot->nic - t - 1 : t; ijk[1] = layer; break;
+        case EB200_WEST: ijk[0] = layer; ijk[1] = rev ? ot->njc - t - 1 : t; break;
+        default: set_err("bad face"); return -1;
+        }
+        ijk[2] = 0;
+        return 0;
+    }
+    if ((face ^ 1) != oface) { set_err("3D full-face copy: only aligned opposite faces (orientation 0) are supported"); return -1; }
+    const int d = face / 2, d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+    const int on[3] = { ot->nic, ot->njc, ot->nkc };
+    ijk[d1] = t1; ijk[d2] = t2;
+    ijk[d] = (oface & 1) ? on[d] - 1 - layer : layer;
+    return 0;
+}
+
+// Enumerate the ghost cells behind one block face in a fixed order: (t2, t1, layer).
+template <class Fn>
+void for_face_ghosts(const Sim* s, const Block* b, int face, Fn fn)
+{
+    const int d = face / 2, hi = face & 1;
+    const int n[3] = { b->nic, b->njc, b->nkc };
+    const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+    for (int a2 = 0; a2 < n[d2]; ++a2) for (int a1 = 0; a1 < n[d1]; ++a1) {
+        int idx[3]; idx[d1] = a1; idx[d2] = a2; idx[d] = hi ? n[d] : 0;
+        const long long cf = b->cidx(idx[0], idx[1], idx[2]);     // plus-side cell of the boundary face
+        const int t1 = s->threeD ? a1 : (d == 0 ? idx[1] : idx[0]);
+        for (int layer = 0; layer < EB_NG; ++layer) {
+            const long long ghost = hi ? cf + layer * b->stride[d] : cf - (1 + layer) * b->stride[d];
+            const long long mirror = hi ? cf - (1 + layer) * b->stride[d] : cf + layer * b->stride[d];
+            const long long first = hi ? cf - b->stride[d] : cf;
+            fn(t1, a2, layer, cf, ghost, mirror, first);
+        }
+    }
+}
+
+int record_flux_events(Sim* s, cudaEvent_t* e0, cudaEvent_t* e1)
+{
+    if (s->ev_used >= s->ev_pool.size()) {
+        if (s->ev_pool.size() >= 4096) { *e0 = *e1 = nullptr; return 0; }
+        cudaEvent_t a, b;
+        CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b));
+        s->ev_pool.push_back({ a, b });
+    }
+    *e0 = s->ev_pool[s->ev_used].first; *e1 = s->ev_pool[s->ev_used].second;
+    s->ev_used++;
+    return 0;
+}
+
+int drain_flux_events(Sim* s)
+{
+    for (size_t i = 0; i < s->ev_used; ++i) {
+        float ms = 0.f;
+        CUDA_OK(cudaEventSynchronize(s->ev_pool[i].second));
+        CUDA_OK(cudaEventElapsedTime(&ms, s->ev_pool[i].first, s->ev_pool[i].second));
+        s->flux_ms_acc += ms; s->flux_launches++;
+    }
+    s->ev_used = 0;
+    return 0;
+}
+
+#define MODE_CALL(s, fn, ...)                                         \
+    do {                                                              \
+        if ((s)->cfg.strict_fp) eb_strict::fn(__VA_ARGS__);           \
+        else eb_fast::fn(__VA_ARGS__);                                \
+        (s)->launches++;                                              \
+    } while (0)
+
+// Ghost cells of the buffer that holds the current state: exchange with other processes,
+// then same-GPU copies and boundary conditions (phases 02 and 03 of the reference step).
+int fill_ghost_cells(Sim* s, double* prim)
+{
+    if (!s->peers.empty()) {
+        if (!s->exchange) { set_err("blocks on other ranks are connected but no exchange callback is installed"); return -5; }
+        const int np = (int)s->peers.size();
+        std::vector<int> ranks(np);
+        std::vector<double*> sp(np), rp(np);
+        std::vector<long long> sc(np), rc(np);
+        for (int p = 0; p < np; ++p) {
+            Peer& pr = s->peers[p];
+            MODE_CALL(s, launch_pack, s->P, prim, pr.d_send_idx, (long long)pr.send_idx.size(), pr.d_send, s->stream);
+            ranks[p] = pr.rank; sp[p] = pr.d_send; rp[p] = pr.d_recv;
+            sc[p] = (long long)pr.send_idx.size() * s->P.nprim; rc[p] = (long long)pr.recv_idx.size() * s->P.nprim;
+        }
+        int rc_cb = s->exchange(s->exchange_user, np, ranks.data(), sp.data(), sc.data(), rp.data(), rc.data(), (void*)s->stream);
+        if (rc_cb != 0) { set_err("exchange callback failed (%d)", rc_cb); return -6; }
+        for (int p = 0; p < np; ++p) {
+            Peer& pr = s->peers[p];
+            MODE_CALL(s, launch_unpack, s->P, prim, pr.d_recv_idx, (long long)pr.recv_idx.size(), pr.d_recv, s->stream);
+        }
+    }
+    if (s->ncopy + s->nrefl + s->nfill > 0)
+        MODE_CALL(s, launch_ghosts, s->P, s->d_desc, s->A, prim, s->d_copy, s->ncopy, s->d_refl, s->nrefl, s->d_fill, s->nfill, s->d_params, s->stream);
+    return 0;
+}
+
+// All stages of one step, enqueued on the stream (no host synchronisation).
+int enqueue_step(Sim* s, double dt)
+{
+    const int ns = s->n_stages;
+    // the start-of-step buffer stays intact; the two others ping-pong between stages
+    const int work[2] = { (s->cur + 1) % 3, (s->cur + 2) % 3 };
+    int in_buf = s->cur;
+    for (int stage = 1; stage <= ns; ++stage) {
+        const int out_buf = work[(stage - 1) & 1];
+        double* prim_in = s->A.prim[in_buf];
+        double* prim_out = s->A.prim[out_buf];
+        int rc = fill_ghost_cells(s, prim_in);
+        if (rc) return rc;
+        EbStageArgs S;
+        memset(&S, 0, sizeof S);
+        S.prim_in = prim_in; S.prim_out = prim_out;
+        S.U0 = s->A.U[s->Ulev[0]];
+        S.U_out = (stage == ns) ? s->A.U[s->Ulev[ns]] : nullptr;
+        for (int m = 0; m < 3; ++m) S.dUdt_prev[m] = (m < stage - 1) ? s->A.dUdt[m] : nullptr;
+        S.dUdt_out = (stage < ns) ? s->A.dUdt[stage - 1] : nullptr;
+        double g[3]; stage_gammas(s->cfg.update_scheme, stage, g);
+        if (stage == 1) { S.dt_g[0] = dt * g[0]; S.dt_g[3] = dt; }
+        else { S.dt_g[0] = g[0]; S.dt_g[1] = g[1]; S.dt_g[2] = g[2]; S.dt_g[3] = dt; }
+        S.stage = stage; S.n_stages = ns; S.status = s->d_status;
+        cudaEvent_t e0, e1;
+        if (record_flux_events(s, &e0, &e1)) return -100;
+        if (e0) CUDA_OK(cudaEventRecord(e0, s->stream));
+        if (s->cfg.strict_fp) eb_strict::launch_flux_update(s->cfg.flux_calculator, s->cfg.gas_model, s->P, s->d_gas, s->d_desc, (int)s->hdesc.size(), s->ncta, s->A, S, s->which, s->stream);
+        else eb_fast::launch_flux_update(s->cfg.flux_calculator, s->cfg.gas_model, s->P, s->d_gas, s->d_desc, (int)s->hdesc.size(), s->ncta, s->A, S, s->which, s->stream);
+        s->launches += ((s->which & 1) ? 1 : 0) + ((s->which & 2) ? 1 : 0);
+        if (e1) CUDA_OK(cudaEventRecord(e1, s->stream));
+        CUDA_OK(cudaGetLastError());
+        in_buf = out_buf;
+    }
+    s->cur = in_buf;
+    return 0;
+}
+
+int read_status(Sim* s)
+{
+    CUDA_OK(cudaMemcpyAsync(s->h_status, s->d_status, 8 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int eb200_last_error(char* dest, int n)
+{
+    int len = (int)strlen(g_err);
+    if (dest && n > 0) { strncpy(dest, g_err, n - 1); dest[n - 1] = 0; }
+    return len;
+}
+
+int eb200_init(const eb200_config* cfg)
+{
+    if (!cfg) { set_err("null config"); return -1; }
+    if (cfg->dimensions != 2 && cfg->dimensions != 3) { set_err("dimensions must be 2 or 3"); return -1; }
+    if (cfg->n_species < 1 || cfg->n_species > EB_MAXSP) { set_err("bad n_species"); return -1; }
+    if (cfg->gas_model == EB200_GAS_IDEAL && cfg->n_species != 1) { set_err("ideal gas has one species"); return -1; }
+    if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT && cfg->n_species != 5) {
+        set_err("thermally perfect gas: kernels are built for 5 species (got %d)", cfg->n_species); return -1;
+    }
+    if (cfg->flux_calculator < 0 || cfg->flux_calculator > 5) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
+    if (cfg->flux_calculator == EB200_FLUX_ROE && cfg->n_species > 1) { set_err("roe with multiple species is not on this path yet"); return -1; }
+    if (!n_stages_for(cfg->update_scheme)) { set_err("unsupported update scheme %d", cfg->update_scheme); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_err("no CUDA device available: eb200 has no CPU fallback");
+        return -2;
+    }
+    CUDA_OK(cudaSetDevice(cfg->device));
+    auto s = std::make_unique<Sim>();
+    s->cfg = *cfg;
+    s->threeD = cfg->dimensions == 3; s->nfaces = s->threeD ? 6 : 4;
+    s->n_stages = n_stages_for(cfg->update_scheme);
+    memset(&s->A, 0, sizeof s->A);
+    EbParams& P = s->P; memset(&P, 0, sizeof P);
+    P.dims = cfg->dimensions; P.axisymmetric = cfg->axisymmetric; P.nsp = cfg->n_species;
+    P.iZMom = s->threeD ? 3 : -1; P.iEnergy = s->threeD ? 4 : 3;
+    P.ncq = P.iEnergy + 1; P.iSpecies = -1;
+    if (P.nsp > 1) { P.iSpecies = P.ncq; P.ncq += P.nsp; }
+    P.nprim = EB200_NPRIM_BASE + (P.nsp > 1 ? 2 * P.nsp : 0);
+    P.interpolation_order = cfg->interpolation_order; P.apply_limiter = cfg->apply_limiter;
+    P.extrema_clipping = cfg->extrema_clipping; P.local_frame = cfg->interpolate_in_local_frame;
+    P.entropy_fix = cfg->apply_entropy_fix; P.ignore_low_T = cfg->ignore_low_T_thermo_update_failure;
+    P.eps_va = cfg->epsilon_van_albada; P.M_inf = cfg->M_inf; P.max_velocity = cfg->max_velocity;
+    P.max_temp = cfg->max_temp; P.min_temp = cfg->min_temp; P.low_T = cfg->suggested_low_T_value;
+    EbGas& g = s->hgas; memset(&g, 0, sizeof g);
+    g.model = cfg->gas_model; g.nsp = cfg->n_species;
+    if (cfg->gas_model == EB200_GAS_IDEAL) {
+        g.Rgas = 8.31451 / cfg->ideal_mol_mass;              // ideal_gas.d:64-68
+        g.gamma = cfg->ideal_gamma;
+        g.Cv = g.Rgas / (g.gamma - 1.0);
+        g.Cvinv = 1.0 / g.Cv;
+        g.Cp = g.Rgas * g.gamma / (g.gamma - 1.0);
+        g.gamma_CpCv = g.Cp / g.Cv;                           // gas_model.d:205
+    } else {
+        for (int i = 0; i < g.nsp; ++i) {
+            const eb200_species& sp = cfg->species[i];
+            EbCurve& c = g.curves[i];
+            g.Rsp[i] = 8.31451 / sp.mol_mass;
+            c.R = g.Rsp[i]; c.nseg = sp.nsegments; c.nbreaks = sp.nsegments + 1;
+            if (c.nseg < 1 || c.nseg > EB_MAXSEG) { set_err("bad nsegments for species %d", i); return -1; }
+            for (int k = 0; k <= c.nseg; ++k) c.T_breaks[k] = sp.T_break_points[k];
+            for (int k = 0; k < c.nseg; ++k) c.T_blends[k] = sp.T_blend_ranges[k];
+            memcpy(c.coeffs, sp.coeffs, sizeof c.coeffs);
+            c.T_low = c.T_breaks[0]; c.T_high = c.T_breaks[c.nbreaks - 1];
+            c.Cp_low = h_Cp(c, c.T_low); c.Cp_high = h_Cp(c, c.T_high);
+            c.h_low = h_h(c, c.T_low); c.h_high = h_h(c, c.T_high);
+        }
+    }
+    CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (int l = 0; l <= s->n_stages; ++l) s->Ulev.push_back(l);
+    int h = -1;
+    for (size_t i = 0; i < g_sims.size(); ++i) if (!g_sims[i]) { h = (int)i; break; }
+    if (h < 0) { g_sims.emplace_back(); h = (int)g_sims.size() - 1; }
+    g_sims[h] = std::move(s);
+    return h;
+}
+
+int eb200_finalize(int sim)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    cudaSetDevice(s->cfg.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void* p : s->allocs) cudaFree(p);
+    for (auto& e : s->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (s->h_status) cudaFreeHost(s->h_status);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    g_sims[sim].reset();
+    return 0;
+}
+
+int eb200_block_create(int sim, int blk_id, int nic, int njc, int nkc, int owner_rank)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (s->committed) { set_err("block_create after commit"); return -1; }
+    if (!s->threeD && nkc != 1) { set_err("nkc must be 1 in 2D"); return -1; }
+    if (nic < EB_NG || njc < EB_NG || (s->threeD && nkc < EB_NG)) { set_err("Too few cells for ghost cell copies."); return -1; }
+    for (auto& b : s->blocks) if (b->id == blk_id) { set_err("block %d declared twice", blk_id); return -1; }
+    auto b = std::make_unique<Block>();
+    b->id = blk_id; b->nic = nic; b->njc = njc; b->nkc = nkc; b->owner = owner_rank;
+    b->local = (owner_rank == s->cfg.rank);
+    b->NI = nic + 2 * EB_NG; b->NJ = njc + 2 * EB_NG; b->NK = s->threeD ? nkc + 2 * EB_NG : 1;
+    b->kg = s->threeD ? EB_NG : 0;
+    b->ncp = (long long)b->NI * b->NJ * b->NK;
+    b->stride[0] = 1; b->stride[1] = b->NI; b->stride[2] = (long long)b->NI * b->NJ;
+    s->blocks.push_back(std::move(b));
+    return 0;
+}
+
+int eb200_block_set_geometry(int sim, int blk_id, const double* vol, const double* areaxy,
+                             const double* len_i, const double* len_j, const double* len_k,
+                             const double* const face[3])
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Block* b = get_blk(s, blk_id); if (!b) return -1;
+    if (!b->local) { set_err("geometry given for non-local block %d", blk_id); return -1; }
+    if (s->committed) { set_err("set_geometry after commit"); return -1; }
+    const long long n = b->ncp;
+    if (!vol || !len_i || !len_j || !face) { set_err("null geometry array"); return -1; }
+    b->vol.assign(vol, vol + n);
+    if (areaxy) b->areaxy.assign(areaxy, areaxy + n);
+    else if (s->cfg.axisymmetric) { set_err("areaxy required for axisymmetric"); return -1; }
+    else b->areaxy.assign(n, 0.0);
+    b->len[0].assign(len_i, len_i + n); b->len[1].assign(len_j, len_j + n);
+    if (s->threeD) { if (!len_k) { set_err("len_k required in 3D"); return -1; } b->len[2].assign(len_k, len_k + n); }
+    for (int d = 0; d < s->cfg.dimensions; ++d) {
+        if (!face[d]) { set_err("face geometry missing for direction %d", d); return -1; }
+        b->face[d].assign(face[d], face[d] + 10 * n);
+    }
+    b->has_geometry = true;
+    return 0;
+}
+
+int eb200_block_set_bc(int sim, int blk_id, int face, int kind, const double* params, int nparams,
+                       int other_blk, int other_face, int orientation)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Block* b = get_blk(s, blk_id); if (!b) return -1;
+    if (s->committed) { set_err("set_bc after commit"); return -1; }
+    if (face < 0 || face >= s->nfaces) { set_err("bad face %d", face); return -1; }
+    if (kind < 0 || kind > EB200_BC_EXCHANGE_FULL_FACE) { set_err("unknown bc kind %d", kind); return -1; }
+    BC& bc = b->bc[face];
+    bc.kind = kind; bc.other_blk = other_blk; bc.other_face = other_face; bc.orientation = orientation;
+    if (kind == EB200_BC_INFLOW_SUPERSONIC) {
+        if (nparams != s->P.nprim || !params) { set_err("inflow FlowState needs %d values", s->P.nprim); return -1; }
+        bc.params.assign(params, params + nparams);
+    }
+    if (kind == EB200_BC_EXCHANGE_FULL_FACE) {
+        if (s->threeD && orientation != 0) { set_err("only orientation 0 is supported in 3D"); return -1; }
+        if (other_face < 0 || other_face >= s->nfaces) { set_err("bad other_face"); return -1; }
+    }
+    return 0;
+}
+
+int eb200_set_exchange(int sim, eb200_exchange_fn fn, void* user)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    s->exchange = fn; s->exchange_user = user;
+    return 0;
+}
+
+int eb200_commit(int sim)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (s->committed) { set_err("commit called twice"); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    // 1. arena offsets
+    long long total = 0;
+    for (auto& b : s->blocks) {
+        if (!b->local) continue;
+        if (!b->has_geometry) { set_err("local block %d has no geometry", b->id); return -1; }
+        b->cell0 = total; b->local_index = (int)s->local.size();
+        total += (b->ncp + 31) / 32 * 32;
+        s->local.push_back(b.get());
+    }
+    if (s->local.empty()) { set_err("no local blocks on rank %d", s->cfg.rank); return -1; }
+    if (total >= (1LL << 31)) { set_err("too many cells on one device (%lld): indices are 32-bit", total); return -1; }
+    s->P.total = total;
+    const int nprim = s->P.nprim, ncq = s->P.ncq, ns = s->n_stages, dims = s->cfg.dimensions;
+    // 2. descriptors + Cartesian detection + tiling
+    s->hdesc.resize(s->local.size());
+    bool any_general = false, any_cart = false;
+    long long cells_total = 0;
+    for (size_t n = 0; n < s->local.size(); ++n) {
+        Block* b = s->local[n];
+        EbBlockDesc& D = s->hdesc[n]; memset(&D, 0, sizeof D);
+        D.nic = b->nic; D.njc = b->njc; D.nkc = b->nkc; D.NI = b->NI; D.NJ = b->NJ; D.NK = b->NK; D.kg = b->kg;
+        D.cell0 = b->cell0; for (int d = 0; d < 3; ++d) D.stride[d] = b->stride[d];
+        for (int f = 0; f < 6; ++f) D.bc_kind[f] = b->bc[f].kind;
+        b->cartesian = detect_cartesian(s, b, D);
+        D.cartesian = b->cartesian ? 1 : 0;
+        (b->cartesian ? any_cart : any_general) = true;
+        cells_total += (long long)b->nic * b->njc * b->nkc;
+    }
+    s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0);
+    {
+        // k-chunking (3D): enough CTAs to fill 148 SMs several times over, else whole columns
+        long long tiles_plane = 0;
+        for (size_t n = 0; n < s->local.size(); ++n) {
+            EbBlockDesc& D = s->hdesc[n];
+            D.tiles_i = (D.nic + 31) / 32; D.tiles_j = (D.njc + EB_TILE_Y - 1) / EB_TILE_Y;
+            tiles_plane += (long long)D.tiles_i * D.tiles_j;
+        }
+        const long long want = 148LL * 8;
+        long long tile0 = 0;
+        for (size_t n = 0; n < s->local.size(); ++n) {
+            EbBlockDesc& D = s->hdesc[n];
+            int chunk = D.nkc;
+            if (s->threeD && tiles_plane < want) {
+                long long nch = (want + tiles_plane - 1) / tiles_plane;
+                chunk = (int)std::max<long long>(8, (D.nkc + nch - 1) / nch);
+                chunk = std::min(chunk, D.nkc);
+            }
+            D.chunk_m = s->threeD ? chunk : 1;
+            D.tiles_m = s->threeD ? (D.nkc + chunk - 1) / chunk : 1;
+            D.tile0 = tile0;
+            tile0 += (long long)D.tiles_i * D.tiles_j * D.tiles_m;
+        }
+        s->ncta = tile0;
+    }
+    // 3. device memory
+    for (int p = 0; p < 3; ++p) if (dev_alloc(s, &s->A.prim[p], (size_t)nprim * total)) return -100;
+    for (int l = 0; l <= ns; ++l) if (dev_alloc(s, &s->A.U[l], (size_t)ncq * total)) return -100;
+    for (int l = 0; l < ns - 1; ++l) if (dev_alloc(s, &s->A.dUdt[l], (size_t)ncq * total)) return -100;   // residuals needed by later stages
+    if (any_general) {
+        if (dev_alloc(s, &s->A.vol, (size_t)total)) return -100;
+        if (s->cfg.axisymmetric) if (dev_alloc(s, &s->A.areaxy, (size_t)total)) return -100;
+        for (int d = 0; d < dims; ++d) {
+            if (dev_alloc(s, &s->A.len[d], (size_t)total)) return -100;
+            if (dev_alloc(s, &s->A.face[d], (size_t)10 * total)) return -100;
+        }
+        for (Block* b : s->local) {
+            if (b->cartesian) continue;
+            const size_t bytes = (size_t)b->ncp * sizeof(double);
+            CUDA_OK(cudaMemcpyAsync(s->A.vol + b->cell0, b->vol.data(), bytes, cudaMemcpyHostToDevice, s->stream));
+            if (s->cfg.axisymmetric) CUDA_OK(cudaMemcpyAsync(s->A.areaxy + b->cell0, b->areaxy.data(), bytes, cudaMemcpyHostToDevice, s->stream));
+            for (int d = 0; d < dims; ++d) {
+                CUDA_OK(cudaMemcpyAsync(s->A.len[d] + b->cell0, b->len[d].data(), bytes, cudaMemcpyHostToDevice, s->stream));
+                for (int m = 0; m < 10; ++m)
+                    CUDA_OK(cudaMemcpyAsync(s->A.face[d] + (long long)m * total + b->cell0, b->face[d].data() + (long long)m * b->ncp,
+                                            bytes, cudaMemcpyHostToDevice, s->stream));
+            }
+        }
+    }
+    if (dev_upload(s, &s->d_desc, s->hdesc)) return -100;
+    {
+        std::vector<EbGas> gv(1, s->hgas);
+        if (dev_upload(s, &s->d_gas, gv)) return -100;
+    }
+    if (dev_alloc(s, &s->d_status, 8)) return -100;
+    if (dev_alloc(s, &s->d_red, 2)) return -100;
+    if (dev_alloc(s, &s->d_last, 1)) return -100;
+    CUDA_OK(cudaMallocHost((void**)&s->h_status, 8 * sizeof(int)));
+    // 4. ghost-cell work lists
+    std::vector<EbCopyItem> copy; std::vector<EbReflectItem> refl; std::vector<EbFillItem> fill;
+    std::vector<double> params;
+    std::map<int, Peer> peers;
+    struct Key { int blk, face; };
+    // outgoing halo: for every face of a REMOTE block that is connected to one of my blocks,
+    // gather my interior cells in that block's ghost enumeration order.
+    std::map<int, std::vector<std::pair<std::pair<int, int>, std::vector<int>>>> send_sets, recv_sets;
+    for (Block* b : s->local) {
+        for (int f = 0; f < s->nfaces; ++f) {
+            BC& bc = b->bc[f];
+            const int d = f / 2;
+            if (bc.kind == EB200_BC_EXCHANGE_FULL_FACE) {
+                Block* ot = get_blk(s, bc.other_blk);
+                if (!ot) { set_err("block %d face %d: neighbour block %d was not declared", b->id, f, bc.other_blk); return -1; }
+                std::vector<int> recv_list, send_list;
+                int err = 0;
+                for_face_ghosts(s, b, f, [&](int t1, int t2, int layer, long long, long long ghost, long long, long long) {
+                    int ijk[3];
+                    if (full_face_source(s, f, ot, bc.other_face, t1, t2, layer, ijk)) { err = 1; return; }
+                    if (ot->local) copy.push_back({ (int)(b->cell0 + ghost), (int)(ot->cell0 + ot->cidx(ijk[0], ijk[1], ijk[2])) });
+                    else recv_list.push_back((int)(b->cell0 + ghost));
+                });
+                if (err) return -1;
+                if (!ot->local) {
+                    // what the neighbour needs from me: its ghost cells behind (ot, other_face), in ITS order
+                    for_face_ghosts(s, ot, bc.other_face, [&](int t1, int t2, int layer, long long, long long, long long, long long) {
+                        int ijk[3];
+                        if (full_face_source(s, bc.other_face, b, f, t1, t2, layer, ijk)) { err = 1; return; }
+                        send_list.push_back((int)(b->cell0 + b->cidx(ijk[0], ijk[1], ijk[2])));
+                    });
+                    if (err) return -1;
+                    recv_sets[ot->owner].push_back({ { b->id, f }, recv_list });
+                    send_sets[ot->owner].push_back({ { ot->id, bc.other_face }, send_list });
+                }
+            } else if (bc.kind == EB200_BC_WALL_WITH_SLIP) {
+                for_face_ghosts(s, b, f, [&](int, int, int, long long cf, long long ghost, long long mirror, long long) {
+                    refl.push_back({ (int)(b->cell0 + ghost), (int)(b->cell0 + mirror), (int)(b->cell0 + cf), b->local_index * 4 + d });
+                });
+            } else if (bc.kind == EB200_BC_INFLOW_SUPERSONIC) {
+                bc.param_index = (int)(params.size() / nprim);
+                params.insert(params.end(), bc.params.begin(), bc.params.end());
+                for_face_ghosts(s, b, f, [&](int, int, int, long long, long long ghost, long long, long long) {
+                    fill.push_back({ (int)(b->cell0 + ghost), bc.param_index });
+                });
+            } else {   // zero-order extrapolation (both outflow kinds)
+                for_face_ghosts(s, b, f, [&](int, int, int, long long, long long ghost, long long, long long first) {
+                    copy.push_back({ (int)(b->cell0 + ghost), (int)(b->cell0 + first) });
+                });
+            }
+        }
+    }
+    s->ncopy = (long long)copy.size(); s->nrefl = (long long)refl.size(); s->nfill = (long long)fill.size();
+    if (dev_upload(s, &s->d_copy, copy)) return -100;
+    if (dev_upload(s, &s->d_refl, refl)) return -100;
+    if (dev_upload(s, &s->d_fill, fill)) return -100;
+    if (dev_upload(s, &s->d_params, params)) return -100;
+    // peers: both sides order their sets by (receiving block id, receiving face)
+    for (auto& kv : recv_sets) {
+        Peer p; p.rank = kv.first;
+        auto rs = kv.second; auto ss = send_sets[kv.first];
+        std::sort(rs.begin(), rs.end(), [](auto& a, auto& b) { return a.first < b.first; });
+        std::sort(ss.begin(), ss.end(), [](auto& a, auto& b) { return a.first < b.first; });
+        for (auto& e : rs) p.recv_idx.insert(p.recv_idx.end(), e.second.begin(), e.second.end());
+        for (auto& e : ss) p.send_idx.insert(p.send_idx.end(), e.second.begin(), e.second.end());
+        if (dev_upload(s, &p.d_send_idx, p.send_idx)) return -100;
+        if (dev_upload(s, &p.d_recv_idx, p.recv_idx)) return -100;
+        if (dev_alloc(s, &p.d_send, p.send_idx.size() * (size_t)nprim)) return -100;
+        if (dev_alloc(s, &p.d_recv, p.recv_idx.size() * (size_t)nprim)) return -100;
+        s->peers.push_back(std::move(p));
+    }
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    // host geometry copies are no longer needed
+    for (Block* b : s->local) {
+        std::vector<double>().swap(b->vol); std::vector<double>().swap(b->areaxy);
+        for (int d = 0; d < 3; ++d) { std::vector<double>().swap(b->len[d]); std::vector<double>().swap(b->face[d]); }
+    }
+    s->committed = true;
+    (void)cells_total;
+    return 0;
+}
+
+int eb200_upload_flow(int sim, int blk_id, const double* const* prims, int nprims)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Block* b = get_blk(s, blk_id); if (!b) return -1;
+    if (!s->committed || !b->local) { set_err("upload_flow needs a committed local block"); return -1; }
+    if (nprims != s->P.nprim) { set_err("expected %d primitive arrays", s->P.nprim); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    const size_t bytes = (size_t)b->ncp * sizeof(double);
+    double* prim = s->A.prim[s->cur];
+    for (int v = 0; v < nprims; ++v)
+        CUDA_OK(cudaMemcpyAsync(prim + (long long)v * s->P.total + b->cell0, prims[v], bytes, cudaMemcpyHostToDevice, s->stream));
+    CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
+    MODE_CALL(s, launch_decode, s->P, s->cfg.gas_model, s->d_gas, s->hdesc[b->local_index], prim, prim, s->A.U[s->Ulev[0]], 1, s->d_status, s->stream);
+    CUDA_OK(cudaGetLastError());
+    if (read_status(s)) return -100;
+    if (s->h_status[0]) { set_err("decode_conserved failed at upload, block %d", blk_id); return -1; }
+    return 0;
+}
+
+int eb200_download_flow(int sim, int blk_id, double* const* prims, int nprims)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Block* b = get_blk(s, blk_id); if (!b) return -1;
+    if (!s->committed || !b->local) { set_err("download_flow needs a committed local block"); return -1; }
+    if (nprims != s->P.nprim) { set_err("expected %d primitive arrays", s->P.nprim); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    const size_t bytes = (size_t)b->ncp * sizeof(double);
+    const double* prim = s->A.prim[s->cur];
+    for (int v = 0; v < nprims; ++v)
+        CUDA_OK(cudaMemcpyAsync(prims[v], prim + (long long)v * s->P.total + b->cell0, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int eb200_download_conserved(int sim, int blk_id, double* const* U, int ncq)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Block* b = get_blk(s, blk_id); if (!b) return -1;
+    if (!s->committed || !b->local) { set_err("download_conserved needs a committed local block"); return -1; }
+    if (ncq != s->P.ncq) { set_err("expected %d conserved arrays", s->P.ncq); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    const size_t bytes = (size_t)b->ncp * sizeof(double);
+    const double* Ud = s->A.U[s->Ulev[0]];
+    for (int q = 0; q < ncq; ++q)
+        CUDA_OK(cudaMemcpyAsync(U[q], Ud + (long long)q * s->P.total + b->cell0, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int eb200_compute_dt(int sim, double dt_current, double cfl_value, int check_cfl, double out[3])
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (!s->committed) { set_err("not committed"); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    double cfl_allow;
+    switch (s->n_stages) { case 1: cfl_allow = 0.9; break; case 2: cfl_allow = 1.2; break; case 3: cfl_allow = 1.6; break; default: cfl_allow = 0.9; }
+    const double cfl_adjust = 0.5;
+    double dt_allow_g = 1.7976931348623157e308, cfl_max_g = 0.0;
+    const unsigned long long init[2] = { 0x7ff0000000000000ULL, 0ULL };
+    for (Block* b : s->local) {
+        CUDA_OK(cudaMemcpyAsync(s->d_red, init, sizeof init, cudaMemcpyHostToDevice, s->stream));
+        MODE_CALL(s, launch_signal, s->P, s->hdesc[b->local_index], s->A, s->A.prim[s->cur], dt_current, cfl_value, s->d_red, s->d_last, s->stream);
+        CUDA_OK(cudaGetLastError());
+        unsigned long long red[2]; double last_signal;
+        CUDA_OK(cudaMemcpyAsync(red, s->d_red, sizeof red, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_OK(cudaMemcpyAsync(&last_signal, s->d_last, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        double dt_allow, cfl_max;
+        memcpy(&dt_allow, &red[0], 8); memcpy(&cfl_max, &red[1], 8);
+        if (check_cfl && (cfl_max < 0.0 || cfl_max > cfl_allow)) {        // fluidblock.d:1072-1082
+            cfl_max = cfl_adjust * cfl_allow;
+            dt_allow = cfl_max / last_signal;
+        }
+        dt_allow_g = std::min(dt_allow_g, dt_allow);
+        cfl_max_g = std::max(cfl_max_g, cfl_max);
+    }
+    out[0] = dt_allow_g; out[1] = cfl_max_g; out[2] = 0.0;
+    return 0;
+}
+
+static int finish_steps(Sim* s, int cur0, int* n_bad_cells, bool can_restore)
+{
+    if (read_status(s)) return -100;
+    const int ns = s->n_stages;
+    int bad = s->h_status[ns];
+    int worst = 0;
+    for (int st = 1; st <= ns; ++st) worst = std::max(worst, s->h_status[st]);
+    if (n_bad_cells) *n_bad_cells = bad;
+    if (s->h_status[0] != 0) {
+        if (!can_restore) { set_err("a cell could not be decoded during run_steps"); return -3; }
+        // U[0] and the start-of-step FlowStates (buffer cur0) were never written: just point back
+        s->cur = cur0;
+        return 1;
+    }
+    if (worst > s->cfg.max_invalid_cells) {
+        set_err("Too many bad cells during explicit gasdynamic update (%d).", worst);
+        return -2;
+    }
+    return 0;
+}
+
+int eb200_step(int sim, double t0, double dt, int* n_bad_cells)
+{
+    (void)t0;
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (!s->committed) { set_err("not committed"); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
+    const int cur0 = s->cur;
+    int rc = enqueue_step(s, dt);
+    if (rc) return rc;
+    rc = finish_steps(s, cur0, n_bad_cells, true);
+    if (rc == 0) std::swap(s->Ulev[0], s->Ulev[s->n_stages]);     // :1557-1561 swap(U[0], U[end])
+    if (s->ev_used > 2048) drain_flux_events(s);
+    return rc;
+}
+
+int eb200_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells)
+{
+    (void)t0;
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (!s->committed) { set_err("not committed"); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
+    for (int n = 0; n < nsteps; ++n) {
+        int rc = enqueue_step(s, dt);
+        if (rc) return rc;
+        std::swap(s->Ulev[0], s->Ulev[s->n_stages]);
+        if (s->ev_used > 2048) drain_flux_events(s);
+    }
+    return finish_steps(s, s->cur, n_bad_cells, false);
+}
+
+long long eb200_kernel_launches(int sim)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    return s->launches;
+}
+
+int eb200_flux_kernel_time(int sim, int reset, double* ms, long long* launches)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    if (drain_flux_events(s)) return -100;
+    if (ms) *ms = s->flux_ms_acc;
+    if (launches) *launches = s->flux_launches;
+    if (reset) { s->flux_ms_acc = 0.0; s->flux_launches = 0; }
+    return 0;
+}
+
+// Test hook (declared in include/eb200.h): reconstruction + flux for a batch of independent faces.
+int eb200_debug_face_flux(int sim, int nfaces, const double* cells, const double* len, const double* geo,
+                          double* F, int* ok)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (nfaces <= 0) return 0;
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    const int nprim = s->P.nprim, ncq = s->P.ncq;
+    const long long total = 4LL * nfaces;
+    std::vector<double> hprim((size_t)nprim * total), hlen((size_t)total), hface((size_t)10 * total, 0.0);
+    for (int n = 0; n < nfaces; ++n) {
+        for (int m = 0; m < 4; ++m) {
+            for (int v = 0; v < nprim; ++v) hprim[(size_t)v * total + 4 * n + m] = cells[((size_t)n * 4 + m) * nprim + v];
+            hlen[4 * n + m] = len[(size_t)n * 4 + m];
+        }
+        for (int g = 0; g < 10; ++g) hface[(size_t)g * total + 4 * n + 2] = geo[(size_t)n * 10 + g];
+    }
+    double *dprim = nullptr, *dlen = nullptr, *dface = nullptr, *dF = nullptr; int* dok = nullptr;
+    CUDA_OK(cudaMalloc(&dprim, hprim.size() * 8)); CUDA_OK(cudaMalloc(&dlen, hlen.size() * 8));
+    CUDA_OK(cudaMalloc(&dface, hface.size() * 8)); CUDA_OK(cudaMalloc(&dF, (size_t)nfaces * ncq * 8));
+    CUDA_OK(cudaMalloc(&dok, (size_t)nfaces * sizeof(int)));
+    CUDA_OK(cudaMemcpy(dprim, hprim.data(), hprim.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(dlen, hlen.data(), hlen.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(dface, hface.data(), hface.size() * 8, cudaMemcpyHostToDevice));
+    EbParams P = s->P; P.total = total;
+    EbArena A; memset(&A, 0, sizeof A);
+    A.len[0] = dlen; A.face[0] = dface;
+    EbGas* dgas = s->d_gas;
+    if (!dgas) {     // before commit: upload the gas parameters on the fly
+        CUDA_OK(cudaMalloc((void**)&dgas, sizeof(EbGas)));
+        CUDA_OK(cudaMemcpy(dgas, &s->hgas, sizeof(EbGas), cudaMemcpyHostToDevice));
+    }
+    if (s->cfg.strict_fp) eb_strict::launch_face_debug(s->cfg.flux_calculator, s->cfg.gas_model, P, dgas, A, dprim, nfaces, dF, dok, s->stream);
+    else eb_fast::launch_face_debug(s->cfg.flux_calculator, s->cfg.gas_model, P, dgas, A, dprim, nfaces, dF, dok, s->stream);
+    s->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    CUDA_OK(cudaMemcpy(F, dF, (size_t)nfaces * ncq * 8, cudaMemcpyDeviceToHost));
+    if (ok) CUDA_OK(cudaMemcpy(ok, dok, (size_t)nfaces * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dprim); cudaFree(dlen); cudaFree(dface); cudaFree(dF); cudaFree(dok);
+    if (!s->d_gas) cudaFree(dgas);
+    return 0;
+}
+
+int eb200_block_is_cartesian(int sim, int blk_id)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Block* b = get_blk(s, blk_id); if (!b) return -1;
+    if (!s->committed || !b->local) { set_err("block_is_cartesian needs a committed local block"); return -1; }
+    return b->cartesian ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// eb200_internal.h -- structures shared by the host runtime (eb200.cu) and the kernels.
+//
+// Device data layout (all FP64, structure of arrays):
+//   every per-cell field of every local block lives in one arena array of `total`
+//   doubles; block b occupies [cell0, cell0 + NI*NJ*NK) in the padded block layout of
+//   include/eb200.h (i fastest).  Field f of a group of nf fields is base + f*total.
+//   prim[3]   : FlowState variables, nprim fields each: the start-of-step state is never
+//               overwritten during a step (exact restore after a failed step), the two other
+//               buffers ping-pong between stages
+//   U[ns+1]   : conserved quantities per time level, ncq fields each
+//   dUdt[ns]  : residuals per stage
+//   geometry  : vol, areaxy, len[3], face[d][10]  (only allocated when some block is
+//               not uniform-Cartesian; Cartesian blocks carry constants in BlockDesc)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/eb200.h"
+
+#define EB_NG EB200_NGHOST
+#define EB_MAXSP EB200_MAX_SPECIES
+#define EB_MAXSEG EB200_MAX_SEGMENTS
+
+// l2r2_prepare() results (reference src/eilmer/onedinterp.d:338-354)
+struct EbWeights {
+    double aL0, aR0, lenL0, lenR0;
+    double two_over_L0L1, two_over_R0L0, two_over_R1R0;
+    double two_L0_plus_L1, two_R0_plus_R1;
+};
+
+// Per-direction frame of an axis-aligned face: local (x,y,z) = sgn[m]*v[perm[m]]
+struct EbAxisFrame {
+    int perm[3];
+    int neg[3];   // 1: negate
+};
+
+struct EbBlockDesc {
+    int nic, njc, nkc;
+    int NI, NJ, NK, kg;
+    int cartesian;
+    int bc_kind[6];
+    long long cell0;          // offset into the arena
+    long long stride[3];
+    // tiling of the fused flux kernel
+    int tiles_i, tiles_j, tiles_m, chunk_m;
+    long long tile0;          // first CTA index of this block
+    // uniform-Cartesian constants
+    double vol, vol_inv, areaxy;
+    double len[3], area[3];
+    EbWeights w[3];
+    EbAxisFrame fr[3];
+    double nvec[3][3];        // face normal per direction (exact +-1/0), used by flux BCs and CFL
+};
+
+struct EbCurve {             // reference src/gas/thermo/cea_thermo_curves.d
+    double R;
+    int nseg, nbreaks;
+    double T_breaks[EB_MAXSEG + 1], T_blends[EB_MAXSEG];
+    double coeffs[EB_MAXSEG][9];
+    double T_low, T_high, Cp_low, Cp_high, h_low, h_high;
+};
+
+struct EbGas {
+    int model, nsp;
+    // ideal gas (reference src/gas/ideal_gas.d:64-68)
+    double Rgas, gamma, Cv, Cvinv, Cp, gamma_CpCv;
+    double Rsp[EB_MAXSP];
+    EbCurve curves[EB_MAXSP];
+};
+
+struct EbParams {            // passed by value to kernels (kept small)
+    int dims, axisymmetric, nsp, ncq, nprim;
+    int interpolation_order, apply_limiter, extrema_clipping, local_frame, entropy_fix;
+    int ignore_low_T;
+    int iZMom, iEnergy, iSpecies;
+    double eps_va, M_inf, max_velocity, max_temp, min_temp, low_T;
+    long long total;          // arena length (field stride)
+};
+
+struct EbArena {             // device pointers
+    double* prim[3];          // [cur] = state at the start of the step (kept intact), the other two ping-pong
+    double* U[5];
+    double* dUdt[4];
+    double* vol; double* areaxy; double* len[3]; double* face[3];
+};
+
+struct EbStageArgs {
+    const double* prim_in; double* prim_out;
+    const double* U0; double* U_out;       // U_out: only written in the final stage (else nullptr)
+    const double* dUdt_prev[3];            // residuals of earlier stages (nullptr when unused)
+    double* dUdt_out;                      // nullptr when no later stage needs it
+    double dt_g[4];                        // stage 1: dt*g0 ; stage>1: g[0..2] and dt in [3]
+    int stage, n_stages;
+    int* status;                           // [0] step-failed flag, [1..4] invalid-cell count per stage
+};
+
+// ghost-cell work lists (indices into the arena)
+struct EbCopyItem { int dst, src; };
+struct EbReflectItem { int dst, src, fidx, meta; };   // meta = blk*4 + dir
+struct EbFillItem { int dst, param; };
+
+// launchers implemented once per arithmetic mode (namespaces eb_strict / eb_fast)
+// `which`: bit 0 = launch the uniform-Cartesian kernel, bit 1 = the general-metric kernel
+#define EB_DECLARE_LAUNCHERS(ns)                                                                         \
+    namespace ns {                                                                                       \
+    void launch_flux_update(int flux_calc, int gas_model, const EbParams& P, const EbGas* gas,           \
+                            const EbBlockDesc* desc, int nblocks, long long ncta, const EbArena& A,      \
+                            const EbStageArgs& S, int which, cudaStream_t st);                           \
+    void launch_face_debug(int flux_calc, int gas_model, const EbParams& P, const EbGas* gas,            \
+                           const EbArena& A, const double* prim, int nfaces, double* Fout, int* ok_out,  \
+                           cudaStream_t st);                                                             \
+    void launch_decode(const EbParams& P, int gas_model, const EbGas* gas, const EbBlockDesc& hdesc,     \
+                       const double* prim_in, double* prim_out, double* U, int do_encode, int* status,   \
+                       cudaStream_t st);                                                                 \
+    void launch_signal(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A, const double* prim, \
+                       double dt_current, double cfl_value, unsigned long long* red, double* last_signal, \
+                       cudaStream_t st);                                                                 \
+    void launch_ghosts(const EbParams& P, const EbBlockDesc* desc, const EbArena& A, double* prim,       \
+                       const EbCopyItem* copy, long long ncopy, const EbReflectItem* refl,               \
+                       long long nrefl, const EbFillItem* fill, long long nfill, const double* params,   \
+                       cudaStream_t st);                                                                 \
+    void launch_pack(const EbParams& P, const double* prim, const int* idx, long long n, double* buf,    \
+                     cudaStream_t st);                                                                   \
+    void launch_unpack(const EbParams& P, double* prim, const int* idx, long long n, const double* buf,  \
+                       cudaStream_t st);                                                                 \
+    }
+
+EB_DECLARE_LAUNCHERS(eb_strict)
+EB_DECLARE_LAUNCHERS(eb_fast)

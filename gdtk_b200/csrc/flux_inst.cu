@@ -1,0 +1,28 @@
+// flux_inst.cu -- instantiates the fused flux+update kernel for ONE flux calculator
+// (-DEB_FLUX=0..5, enum eb200_flux_calculator) in ONE arithmetic mode (-DEB_NS=...).
+#ifndef EB_FLUX
+#error "EB_FLUX must be defined"
+#endif
+#ifdef EB_NO_TPG
+#define EB_FLUX_HAS_TPG 0
+#else
+#define EB_FLUX_HAS_TPG (EB_FLUX != 5)   /* roe with several species is not on this path */
+#endif
+#include "flux_kernel.cuh"
+
+#define EB_CAT2(a, b) a##b
+#define EB_CAT(a, b) EB_CAT2(a, b)
+
+namespace EB_NS {
+void EB_CAT(launch_flux_update_k, EB_FLUX)(const EbParams& P, int gas_model, const EbGas* gas, const EbBlockDesc* desc,
+                                          int nblocks, long long ncta, const EbArena& A, const EbStageArgs& S,
+                                          int tile_y, int which, cudaStream_t st)
+{
+    launch_flux_update_impl<EB_FLUX>(P, gas_model, gas, desc, nblocks, ncta, A, S, tile_y, which, st);
+}
+void EB_CAT(launch_face_debug_k, EB_FLUX)(const EbParams& P, int gas_model, const EbGas* gas, const EbArena& A,
+                                         const double* prim, int nfaces, double* Fout, int* ok_out, cudaStream_t st)
+{
+    launch_face_debug_impl<EB_FLUX>(P, gas_model, gas, A, prim, nfaces, Fout, ok_out, st);
+}
+}  // namespace EB_NS

@@ -1,0 +1,263 @@
+// misc_kernels.cu -- the small kernels around the fused flux kernel: encode/decode at
+// upload, CFL signal reduction, ghost-cell fill (boundary conditions and same-GPU
+// full-face copies) and halo pack/unpack.  Compiled once per arithmetic mode
+// (-DEB_NS=eb_strict -fmad=false, -DEB_NS=eb_fast).
+#include "device_math.cuh"
+
+namespace EB_NS {
+
+// per-flux launchers live in flux_inst.cu (one object per flux calculator)
+#define EB_DECL_FLUX(k)                                                                                        \
+    void launch_flux_update_k##k(const EbParams& P, int gas_model, const EbGas* gas, const EbBlockDesc* desc,  \
+                                 int nblocks, long long ncta, const EbArena& A, const EbStageArgs& S,          \
+                                 int tile_y, int which, cudaStream_t st);
+EB_DECL_FLUX(0) EB_DECL_FLUX(1) EB_DECL_FLUX(2) EB_DECL_FLUX(3) EB_DECL_FLUX(4) EB_DECL_FLUX(5)
+#define EB_DECL_DBG(k)                                                                                         \
+    void launch_face_debug_k##k(const EbParams& P, int gas_model, const EbGas* gas, const EbArena& A,           \
+                                const double* prim, int nfaces, double* Fout, int* ok_out, cudaStream_t st);
+EB_DECL_DBG(0) EB_DECL_DBG(1) EB_DECL_DBG(2) EB_DECL_DBG(3) EB_DECL_DBG(4) EB_DECL_DBG(5)
+
+void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* gas, const EbArena& A, const double* prim,
+                       int nfaces, double* Fout, int* ok_out, cudaStream_t st)
+{
+    switch (flux_calc) {
+    case 0: launch_face_debug_k0(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 1: launch_face_debug_k1(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 2: launch_face_debug_k2(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 3: launch_face_debug_k3(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 4: launch_face_debug_k4(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 5: launch_face_debug_k5(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    }
+}
+
+void launch_flux_update(int flux_calc, int gm, const EbParams& P, const EbGas* gas, const EbBlockDesc* desc, int nblocks,
+                        long long ncta, const EbArena& A, const EbStageArgs& S, int which, cudaStream_t st)
+{
+    switch (flux_calc) {
+    case 0: launch_flux_update_k0(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
+    case 1: launch_flux_update_k1(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
+    case 2: launch_flux_update_k2(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
+    case 3: launch_flux_update_k3(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
+    case 4: launch_flux_update_k4(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
+    case 5: launch_flux_update_k5(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// encode_conserved (fvcell.d:511-583) + decode_conserved for every interior cell of one
+// block: what init_simulation does after reading the flow (simcore.d:325-334), and the
+// restore path after a failed step.
+
+template <int DIM, int GASM, int NSP>
+__global__ void decode_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc D,
+                              const double* __restrict__ prim_in, double* __restrict__ prim_out,
+                              double* __restrict__ U, int do_encode, int* status)
+{
+    typedef Layout<DIM, NSP> Lay;
+    constexpr int NCQ = Lay::NCQ;
+    const long long n = (long long)D.nic * D.njc * D.nkc;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = (int)(t % D.nic), j = (int)((t / D.nic) % D.njc), k = (int)(t / ((long long)D.nic * D.njc));
+    const long long c = D.cell0 + ((long long)(k + D.kg) * D.NJ + (j + EB_NG)) * D.NI + (i + EB_NG);
+    const long long total = P.total;
+    Prim<NSP> Q;
+    load_prim<NSP>(Q, prim_in, total, c);
+    if (DIM == 2) Q.vz = 0.0;
+    double Uc[NCQ];
+    if (do_encode) {
+        Uc[Lay::iMass] = Q.rho;
+        Uc[Lay::iXMom] = Q.rho * Q.vx; Uc[Lay::iYMom] = Q.rho * Q.vy;
+        if (DIM == 3) Uc[Lay::iZMom] = Q.rho * Q.vz;
+        double ke = 0.5 * (Q.vx * Q.vx + Q.vy * Q.vy + Q.vz * Q.vz);
+        Uc[Lay::iEnergy] = Q.rho * (Q.u + ke);
+        if (NSP > 1) {
+#pragma unroll
+            for (int s = 0; s < NSP; ++s) Uc[Lay::iSpecies + s] = Q.rho * Q.massf[s];
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) Uc[q] = U[q * total + c];
+    }
+    bool modified;
+    int rc = decode_cell<DIM, GASM, NSP>(P, gas, Uc, Q, modified);
+    if (rc) { atomicOr(&status[0], 1); return; }
+    store_prim<NSP>(Q, prim_out, total, c);
+    if (do_encode || modified) {
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) U[q * total + c] = Uc[q];
+    }
+}
+
+void launch_decode(const EbParams& P, int gas_model, const EbGas* gas, const EbBlockDesc& hdesc,
+                   const double* prim_in, double* prim_out, double* U, int do_encode, int* status, cudaStream_t st)
+{
+    const long long n = (long long)hdesc.nic * hdesc.njc * hdesc.nkc;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+#define EB_DEC(DIM, GASM, NSP) decode_kernel<DIM, GASM, NSP><<<blocks, threads, 0, st>>>(P, gas, hdesc, prim_in, prim_out, U, do_encode, status)
+    if (gas_model == EB200_GAS_IDEAL) { if (P.dims == 3) EB_DEC(3, EB200_GAS_IDEAL, 1); else EB_DEC(2, EB200_GAS_IDEAL, 1); }
+#ifndef EB_NO_TPG
+    else if (P.nsp == 5) { if (P.dims == 3) EB_DEC(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_DEC(2, EB200_GAS_THERMALLY_PERFECT, 5); }
+#endif
+#undef EB_DEC
+}
+
+// ---------------------------------------------------------------------------------------
+// FVCell.signal_frequency (fvcell.d:975-1058, structured, non-stringent, inviscid) and the
+// per-block min/max of FluidBlock.determine_time_step_size (fluidblock.d:1031-1069).
+// red[0] = min dt_local, red[1] = max cfl_local as bit patterns of non-negative doubles.
+
+template <int DIM>
+__global__ void signal_kernel(const EbParams P, const EbBlockDesc D, const EbArena A, const double* __restrict__ prim,
+                              double dt_current, double cfl_value, unsigned long long* red, double* last_signal)
+{
+    const long long n = (long long)D.nic * D.njc * D.nkc;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = P.total;
+    double dt_local = __longlong_as_double(0x7ff0000000000000LL), cfl_local = 0.0;
+    if (t < n) {
+        const int i = (int)(t % D.nic), j = (int)((t / D.nic) % D.njc), k = (int)(t / ((long long)D.nic * D.njc));
+        const long long c = D.cell0 + ((long long)(k + D.kg) * D.NJ + (j + EB_NG)) * D.NI + (i + EB_NG);
+        const double vx = ldg(prim + 5 * total + c), vy = ldg(prim + 6 * total + c);
+        const double vz = (DIM == 3) ? ldg(prim + 7 * total + c) : 0.0;
+        const double a = ldg(prim + 4 * total + c);
+        double nN[3], nE[3], nT[3] = {0.0, 0.0, 0.0}, lenI, lenJ, lenK = 1.0;
+        if (D.cartesian) {
+            for (int m = 0; m < 3; ++m) { nE[m] = D.nvec[0][m]; nN[m] = D.nvec[1][m]; nT[m] = D.nvec[2][m]; }
+            lenI = D.len[0]; lenJ = D.len[1]; lenK = D.len[2];
+        } else {
+            const long long cE = c + 1, cN = c + D.stride[1], cT = c + D.stride[2];
+            for (int m = 0; m < 3; ++m) {
+                nE[m] = ldg(A.face[0] + m * total + cE); nN[m] = ldg(A.face[1] + m * total + cN);
+                if (DIM == 3) nT[m] = ldg(A.face[2] + m * total + cT);
+            }
+            lenI = ldg(A.len[0] + c); lenJ = ldg(A.len[1] + c);
+            if (DIM == 3) lenK = ldg(A.len[2] + c);
+        }
+        double un_N = fabs(vx * nN[0] + vy * nN[1] + vz * nN[2]);
+        double un_E = fabs(vx * nE[0] + vy * nE[1] + vz * nE[2]);
+        double signal = 0.0;
+        signal = fmax(signal, (un_N + a) / lenJ);
+        signal = fmax(signal, (un_E + a) / lenI);
+        if (DIM == 3) {
+            double un_T = fabs(vx * nT[0] + vy * nT[1] + vz * nT[2]);
+            signal = fmax(signal, (un_T + a) / lenK);
+        }
+        cfl_local = dt_current * signal;
+        dt_local = cfl_value / signal;
+        if (t == n - 1) *last_signal = signal;
+        if (!(dt_local == dt_local)) dt_local = __longlong_as_double(0x7ff0000000000000LL);
+        if (!(cfl_local == cfl_local) || cfl_local < 0.0) cfl_local = 0.0;
+        if (dt_local < 0.0) dt_local = 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dt_local = fmin(dt_local, __shfl_down_sync(0xffffffffu, dt_local, o));
+        cfl_local = fmax(cfl_local, __shfl_down_sync(0xffffffffu, cfl_local, o));
+    }
+    __shared__ double s_dt[32], s_cfl[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_dt[w] = dt_local; s_cfl[w] = cfl_local; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        dt_local = (lane < nw) ? s_dt[lane] : __longlong_as_double(0x7ff0000000000000LL);
+        cfl_local = (lane < nw) ? s_cfl[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dt_local = fmin(dt_local, __shfl_down_sync(0xffffffffu, dt_local, o));
+            cfl_local = fmax(cfl_local, __shfl_down_sync(0xffffffffu, cfl_local, o));
+        }
+        if (lane == 0) {
+            atomicMin(&red[0], (unsigned long long)__double_as_longlong(dt_local));
+            atomicMax(&red[1], (unsigned long long)__double_as_longlong(cfl_local));
+        }
+    }
+}
+
+void launch_signal(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A, const double* prim,
+                   double dt_current, double cfl_value, unsigned long long* red, double* last_signal, cudaStream_t st)
+{
+    const long long n = (long long)hdesc.nic * hdesc.njc * hdesc.nkc;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    if (P.dims == 3) signal_kernel<3><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, dt_current, cfl_value, red, last_signal);
+    else signal_kernel<2><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, dt_current, cfl_value, red, last_signal);
+}
+
+// ---------------------------------------------------------------------------------------
+// Ghost cells.  copy: same-GPU full-face copies (full_face_copy.d:1891-1899) and zero-order
+// extrapolation (extrapolate_copy.d:129-145); reflect: internal_copy_then_reflect.d:111-134
+// with ghost_cell.d:33-43; fill: flow_state_copy.d:92-107.
+
+__global__ void ghost_kernel(const EbParams P, const EbBlockDesc* __restrict__ descs, const EbArena A, double* __restrict__ prim,
+                             const EbCopyItem* __restrict__ copy, long long ncopy,
+                             const EbReflectItem* __restrict__ refl, long long nrefl,
+                             const EbFillItem* __restrict__ fill, long long nfill, const double* __restrict__ params)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = P.total;
+    const int nprim = P.nprim;
+    if (t < ncopy) {
+        const EbCopyItem it = copy[t];
+        for (int v = 0; v < nprim; ++v) prim[v * total + it.dst] = prim[v * total + it.src];
+    } else if (t < ncopy + nrefl) {
+        const EbReflectItem it = refl[t - ncopy];
+        for (int v = 0; v < nprim; ++v) {
+            if (v >= 5 && v <= 7) continue;
+            prim[v * total + it.dst] = prim[v * total + it.src];
+        }
+        double x = prim[5 * total + it.src], y = prim[6 * total + it.src], z = prim[7 * total + it.src];
+        const int blk = it.meta >> 2, d = it.meta & 3;
+        const EbBlockDesc& D = descs[blk];
+        if (D.cartesian) {
+            EbAxisFrame f = D.fr[d];
+            axis_to_local(f, x, y, z); x = -x; axis_to_global(f, x, y, z);
+        } else {
+            Frame f;
+            if (P.dims == 3) { load_frame<3>(f, A.face[d], total, it.fidx); to_local<3>(f, x, y, z); x = -x; to_global<3>(f, x, y, z); }
+            else { load_frame<2>(f, A.face[d], total, it.fidx); to_local<2>(f, x, y, z); x = -x; to_global<2>(f, x, y, z); }
+        }
+        prim[5 * total + it.dst] = x; prim[6 * total + it.dst] = y; prim[7 * total + it.dst] = z;
+    } else if (t < ncopy + nrefl + nfill) {
+        const EbFillItem it = fill[t - ncopy - nrefl];
+        for (int v = 0; v < nprim; ++v) prim[v * total + it.dst] = params[(long long)it.param * nprim + v];
+    }
+}
+
+void launch_ghosts(const EbParams& P, const EbBlockDesc* desc, const EbArena& A, double* prim,
+                   const EbCopyItem* copy, long long ncopy, const EbReflectItem* refl, long long nrefl,
+                   const EbFillItem* fill, long long nfill, const double* params, cudaStream_t st)
+{
+    const long long n = ncopy + nrefl + nfill;
+    if (n == 0) return;
+    const int threads = 256;
+    ghost_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(P, desc, A, prim, copy, ncopy, refl, nrefl, fill, nfill, params);
+}
+
+// halo pack / unpack for blocks owned by other processes: buf[v*n + t]
+__global__ void pack_kernel(long long total, int nprim, const double* __restrict__ prim, const int* __restrict__ idx, long long n, double* __restrict__ buf)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long c = idx[t];
+    for (int v = 0; v < nprim; ++v) buf[v * n + t] = prim[v * total + c];
+}
+__global__ void unpack_kernel(long long total, int nprim, double* __restrict__ prim, const int* __restrict__ idx, long long n, const double* __restrict__ buf)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long c = idx[t];
+    for (int v = 0; v < nprim; ++v) prim[v * total + c] = buf[v * n + t];
+}
+void launch_pack(const EbParams& P, const double* prim, const int* idx, long long n, double* buf, cudaStream_t st)
+{
+    if (n > 0) pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, P.nprim, prim, idx, n, buf);
+}
+void launch_unpack(const EbParams& P, double* prim, const int* idx, long long n, const double* buf, cudaStream_t st)
+{
+    if (n > 0) unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, P.nprim, prim, idx, n, buf);
+}
+
+}  // namespace EB_NS

@@ -162,11 +162,9 @@ def geometry_3d(x, y, z):
     nic, njc, nkc = niv - 1, njv - 1, nkv - 1
     g = BlockGeometry(3, nic, njc, nkc)
 
-    def V(di, dj, dk, si=slice(None), sj=slice(None), sk=slice(None)):
-        def sh(s, d, n):
-            # cells: index range [0, n-1) shifted by d
-            return slice(d, n - 1 + d)
-        return [a[sh(None, dk, nkv), sh(None, dj, njv), sh(None, di, niv)] for a in P]
+    def V(di, dj, dk):
+        """Vertex (i+di, j+dj, k+dk) of every cell (i, j, k)."""
+        return [a[dk:dk + nkc, dj:dj + njc, di:di + nic] for a in P]
 
     p0, p1, p2, p3 = V(0, 0, 0), V(1, 0, 0), V(1, 1, 0), V(0, 1, 0)
     p4, p5, p6, p7 = V(0, 0, 1), V(1, 0, 1), V(1, 1, 1), V(0, 1, 1)

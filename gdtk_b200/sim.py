@@ -61,6 +61,8 @@ class Config:
         self.reacting = False
         # Not an Eilmer option: selects the FMA-free kernel build (see include/eb200.h).
         self.strict_fp = False
+        # Not an Eilmer option: testing knob, never use the uniform-Cartesian fast path.
+        self.force_general_path = False
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(f"unknown config option {k!r}")
@@ -98,6 +100,7 @@ class Config:
         c.update_scheme = _abi.UPDATE_SCHEMES[self.gasdynamic_update_scheme]
         c.max_invalid_cells = self.max_invalid_cells
         c.strict_fp = int(self.strict_fp)
+        c.reserved_i[0] = int(self.force_general_path)
         c.rank = rank
         c.device = device
         c.epsilon_van_albada = self.epsilon_van_albada
@@ -223,9 +226,8 @@ def identify_block_connections(blocks, dims, tol=1.0e-6):
                         same = _close(pa[0], pb[0], tol) and _close(pa[1], pb[1], tol)
                         rev = _close(pa[0], pb[1], tol) and _close(pa[1], pb[0], tol)
                         # which sense is admissible is fixed by the face pair (full_face_copy.d:704-870)
-                        reversed_pairs = {(fa, fb) for fa in range(4) for fb in range(4)
-                                          if (fa in (_abi.NORTH, _abi.WEST)) == (fb in (_abi.NORTH, _abi.WEST))}
-                        ok = rev if (fa, fb) in reversed_pairs else same
+                        is_rev = (fa in (_abi.NORTH, _abi.WEST)) == (fb in (_abi.NORTH, _abi.WEST))
+                        ok = rev if is_rev else same
                     else:
                         ok = (fa ^ 1) == fb and all(_close(p, q, tol) for p, q in zip(pa, pb))
                     if ok:

@@ -143,7 +143,7 @@ typedef struct eb200_config {
                                        0: fused multiply-add allowed (throughput build) */
     int rank;                       /* this process's rank (0 when single process) */
     int device;                     /* CUDA device ordinal used by this process */
-    int reserved_i[5];
+    int reserved_i[5];              /* [0] != 0: testing knob, never use the uniform-Cartesian fast path */
     double epsilon_van_albada;      /* 1e-12 */
     double M_inf;                   /* 0.01 (ausm_plus_up) */
     double max_velocity;            /* flowstate_limits: 30000 */
@@ -276,6 +276,16 @@ int eb200_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells)
 /* 1 if the block uses the uniform-Cartesian fast path (metrics folded into
  * per-block constants), 0 for the general-metric path, < 0 on error. */
 int eb200_block_is_cartesian(int sim, int blk_id);
+
+/* Test hook: reconstruction (onedinterp.d:751-988) + interface flux (fluxcalc.d:54-184) of
+ * `nfaces` independent faces through the general-metric device code.
+ *   cells[nfaces][4][nprim] : FlowStates of L1, L0, R0, R1 (EB200_PRIM order)
+ *   len[nfaces][4]          : cell lengths along the stencil
+ *   geo[nfaces][10]         : n t1 t2 area
+ *   F[nfaces][ncq]          : flux per unit area, global frame;  ok[nfaces] (may be NULL): 0 where
+ *                             the reference would throw. */
+int eb200_debug_face_flux(int sim, int nfaces, const double* cells, const double* len, const double* geo,
+                          double* F, int* ok);
 
 #ifdef __cplusplus
 }

@@ -1628,6 +1628,19 @@ int orc_cea_eval(int sim, int isp, int what, double T, double* out)
     return -1;
 }
 
+int orc_face_flux(int sim, const double* cells, const double* len, const double* geo, double* F, double* lr);
+
+/* Same signature as eb200_debug_face_flux: a batch of independent faces. */
+int orc_debug_face_flux(int sim, int nfaces, const double* cells, const double* len, const double* geo, double* F, int* ok)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    for (int n = 0; n < nfaces; ++n) {
+        int rc = orc_face_flux(sim, cells + (long)n * 4 * s->nprim, len + 4L * n, geo + 10L * n, F + (long)n * s->ncq, NULL);
+        if (ok) ok[n] = (rc == 0);
+    }
+    return 0;
+}
+
 /* One face: cells[4][nprim] (L1,L0,R0,R1 in EB200_PRIM order), len[4], geo[10] -> F[ncq] (global frame),
  * and the reconstructed Lft/Rght (nprim each, global-frame velocities) in lr[2*nprim]. */
 int orc_face_flux(int sim, const double* cells, const double* len, const double* geo, double* F, double* lr)

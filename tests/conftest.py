@@ -42,6 +42,9 @@ def oracle():
     lib.face_flux = lib.cdll.orc_face_flux
     lib.face_flux.restype = C.c_int
     lib.face_flux.argtypes = [C.c_int, _abi.DP, _abi.DP, _abi.DP, _abi.DP, _abi.DP]
+    lib.debug_face_flux = lib.cdll.orc_debug_face_flux
+    lib.debug_face_flux.restype = C.c_int
+    lib.debug_face_flux.argtypes = [C.c_int, C.c_int, _abi.DP, _abi.DP, _abi.DP, _abi.DP, C.POINTER(C.c_int)]
     lib.set_option = lib.cdll.orc_set_option
     lib.set_option.restype = C.c_int
     lib.set_option.argtypes = [C.c_int, C.c_char_p, C.c_int]
