@@ -109,6 +109,7 @@ SIGNATURES = {
     "flux_kernel_time": (C.c_int, [C.c_int, C.c_int, DP, C.POINTER(C.c_longlong)]),
     "run_steps": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int)]),
     "block_is_cartesian": (C.c_int, [C.c_int, C.c_int]),
+    "cuda_stream": (C.c_void_p, [C.c_int]),
     "debug_face_flux": (C.c_int, [C.c_int, C.c_int, DP, DP, DP, DP, C.POINTER(C.c_int)]),
 }
 

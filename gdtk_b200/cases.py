@@ -80,24 +80,37 @@ def sod(dims=3, ncells=100, nj=2, nk=2, flux_calculator="ausmdv", nblocks=1, **c
     return cfg, gm, list(blocks.values())
 
 
-def _perturbed_prims(gm, geom, base, seed, amplitude=1.0e-3, noise=1.0e-6):
-    """Padded primitive arrays: base FlowState with rho and (consistently) p perturbed by
-    d(rho)/rho = 1e-3 sin(2 pi x) sin(2 pi y) sin(2 pi z) plus seeded noise 1e-6."""
-    shp = (geom.NK, geom.NJ, geom.NI)
-    vals = base.as_prims()
-    prims = [np.full(shp, v) for v in vals]
-    x, y, z = geom.pos
-    pert = amplitude * np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y) * (np.sin(2 * np.pi * z) if geom.dims == 3 else 1.0)
-    rng = np.random.default_rng(seed)
-    pert = pert + noise * (rng.random(shp) - 0.5)
-    fac = 1.0 + pert
-    prims[0] = prims[0] * fac
-    prims[2] = prims[2] * fac      # p = rho R T at unchanged T and u
-    nsp = base.nsp
-    if nsp > 1:
-        for i in range(nsp):
-            prims[8 + nsp + i] = prims[8 + nsp + i] * fac   # rho_s = massf * rho
-    return prims
+class PerturbedState:
+    """Lazy initial state of one block: base FlowState with rho (and consistently p, rho_s)
+    perturbed by d(rho)/rho = 1e-3 sin(2 pi x) sin(2 pi y) sin(2 pi z) plus seeded uniform noise
+    1e-6.  Cell centres are given analytically (origin + spacing) or read from
+    the block geometry."""
+
+    def __init__(self, base, seed, origin=None, spacing=None, amplitude=1.0e-3, noise=1.0e-6):
+        self.base, self.seed, self.origin, self.spacing = base, seed, origin, spacing
+        self.amplitude, self.noise = amplitude, noise
+
+    def padded_arrays(self, geom):
+        shp = (geom.NK, geom.NJ, geom.NI)
+        if self.origin is not None:
+            h, o = self.spacing, self.origin
+            x = ((np.arange(geom.NI) - NG + 0.5) * h[0] + o[0])[None, None, :]
+            y = ((np.arange(geom.NJ) - NG + 0.5) * h[1] + o[1])[None, :, None]
+            z = ((np.arange(geom.NK) - geom.kg + 0.5) * h[2] + o[2])[:, None, None] if geom.dims == 3 else 0.0
+        else:
+            x, y, z = geom.pos
+        pert = self.amplitude * np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y) * (np.sin(2 * np.pi * z) if geom.dims == 3 else 1.0)
+        rng = np.random.default_rng(self.seed)
+        fac = 1.0 + (pert + self.noise * (rng.random(shp) - 0.5))
+        vals = self.base.as_prims()
+        prims = [np.full(shp, v) for v in vals]
+        prims[0] = prims[0] * fac
+        prims[2] = prims[2] * fac      # p = rho R T at unchanged T and u
+        nsp = self.base.nsp
+        if nsp > 1:
+            for i in range(nsp):
+                prims[8 + nsp + i] = prims[8 + nsp + i] * fac   # rho_s = massf * rho
+        return prims
 
 
 def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True, seed=1234,
@@ -105,7 +118,7 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
     """3D ideal-air box (C3/C4): unit cube, n^3 cells in nb^3 blocks; inflow west, simple
     outflow east, slip walls elsewhere; initial state = inflow + smooth perturbation.
     sheared=True tilts the k-lines by 10 degrees (general-metric path, cf.
-    examples/eilmer/3D/simple-ramp)."""
+    examples/eilmer/3D/simple-ramp).  Uniform blocks share one geometry object."""
     gm = gmodel or ideal_air()
     cfg = Config(dimensions=3, flux_calculator=flux_calculator, max_step=10, max_time=1.0,
                  dt_init=1.0e-3, cfl_value=0.5)
@@ -118,6 +131,7 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
     h = 1.0 / n
     blocks = {}
     bid = 0
+    shared = None
     for ib in range(nb):
         for jb in range(nb):
             for kb in range(nb):
@@ -127,16 +141,13 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
                     if sheared:
                         X = X + math.tan(math.radians(10.0)) * Z
                     geom = geometry_3d(X, Y, Z)
+                    init = PerturbedState(inflow, seed + bid)
                 else:
-                    geom = uniform_box_geometry(3, m, m, m, h, h, h)
-                    ii = (np.arange(geom.NI) - NG + 0.5) * h + x0
-                    jj = (np.arange(geom.NJ) - NG + 0.5) * h + y0
-                    kk = (np.arange(geom.NK) - NG + 0.5) * h + z0
-                    geom.pos[0][...] = ii[None, None, :]
-                    geom.pos[1][...] = jj[None, :, None]
-                    geom.pos[2][...] = kk[:, None, None]
-                prims = _perturbed_prims(gm, geom, inflow, seed + bid)
-                blk = FluidBlock(geom, prims, id=bid)
+                    if shared is None:
+                        shared = uniform_box_geometry(3, m, m, m, h, h, h)
+                    geom = shared
+                    init = PerturbedState(inflow, seed + bid, origin=(x0, y0, z0), spacing=(h, h, h))
+                blk = FluidBlock(geom, init, id=bid)
                 blocks[(ib, jb, kb)] = blk
                 bid += 1
     connect_block_array(blocks, 3)
@@ -145,6 +156,7 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
             blk.bcList["west"] = InFlowBC_Supersonic(inflow)
         if ib == nb - 1:
             blk.bcList["east"] = OutFlowBC_Simple()
+    cfg.block_index = {blk.id: key for key, blk in blocks.items()}
     return cfg, gm, list(blocks.values())
 
 
@@ -178,10 +190,6 @@ def ffs(nx=384, ny=128, flux_calculator="ausmdv", uniform_fast=True, **cfg_kw):
     for bid, (i0, i1, j0, j1) in enumerate(specs):
         if uniform_fast:
             geom = uniform_box_geometry(2, i1 - i0, j1 - j0, 1, dx, dy)
-            ii = (np.arange(geom.NI) - NG + 0.5 + i0) * dx
-            jj = (np.arange(geom.NJ) - NG + 0.5 + j0) * dy
-            geom.pos[0][...] = ii[None, None, :]
-            geom.pos[1][...] = jj[None, :, None]
         else:
             X, Y = box_grid_2d(i0 * dx, i1 * dx, j0 * dy, j1 * dy, i1 - i0, j1 - j0)
             geom = geometry_2d(X, Y)

@@ -51,6 +51,7 @@ struct Block {
     long long ncp = 0, cell0 = -1, stride[3] = {0, 0, 0};
     int local_index = -1;
     bool has_geometry = false, cartesian = false;
+    EbBlockDesc cartD;                        // constants of the uniform-Cartesian fast path
     std::vector<double> vol, areaxy, len[3], face[3];
     BC bc[6];
     long long cidx(int i, int j, int k) const { return ((long long)(k + kg) * NJ + (j + EB_NG)) * NI + (i + EB_NG); }
@@ -197,35 +198,42 @@ int dev_upload(Sim* s, T** p, const std::vector<T>& v)
 
 // Is the block uniform-Cartesian?  All face frames of a direction identical and axis-aligned
 // (signed permutation), all lengths / areas / volumes identical bit for bit.  If so, fill the
-// constants of the descriptor.
-bool detect_cartesian(const Sim* s, const Block* b, EbBlockDesc& D)
+// constants of the descriptor.  Works on the caller's arrays (padded block layout).
+bool detect_cartesian(const Sim* s, const Block* b, const double* vol, const double* areaxy,
+                      const double* const len[3], const double* const face[3], EbBlockDesc& D)
 {
     if (s->cfg.axisymmetric) return false;
     if (s->cfg.reserved_i[0]) return false;        // testing knob: force the general-metric path
     const int dims = s->cfg.dimensions;
     const int n[3] = { b->nic, b->njc, b->nkc };
-    // volumes
-    const double v0 = b->vol[b->cidx(0, 0, 0)];
-    for (int k = 0; k < n[2]; ++k) for (int j = 0; j < n[1]; ++j) for (int i = 0; i < n[0]; ++i)
-        if (b->vol[b->cidx(i, j, k)] != v0) return false;
-    D.vol = v0; D.vol_inv = 1.0 / v0; D.areaxy = (dims == 2) ? b->areaxy[b->cidx(0, 0, 0)] : 0.0;
+    const double v0 = vol[b->cidx(0, 0, 0)];
+    for (int k = 0; k < n[2]; ++k) for (int j = 0; j < n[1]; ++j) {
+        const double* row = vol + b->cidx(0, j, k);
+        for (int i = 0; i < n[0]; ++i) if (row[i] != v0) return false;
+    }
+    D.vol = v0; D.vol_inv = 1.0 / v0; D.areaxy = (dims == 2 && areaxy) ? areaxy[b->cidx(0, 0, 0)] : 0.0;
     for (int d = 0; d < 3; ++d) { D.len[d] = 1.0; D.area[d] = 0.0; }
     for (int d = 0; d < dims; ++d) {
         // lengths: interior cells plus the two ghost layers either side along d
         int lo[3] = { 0, 0, 0 }, hi[3] = { n[0], n[1], n[2] };
         lo[d] = -EB_NG; hi[d] = n[d] + EB_NG;
-        const double l0 = b->len[d][b->cidx(0, 0, 0)];
-        for (int k = lo[2]; k < hi[2]; ++k) for (int j = lo[1]; j < hi[1]; ++j) for (int i = lo[0]; i < hi[0]; ++i)
-            if (b->len[d][b->cidx(i, j, k)] != l0) return false;
+        const double l0 = len[d][b->cidx(0, 0, 0)];
+        for (int k = lo[2]; k < hi[2]; ++k) for (int j = lo[1]; j < hi[1]; ++j) {
+            const double* row = len[d] + b->cidx(0, j, k);
+            for (int i = lo[0]; i < hi[0]; ++i) if (row[i] != l0) return false;
+        }
         D.len[d] = l0;
         // faces: index range [0, n[d]] along d
         int fhi[3] = { n[0], n[1], n[2] }; fhi[d] = n[d] + 1;
         double f0[10];
         const long long c0 = b->cidx(0, 0, 0);
-        for (int m = 0; m < 10; ++m) f0[m] = b->face[d][(long long)m * b->ncp + c0];
-        for (int k = 0; k < fhi[2]; ++k) for (int j = 0; j < fhi[1]; ++j) for (int i = 0; i < fhi[0]; ++i) {
-            const long long c = b->cidx(i, j, k);
-            for (int m = 0; m < 10; ++m) if (b->face[d][(long long)m * b->ncp + c] != f0[m]) return false;
+        for (int m = 0; m < 10; ++m) f0[m] = face[d][(long long)m * b->ncp + c0];
+        for (int m = 0; m < 10; ++m) {
+            const double* fm = face[d] + (long long)m * b->ncp;
+            for (int k = 0; k < fhi[2]; ++k) for (int j = 0; j < fhi[1]; ++j) {
+                const double* row = fm + b->cidx(0, j, k);
+                for (int i = 0; i < fhi[0]; ++i) if (row[i] != f0[m]) return false;
+            }
         }
         // axis aligned?
         for (int v = 0; v < 3; ++v) {
@@ -529,15 +537,19 @@ int eb200_block_set_geometry(int sim, int blk_id, const double* vol, const doubl
     if (s->committed) { set_err("set_geometry after commit"); return -1; }
     const long long n = b->ncp;
     if (!vol || !len_i || !len_j || !face) { set_err("null geometry array"); return -1; }
-    b->vol.assign(vol, vol + n);
-    if (areaxy) b->areaxy.assign(areaxy, areaxy + n);
-    else if (s->cfg.axisymmetric) { set_err("areaxy required for axisymmetric"); return -1; }
-    else b->areaxy.assign(n, 0.0);
-    b->len[0].assign(len_i, len_i + n); b->len[1].assign(len_j, len_j + n);
-    if (s->threeD) { if (!len_k) { set_err("len_k required in 3D"); return -1; } b->len[2].assign(len_k, len_k + n); }
-    for (int d = 0; d < s->cfg.dimensions; ++d) {
+    if (!areaxy && s->cfg.axisymmetric) { set_err("areaxy required for axisymmetric"); return -1; }
+    if (s->threeD && !len_k) { set_err("len_k required in 3D"); return -1; }
+    for (int d = 0; d < s->cfg.dimensions; ++d)
         if (!face[d]) { set_err("face geometry missing for direction %d", d); return -1; }
-        b->face[d].assign(face[d], face[d] + 10 * n);
+    const double* lens[3] = { len_i, len_j, len_k };
+    memset(&b->cartD, 0, sizeof b->cartD);
+    b->cartesian = detect_cartesian(s, b, vol, areaxy, lens, face, b->cartD);
+    if (!b->cartesian) {          // the general-metric path needs the arrays on the device: keep a copy until commit
+        b->vol.assign(vol, vol + n);
+        if (areaxy) b->areaxy.assign(areaxy, areaxy + n); else b->areaxy.assign(n, 0.0);
+        b->len[0].assign(len_i, len_i + n); b->len[1].assign(len_j, len_j + n);
+        if (s->threeD) b->len[2].assign(len_k, len_k + n);
+        for (int d = 0; d < s->cfg.dimensions; ++d) b->face[d].assign(face[d], face[d] + 10 * n);
     }
     b->has_geometry = true;
     return 0;
@@ -595,11 +607,11 @@ int eb200_commit(int sim)
     long long cells_total = 0;
     for (size_t n = 0; n < s->local.size(); ++n) {
         Block* b = s->local[n];
-        EbBlockDesc& D = s->hdesc[n]; memset(&D, 0, sizeof D);
+        EbBlockDesc& D = s->hdesc[n];
+        if (b->cartesian) D = b->cartD; else memset(&D, 0, sizeof D);
         D.nic = b->nic; D.njc = b->njc; D.nkc = b->nkc; D.NI = b->NI; D.NJ = b->NJ; D.NK = b->NK; D.kg = b->kg;
         D.cell0 = b->cell0; for (int d = 0; d < 3; ++d) D.stride[d] = b->stride[d];
         for (int f = 0; f < 6; ++f) D.bc_kind[f] = b->bc[f].kind;
-        b->cartesian = detect_cartesian(s, b, D);
         D.cartesian = b->cartesian ? 1 : 0;
         (b->cartesian ? any_cart : any_general) = true;
         cells_total += (long long)b->nic * b->njc * b->nkc;
@@ -938,6 +950,12 @@ int eb200_debug_face_flux(int sim, int nfaces, const double* cells, const double
     cudaFree(dprim); cudaFree(dlen); cudaFree(dface); cudaFree(dF); cudaFree(dok);
     if (!s->d_gas) cudaFree(dgas);
     return 0;
+}
+
+void* eb200_cuda_stream(int sim)
+{
+    Sim* s = get_sim(sim); if (!s) return nullptr;
+    return (void*)s->stream;
 }
 
 int eb200_block_is_cartesian(int sim, int blk_id)

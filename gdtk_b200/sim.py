@@ -63,6 +63,7 @@ class Config:
         self.strict_fp = False
         # Not an Eilmer option: testing knob, never use the uniform-Cartesian fast path.
         self.force_general_path = False
+        self.block_index = None          # optional {block id: (ib, jb, kb)} left by the case factories
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(f"unknown config option {k!r}")
@@ -378,35 +379,51 @@ class Simulation:
         return (shp[2] - 1, shp[1] - 1, shp[0] - 1)
 
     def _copy_ghost_lengths(self, b, face, other, other_face):
+        """Ghost cells behind a connection take the neighbour's cell lengths
+        (full_face_copy.d:1576-1626), with the cell mapping of full_face_source()."""
         g, og = self._geom(b), self._geom(other)
+        if og is g:
+            return            # blocks sharing one (uniform) geometry object: nothing to change
         d, hi = face // 2, face & 1
         n = (g.nic, g.njc, g.nkc)
-        d1, d2 = (d + 1) % 3, (d + 2) % 3
-        odims = (og.nic, og.njc, og.nkc)
-        if self.dims == 2:
-            ranges = (range(n[1] if d == 0 else n[0]), range(1))
-        else:
-            ranges = (range(n[d1]), range(n[d2]))
-        off = (NG, NG, g.kg)
-        ooff = (NG, NG, og.kg)
-        for t2 in ranges[1]:
-            for t1 in ranges[0]:
-                for layer in range(NG):
-                    si, sj, sk = full_face_source(self.dims, face, odims, other_face, t1, t2, layer)
-                    idx = [0, 0, 0]
-                    if self.dims == 2:
-                        idx[1 - d] = t1
-                    else:
-                        idx[d1], idx[d2] = t1, t2
-                    idx[d] = n[d] + layer if hi else -1 - layer
-                    di, dj, dk = idx[0] + off[0], idx[1] + off[1], idx[2] + off[2]
-                    for m in range(3):
-                        g.len[m][dk, dj, di] = og.len[m][sk + ooff[2], sj + ooff[1], si + ooff[0]]
+        on = (og.nic, og.njc, og.nkc)
+        for layer in range(NG):
+            if self.dims == 3:
+                # aligned, orientation 0: in-face indices carry over unchanged
+                dst = [slice(g.kg, g.kg + g.nkc), slice(NG, NG + g.njc), slice(NG, NG + g.nic)]
+                src = [slice(og.kg, og.kg + og.nkc), slice(NG, NG + og.njc), slice(NG, NG + og.nic)]
+                off = (NG, NG, g.kg)[d]
+                ooff = (NG, NG, og.kg)[d]
+                dst[2 - d] = off + (n[d] + layer if hi else -1 - layer)
+                src[2 - d] = ooff + (on[d] - 1 - layer if (other_face & 1) else layer)
+                for m in range(3):
+                    g.len[m][tuple(dst)] = og.len[m][tuple(src)]
+            else:
+                nt = n[1] if d == 0 else n[0]
+                t = np.arange(nt)
+                rev = (face in (_abi.NORTH, _abi.WEST)) == (other_face in (_abi.NORTH, _abi.WEST))
+                tt = (on[1 - (other_face // 2)] - t - 1) if rev else t
+                if other_face // 2 == 0:     # east/west of the other block: i fixed by layer, j runs
+                    si = np.full(nt, on[0] - 1 - layer if other_face == _abi.EAST else layer)
+                    sj = tt
+                else:
+                    sj = np.full(nt, on[1] - 1 - layer if other_face == _abi.NORTH else layer)
+                    si = tt
+                if d == 0:
+                    di = np.full(nt, n[0] + layer if hi else -1 - layer)
+                    dj = t
+                else:
+                    dj = np.full(nt, n[1] + layer if hi else -1 - layer)
+                    di = t
+                for m in range(3):
+                    g.len[m][0, dj + NG, di + NG] = og.len[m][0, sj + NG, si + NG]
 
     def _initial_prims(self, b):
         g = self._geom(b)
         shp = (g.NK, g.NJ, g.NI)
         init = b.initialState
+        if hasattr(init, "padded_arrays"):        # lazy generator: arrays are made when needed and dropped
+            return [np.ascontiguousarray(a, dtype=np.float64).reshape(shp) for a in init.padded_arrays(g)]
         if isinstance(init, dict):
             names = ["rho", "u", "p", "T", "a", "velx", "vely", "velz"]
             return [np.ascontiguousarray(init[k], dtype=np.float64).reshape(shp) for k in names] + \

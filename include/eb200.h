@@ -273,6 +273,10 @@ int eb200_flux_kernel_time(int sim, int reset, double* ms, long long* launches);
  * Returns like eb200_step. */
 int eb200_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells);
 
+/* The cudaStream_t (as void*) on which the library enqueues all its work; lets the caller
+ * record CUDA events around calls and order its own transfers.  NULL on error. */
+void* eb200_cuda_stream(int sim);
+
 /* 1 if the block uses the uniform-Cartesian fast path (metrics folded into
  * per-block constants), 0 for the general-metric path, < 0 on error. */
 int eb200_block_is_cartesian(int sim, int blk_id);

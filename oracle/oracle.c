@@ -1590,6 +1590,7 @@ int orc_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells)
 
 long long orc_kernel_launches(int sim) { (void)sim; return 0; }
 int orc_flux_kernel_time(int sim, int reset, double* ms, long long* launches) { (void)sim; (void)reset; if (ms) *ms = 0; if (launches) *launches = 0; return 0; }
+void* orc_cuda_stream(int sim) { (void)sim; return NULL; }
 int orc_block_is_cartesian(int sim, int blk_id) { (void)sim; (void)blk_id; return 0; }
 
 /* ------------------------------------------------------------------------- */
