@@ -294,8 +294,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="box3d", choices=["box3d", "ffs"])
-    ap.add_argument("--n", type=int, default=512)
-    ap.add_argument("--nb", type=int, default=4)
+    ap.add_argument("--size", dest="n", type=int, default=512)
+    ap.add_argument("--blocks-per-dim", dest="nb", type=int, default=4)
     ap.add_argument("--ffs-nx", type=int, default=4096)
     ap.add_argument("--ffs-ny", type=int, default=1024)
     ap.add_argument("--flux", default="ausmdv")

@@ -114,7 +114,8 @@ SIGNATURES = {
 }
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIBRARY = os.path.join(_HERE, "csrc", "libeb200.so")
+# EB200_LIBRARY: development aid to try another build of the same CUDA library
+DEFAULT_LIBRARY = os.environ.get("EB200_LIBRARY", os.path.join(_HERE, "csrc", "libeb200.so"))
 
 
 class Library:

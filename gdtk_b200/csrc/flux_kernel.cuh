@@ -20,6 +20,9 @@
 #ifndef EB_TILE_Y
 #define EB_TILE_Y 8          // rows of cells per CTA tile (CTA = 32 x EB_TILE_Y threads)
 #endif
+#ifndef EB_MIN_CTAS
+#define EB_MIN_CTAS 1        // second argument of __launch_bounds__: resident CTAs per SM to aim for
+#endif
 
 namespace EB_NS {
 
@@ -220,7 +223,7 @@ __device__ __forceinline__ void finish_cell(const EbParams& P, const EbGas* __re
 }
 
 template <int DIM, int FLUX, int GASM, int NSP, bool CART, int TY>
-__global__ void __launch_bounds__(32 * TY)
+__global__ void __launch_bounds__(32 * TY, EB_MIN_CTAS)
 flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc* __restrict__ descs, int nblocks,
                    const EbArena A, const EbStageArgs S)
 {
