@@ -33,6 +33,37 @@ struct Layout {
 
 __device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
 
+// Division and square root.  The FMA-free build uses IEEE division / sqrt in the reference's
+// operation order.  The throughput build (EB_FAST_MATH) replaces a/b by a * rcp(b) with a
+// branch-free Newton-refined reciprocal (MUFU.RCP64H + 4 DFMA, <= 2 ulp) and lets several
+// quotients share one reciprocal; parity with the reference is then within 1e-10, not bitwise.
+#ifdef EB_FAST_MATH
+__device__ __forceinline__ double eb_rcp(double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0); r = fma(r, e, r);
+    e = fma(-b, r, 1.0); r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double eb_div(double a, double b) { return a * eb_rcp(b); }
+__device__ __forceinline__ double eb_sqrt(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    // two Newton steps on r ~ 1/sqrt(x), then s = x*r with one correction
+    double h = 0.5 * r;
+    double e = fma(-x * r, h, 0.5); r = fma(r, e, r); h = 0.5 * r;
+    e = fma(-x * r, h, 0.5); r = fma(r, e, r);
+    double sq = x * r;
+    sq = fma(fma(-sq, sq, x), 0.5 * r, sq);
+    return (x > 0.0) ? sq : ((x == 0.0) ? 0.0 : sqrt(x));
+}
+#else
+__device__ __forceinline__ double eb_div(double a, double b) { return a / b; }
+__device__ __forceinline__ double eb_sqrt(double x) { return sqrt(x); }
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Face frames
 
@@ -292,7 +323,7 @@ __device__ __forceinline__ bool sound_speed(const EbGas* __restrict__ g, Prim<NS
 {
     if (GASM == EB200_GAS_IDEAL) {          // ideal_gas.d:136-143
         if (Q.T <= 0.0) return false;
-        Q.a = sqrt(g->gamma * g->Rgas * Q.T);
+        Q.a = eb_sqrt(g->gamma * g->Rgas * Q.T);
         return true;
     } else {                                // therm_perf_gas.d:394-430, gas_model.d:205
         double Cp = 0.0, Cv = 0.0, R = 0.0;
@@ -345,8 +376,8 @@ __device__ __forceinline__ void interp_scalar(const EbWeights& w, bool limiter, 
     double delRplus = (qR1 - qR0) * w.two_over_R1R0;
     double sL = 1.0, sR = 1.0;
     if (limiter) {
-        sL = (delLminus * del + fabs(delLminus * del) + eps) / (delLminus * delLminus + del * del + eps);
-        sR = (del * delRplus + fabs(del * delRplus) + eps) / (del * del + delRplus * delRplus + eps);
+        sL = eb_div(delLminus * del + fabs(delLminus * del) + eps, delLminus * delLminus + del * del + eps);
+        sR = eb_div(del * delRplus + fabs(del * delRplus) + eps, del * del + delRplus * delRplus + eps);
     }
     qL = qL0 + sL * w.aL0 * (del * w.two_L0_plus_L1 + delLminus * w.lenR0);
     qR = qR0 - sR * w.aR0 * (delRplus * w.lenL0 + del * w.two_R0_plus_R1);
@@ -373,12 +404,12 @@ __device__ __forceinline__ void l2r2_prepare(EbWeights& w, double lenL1, double 
 // Flux calculators (local frame: x = face normal).  reference src/eilmer/fluxcalc.d
 
 #define EB_UNPACK_LR                                                                  \
-    const double rL = L.rho, pL = L.p, pLrL = pL / rL;                                \
+    const double rL = L.rho, pL = L.p, pLrL = eb_div(pL, rL);                                \
     const double uL = L.vx, vL = L.vy, wL = (DIM == 3 ? L.vz : 0.0);                  \
     const double eL = L.u, aL = L.a;                                                  \
     const double keL = 0.5 * (uL * uL + vL * vL + wL * wL);                           \
     const double HL = eL + pLrL + keL;                                                \
-    const double rR = R.rho, pR = R.p, pRrR = pR / rR;                                \
+    const double rR = R.rho, pR = R.p, pRrR = eb_div(pR, rR);                                \
     const double uR = R.vx, vR = R.vy, wR = (DIM == 3 ? R.vz : 0.0);                  \
     const double eR = R.u, aR = R.a;                                                  \
     const double keR = 0.5 * (uR * uR + vR * vR + wR * wR);                           \
@@ -390,13 +421,36 @@ __device__ __forceinline__ void flux_ausmdv(const Prim<NSP>& L, const Prim<NSP>&
 {
     typedef Layout<DIM, NSP> Lay;
     EB_UNPACK_LR
+    double am = fmax(aL, aR);
+    double duL = 0.5 * (uL + fabs(uL));
+    double duR = 0.5 * (uR - fabs(uR));
+    double pLplus, uLplus, pRminus, uRminus;
+#ifdef EB_FAST_MATH
+    // shared reciprocals: 1/(pLrL+pRrR) for both alphas, 1/am for both Mach numbers and the 1/(4 am) terms
+    const double rs = eb_rcp(pLrL + pRrR), ram = eb_rcp(am), qam = 0.25 * ram;
+    double alphaL = 2.0 * pLrL * rs;
+    double alphaR = 2.0 * pRrR * rs;
+    double ML = uL * ram;
+    double MR = uR * ram;
+    if (fabs(ML) <= 1.0) {
+        pLplus = pL * (ML + 1.0) * (ML + 1.0) * (2.0 - ML) * 0.25;
+        uLplus = alphaL * ((uL + am) * (uL + am) * qam - duL) + duL;
+    } else {
+        pLplus = (uL > 0.0) ? pL : 0.0;       // pL*duL/uL
+        uLplus = duL;
+    }
+    if (fabs(MR) <= 1.0) {
+        pRminus = pR * (MR - 1.0) * (MR - 1.0) * (2.0 + MR) * 0.25;
+        uRminus = alphaR * (-(uR - am) * (uR - am) * qam - duR) + duR;
+    } else {
+        pRminus = (uR < 0.0) ? pR : 0.0;      // pR*duR/uR
+        uRminus = duR;
+    }
+#else
     double alphaL = 2.0 * pLrL / (pLrL + pRrR);
     double alphaR = 2.0 * pRrR / (pLrL + pRrR);
-    double am = fmax(aL, aR);
     double ML = uL / am;
     double MR = uR / am;
-    double pLplus, uLplus;
-    double duL = 0.5 * (uL + fabs(uL));
     if (fabs(ML) <= 1.0) {
         pLplus = pL * (ML + 1.0) * (ML + 1.0) * (2.0 - ML) * 0.25;
         uLplus = alphaL * ((uL + am) * (uL + am) / (4.0 * am) - duL) + duL;
@@ -404,8 +458,6 @@ __device__ __forceinline__ void flux_ausmdv(const Prim<NSP>& L, const Prim<NSP>&
         pLplus = pL * duL / uL;
         uLplus = duL;
     }
-    double pRminus, uRminus;
-    double duR = 0.5 * (uR - fabs(uR));
     if (fabs(MR) <= 1.0) {
         pRminus = pR * (MR - 1.0) * (MR - 1.0) * (2.0 + MR) * 0.25;
         uRminus = alphaR * (-(uR - am) * (uR - am) / (4.0 * am) - duR) + duR;
@@ -413,10 +465,11 @@ __device__ __forceinline__ void flux_ausmdv(const Prim<NSP>& L, const Prim<NSP>&
         pRminus = pR * duR / uR;
         uRminus = duR;
     }
+#endif
     double ru_half = uLplus * rL + uRminus * rR;
     double p_half = pLplus + pRminus;
     double dp = pL - pR;
-    dp = 10.0 * fabs(dp) / fmin(pL, pR);
+    dp = eb_div(10.0 * fabs(dp), fmin(pL, pR));
     double s = 0.5 * fmin(1.0, dp);
     double ru2_AUSMV = uLplus * rL * uL + uRminus * rR * uR;
     double ru2_AUSMD = 0.5 * (ru_half * (uL + uR) - fabs(ru_half) * (uR - uL));
@@ -471,7 +524,7 @@ __device__ __forceinline__ void flux_ldfss(const Prim<NSP>& L, const Prim<NSP>& 
     EB_UNPACK_LR
     double am = 0.5 * (aL + aR);
     double ML, MR;
-    if (VARIANT == 0) { ML = uL / aL; MR = uR / aR; } else { ML = uL / am; MR = uR / am; }
+    if (VARIANT == 0) { ML = eb_div(uL, aL); MR = eb_div(uR, aR); } else { ML = eb_div(uL, am); MR = eb_div(uR, am); }
     double MpL = 0.25 * ((ML + 1.0) * (ML + 1.0));
     double MmR = -0.25 * ((MR - 1.0) * (MR - 1.0));
     double alphaL = 0.5 * (1.0 + sgn_d(ML));
@@ -482,7 +535,7 @@ __device__ __forceinline__ void flux_ldfss(const Prim<NSP>& L, const Prim<NSP>& 
     double PR = 0.25 * ((MR - 1.0) * (MR - 1.0)) * (2.0 + MR);
     double DL = alphaL * (1.0 + betaL) - betaL * PL;
     double DR = alphaR * (1.0 + betaR) - betaR * PR;
-    double sq = sqrt(0.5 * (ML * ML + MR * MR)) - 1.0;
+    double sq = eb_sqrt(0.5 * (ML * ML + MR * MR)) - 1.0;
     double Mhalf = 0.25 * betaL * betaR * (sq * sq);
     double cL, cR;                  // (a * rho * C) of each side
     if (VARIANT == 0) {
@@ -491,8 +544,8 @@ __device__ __forceinline__ void flux_ldfss(const Prim<NSP>& L, const Prim<NSP>& 
         cL = aL * rL * CL; cR = aR * rR * CR;
     } else {
         const double delta = 2.0;
-        double MhalfL = Mhalf * (1.0 - ((pL - pR) / (pL + pR) + delta * (fabs(pL - pR) / pL)));
-        double MhalfR = Mhalf * (1.0 + ((pL - pR) / (pL + pR) - delta * (fabs(pL - pR) / pR)));
+        double MhalfL = Mhalf * (1.0 - (eb_div(pL - pR, pL + pR) + delta * eb_div(fabs(pL - pR), pL)));
+        double MhalfR = Mhalf * (1.0 + (eb_div(pL - pR, pL + pR) - delta * eb_div(fabs(pL - pR), pR)));
         double CL = alphaL * (1.0 + betaL) * ML - betaL * MpL - MhalfL;
         double CR = alphaR * (1.0 + betaR) * MR - betaR * MmR + MhalfR;
         cL = am * rL * CL; cR = am * rR * CR;
@@ -519,19 +572,19 @@ __device__ __forceinline__ void flux_hanel(const Prim<NSP>& L, const Prim<NSP>& 
     EB_UNPACK_LR
     double pLplus, uLplus;
     if (fabs(uL) <= aL) {
-        uLplus = 1.0 / (4.0 * aL) * (uL + aL) * (uL + aL);
-        pLplus = pL * uLplus * (1.0 / aL * (2.0 - uL / aL));
+        uLplus = eb_div(1.0, 4.0 * aL) * (uL + aL) * (uL + aL);
+        pLplus = pL * uLplus * (eb_div(1.0, aL) * (2.0 - eb_div(uL, aL)));
     } else {
         uLplus = 0.5 * (uL + fabs(uL));
-        pLplus = pL * uLplus * (1.0 / uL);
+        pLplus = pL * uLplus * eb_div(1.0, uL);
     }
     double pRminus, uRminus;
     if (fabs(uR) <= aR) {
-        uRminus = -1.0 / (4.0 * aR) * (uR - aR) * (uR - aR);
-        pRminus = pR * uRminus * (1.0 / aR * (-2.0 - uR / aR));
+        uRminus = eb_div(-1.0, 4.0 * aR) * (uR - aR) * (uR - aR);
+        pRminus = pR * uRminus * (eb_div(1.0, aR) * (-2.0 - eb_div(uR, aR)));
     } else {
         uRminus = 0.5 * (uR - fabs(uR));
-        pRminus = pR * uRminus * (1.0 / uR);
+        pRminus = pR * uRminus * eb_div(1.0, uR);
     }
     double p_half = pLplus + pRminus;
     F[Lay::iMass] = (uLplus * rL + uRminus * rR);
@@ -559,24 +612,24 @@ __device__ __forceinline__ void flux_ausm_plus_up(const Prim<NSP>& L, const Prim
     const double rL = L.rho, pL = L.p, uL = L.vx, vL = L.vy, wL = (DIM == 3 ? L.vz : 0.0);
     const double eL = L.u, aL = L.a;
     const double keL = 0.5 * (uL * uL + vL * vL + wL * wL);
-    const double HL = eL + pL / rL + keL;
+    const double HL = eL + eb_div(pL, rL) + keL;
     const double rR = R.rho, pR = R.p, uR = R.vx, vR = R.vy, wR = (DIM == 3 ? R.vz : 0.0);
     const double eR = R.u, aR = R.a;
     const double keR = 0.5 * (uR * uR + vR * vR + wR * wR);
-    const double HR = eR + pR / rR + keR;
+    const double HR = eR + eb_div(pR, rR) + keR;
     double a_half = 0.5 * (aR + aL);
-    double ML = uL / a_half;
-    double MR = uR / a_half;
-    double MbarSq = (uL * uL + uR * uR) / (2.0 * a_half * a_half);
+    double ML = eb_div(uL, a_half);
+    double MR = eb_div(uR, a_half);
+    double MbarSq = eb_div(uL * uL + uR * uR, 2.0 * a_half * a_half);
     double M0Sq = fmin(1.0, fmax(MbarSq, M_inf * M_inf));
-    double sqM0 = sqrt(M0Sq);
+    double sqM0 = eb_sqrt(M0Sq);
     double fa = sqM0 * (2.0 - sqM0);
     double alpha = 0.1875 * (-4.0 + 5 * fa * fa);
     const double beta = 0.125;
     double M4plus_ML, P5plus_ML, M4minus_MR, P5minus_MR;
     if (fabs(ML) >= 1.0) {
         M4plus_ML = M1plus(ML);
-        P5plus_ML = (1.0 / ML) * M1plus(ML);
+        P5plus_ML = eb_div(1.0, ML) * M1plus(ML);
     } else {
         double M2p = M2plus(ML), M2m = M2minus(ML);
         M4plus_ML = M2p * (1.0 - 16.0 * beta * M2m);
@@ -584,7 +637,7 @@ __device__ __forceinline__ void flux_ausm_plus_up(const Prim<NSP>& L, const Prim
     }
     if (fabs(MR) >= 1.0) {
         M4minus_MR = M1minus(MR);
-        P5minus_MR = (1.0 / MR) * M1minus(MR);
+        P5minus_MR = eb_div(1.0, MR) * M1minus(MR);
     } else {
         double M2p = M2plus(MR), M2m = M2minus(MR);
         M4minus_MR = M2m * (1.0 + 16.0 * beta * M2p);
@@ -592,7 +645,7 @@ __device__ __forceinline__ void flux_ausm_plus_up(const Prim<NSP>& L, const Prim
     }
     const double KP = 0.25, KU = 0.75, SIGMA = 1.0;
     double r_half = 0.5 * (rL + rR);
-    double Mp = -KP / fa * fmax((1.0 - SIGMA * MbarSq), 0.0) * (pR - pL) / (r_half * a_half * a_half);
+    double Mp = eb_div(eb_div(-KP, fa) * fmax((1.0 - SIGMA * MbarSq), 0.0) * (pR - pL), r_half * a_half * a_half);
     double Pu = -KU * P5plus_ML * P5minus_MR * (rL + rR) * fa * a_half * (uR - uL);
     double M_half = M4plus_ML + M4minus_MR + Mp;
     double ru_half = a_half * M_half;
@@ -627,29 +680,29 @@ __device__ __forceinline__ void flux_roe(const Prim<NSP>& L, const Prim<NSP>& R,
     typedef Layout<DIM, NSP> Lay;
     EB_UNPACK_LR
     (void)aL; (void)aR;
-    const double sL = sqrt(rL), sR = sqrt(rR), sden = sL + sR;   // recomputed in the reference; same values
-    double ghat = (sL * gL + sR * gR) / sden;
-    double rhat = sqrt(rL * rR);
-    double uhat = (sL * uL + sR * uR) / sden;
-    double vhat = (sL * vL + sR * vR) / sden;
-    double what = (sL * wL + sR * wR) / sden;
-    double Hhat = (sL * HL + sR * HR) / sden;
-    double tkehat = (sL * 0.0 + sR * 0.0) / sden;
+    const double sL = eb_sqrt(rL), sR = eb_sqrt(rR), sden = sL + sR;   // recomputed in the reference; same values
+    double ghat = eb_div((sL * gL + sR * gR), sden);
+    double rhat = eb_sqrt(rL * rR);
+    double uhat = eb_div((sL * uL + sR * uR), sden);
+    double vhat = eb_div((sL * vL + sR * vR), sden);
+    double what = eb_div((sL * wL + sR * wR), sden);
+    double Hhat = eb_div((sL * HL + sR * HR), sden);
+    double tkehat = eb_div((sL * 0.0 + sR * 0.0), sden);
     double kehat = 0.5 * (uhat * uhat + vhat * vhat + what * what);
     double ahat2 = (ghat - 1.0) * (Hhat - kehat - tkehat);
-    double ahat = sqrt(ahat2);
+    double ahat = eb_sqrt(ahat2);
     double dr = rR - rL, dp = pR - pL, du = uR - uL, dv = vR - vL, dw = wR - wL;
     double lam0 = uhat, lam1 = uhat + ahat, lam2 = uhat - ahat;
     const double phi = 0.5;
-    double V = sqrt(uhat * uhat + vhat * vhat + what * what);
+    double V = eb_sqrt(uhat * uhat + vhat * vhat + what * what);
     double lref = phi * (V + ahat);
-    lam0 = (fabs(lam0) >= 2 * lref) ? fabs(lam0) : (lam0 * lam0) / (4 * lref) + lref;
-    lam1 = (fabs(lam1) >= 2 * lref) ? fabs(lam1) : (lam1 * lam1) / (4 * lref) + lref;
-    lam2 = (fabs(lam2) >= 2 * lref) ? fabs(lam2) : (lam2 * lam2) / (4 * lref) + lref;
+    lam0 = (fabs(lam0) >= 2 * lref) ? fabs(lam0) : eb_div(lam0 * lam0, 4 * lref) + lref;
+    lam1 = (fabs(lam1) >= 2 * lref) ? fabs(lam1) : eb_div(lam1 * lam1, 4 * lref) + lref;
+    lam2 = (fabs(lam2) >= 2 * lref) ? fabs(lam2) : eb_div(lam2 * lam2, 4 * lref) + lref;
     const double a0 = fabs(lam0), a1 = fabs(lam1), a2 = fabs(lam2);
-    const double w0 = (dr - dp / ahat2);
-    const double w1 = ((dp + rhat * ahat * du) / (2.0 * ahat2));
-    const double w2 = ((dp - rhat * ahat * du) / (2.0 * ahat2));
+    const double w0 = (dr - eb_div(dp, ahat2));
+    const double w1 = eb_div(dp + rhat * ahat * du, 2.0 * ahat2);
+    const double w2 = eb_div(dp - rhat * ahat * du, 2.0 * ahat2);
     double FL, FR;
     FL = rL * uL; FR = rR * uR;
     F[Lay::iMass] = 0.5 * (FL + FR - (a0 * w0) - (a1 * w1) - (a2 * w2));
@@ -683,7 +736,7 @@ __device__ __forceinline__ int decode_cell(const EbParams& P, const EbGas* __res
     double rho = U[Lay::iMass];
     if (!(rho > 0.0)) return 1;
     Q.rho = rho;
-    double dinv = 1.0 / rho;
+    double dinv = eb_div(1.0, rho);
     Q.vx = U[Lay::iXMom] * dinv; Q.vy = U[Lay::iYMom] * dinv;
     Q.vz = (DIM == 3) ? U[Lay::iZMom] * dinv : 0.0;
     double u = U[Lay::iEnergy] * dinv;

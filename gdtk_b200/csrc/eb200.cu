@@ -247,6 +247,14 @@ bool detect_cartesian(const Sim* s, const Block* b, const double* vol, const dou
             D.fr[d].neg[v] = f0[3 * v + which] < 0.0 ? 1 : 0;
         }
         if (D.fr[d].perm[0] == D.fr[d].perm[1] || D.fr[d].perm[0] == D.fr[d].perm[2] || D.fr[d].perm[1] == D.fr[d].perm[2]) return false;
+        // the fast path is compiled for the frames Eilmer builds on a box grid (CartFrame in
+        // flux_kernel_v2.cuh): 3D (e_d, e_d+1, e_d+2); 2D i-face (x, -y, z), j-face (y, x, z)
+        {
+            int ep[3], en[3] = { 0, 0, 0 };
+            if (dims == 3) { ep[0] = d; ep[1] = (d + 1) % 3; ep[2] = (d + 2) % 3; }
+            else { ep[0] = d; ep[1] = 1 - d; ep[2] = 2; en[1] = (d == 0) ? 1 : 0; }
+            for (int v = 0; v < 3; ++v) if (D.fr[d].perm[v] != ep[v] || D.fr[d].neg[v] != en[v]) return false;
+        }
         for (int m = 0; m < 3; ++m) D.nvec[d][m] = f0[m];
         D.area[d] = f0[9];
         // l2r2_prepare on four equal lengths (onedinterp.d:338-354)
@@ -616,7 +624,7 @@ int eb200_commit(int sim)
         (b->cartesian ? any_cart : any_general) = true;
         cells_total += (long long)b->nic * b->njc * b->nkc;
     }
-    s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0);
+    s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (s->cfg.reserved_i[1] ? 4 : 0);
     {
         // k-chunking (3D): enough CTAs to fill 148 SMs several times over, else whole columns
         long long tiles_plane = 0;

@@ -9,6 +9,7 @@
 #define EB_FLUX_HAS_TPG (EB_FLUX != 5)   /* roe with several species is not on this path */
 #endif
 #include "flux_kernel.cuh"
+#include "flux_kernel_v2.cuh"
 
 #define EB_CAT2(a, b) a##b
 #define EB_CAT(a, b) EB_CAT2(a, b)
@@ -18,7 +19,11 @@ void EB_CAT(launch_flux_update_k, EB_FLUX)(const EbParams& P, int gas_model, con
                                           int nblocks, long long ncta, const EbArena& A, const EbStageArgs& S,
                                           int tile_y, int which, cudaStream_t st)
 {
-    launch_flux_update_impl<EB_FLUX>(P, gas_model, gas, desc, nblocks, ncta, A, S, tile_y, which, st);
+    // tile_y < 0: force the generic kernel (A/B testing); otherwise the tuned kernel handles the reference's
+    // default configuration (ideal gas, second-order reconstruction, limiter on)
+    const bool tuned = (tile_y >= 0) && gas_model == EB200_GAS_IDEAL && P.interpolation_order == 2 && P.apply_limiter != 0;
+    if (tuned) launch_flux_update_v2_impl<EB_FLUX>(P, gas, desc, nblocks, ncta, A, S, which, st);
+    else launch_flux_update_impl<EB_FLUX>(P, gas_model, gas, desc, nblocks, ncta, A, S, tile_y, which, st);
 }
 void EB_CAT(launch_face_debug_k, EB_FLUX)(const EbParams& P, int gas_model, const EbGas* gas, const EbArena& A,
                                          const double* prim, int nfaces, double* Fout, int* ok_out, cudaStream_t st)

@@ -30,16 +30,19 @@ void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* ga
     }
 }
 
+// which: bit 0 Cartesian blocks, bit 1 general-metric blocks, bit 2 force the generic kernel
 void launch_flux_update(int flux_calc, int gm, const EbParams& P, const EbGas* gas, const EbBlockDesc* desc, int nblocks,
                         long long ncta, const EbArena& A, const EbStageArgs& S, int which, cudaStream_t st)
 {
+    const int ty = (which & 4) ? -1 : 0;
+    which &= 3;
     switch (flux_calc) {
-    case 0: launch_flux_update_k0(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
-    case 1: launch_flux_update_k1(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
-    case 2: launch_flux_update_k2(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
-    case 3: launch_flux_update_k3(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
-    case 4: launch_flux_update_k4(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
-    case 5: launch_flux_update_k5(P, gm, gas, desc, nblocks, ncta, A, S, 0, which, st); break;
+    case 0: launch_flux_update_k0(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 1: launch_flux_update_k1(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 2: launch_flux_update_k2(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 3: launch_flux_update_k3(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 4: launch_flux_update_k4(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 5: launch_flux_update_k5(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     }
 }
 

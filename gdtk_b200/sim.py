@@ -63,6 +63,7 @@ class Config:
         self.strict_fp = False
         # Not an Eilmer option: testing knob, never use the uniform-Cartesian fast path.
         self.force_general_path = False
+        self.force_generic_kernel = False  # testing knob: never use the tuned flux kernel
         self.block_index = None          # optional {block id: (ib, jb, kb)} left by the case factories
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -102,6 +103,7 @@ class Config:
         c.max_invalid_cells = self.max_invalid_cells
         c.strict_fp = int(self.strict_fp)
         c.reserved_i[0] = int(self.force_general_path)
+        c.reserved_i[1] = int(self.force_generic_kernel)
         c.rank = rank
         c.device = device
         c.epsilon_van_albada = self.epsilon_van_albada

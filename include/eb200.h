@@ -143,7 +143,8 @@ typedef struct eb200_config {
                                        0: fused multiply-add allowed (throughput build) */
     int rank;                       /* this process's rank (0 when single process) */
     int device;                     /* CUDA device ordinal used by this process */
-    int reserved_i[5];              /* [0] != 0: testing knob, never use the uniform-Cartesian fast path */
+    int reserved_i[5];              /* testing knobs: [0] != 0 never use the uniform-Cartesian fast path;
+                                       [1] != 0 always use the generic flux kernel */
     double epsilon_van_albada;      /* 1e-12 */
     double M_inf;                   /* 0.01 (ausm_plus_up) */
     double max_velocity;            /* flowstate_limits: 30000 */

@@ -118,6 +118,20 @@ def test_cartesian_and_general_paths_agree(product):
         assert identical(U1, U2)
 
 
+@pytest.mark.parametrize("case", ["box3d", "box3d_sheared", "ffs", "cone20"])
+def test_tuned_and_generic_kernels_agree(product, case):
+    """The tuned kernel (shared-memory staging, flux_kernel_v2.cuh) and the generic kernel
+    (flux_kernel.cuh) are two schedules of the same arithmetic: identical bits in strict mode."""
+    factory, kw, n = {"box3d": (cases.box3d, dict(n=32, nb=2), 6),
+                      "box3d_sheared": (cases.box3d, dict(n=16, nb=2, sheared=True), 6),
+                      "ffs": (cases.ffs, dict(nx=120, ny=40), 30),
+                      "cone20": (cases.cone20, dict(), 60)}[case]
+    s1, U1, _ = run_case(factory, product, n, strict=True, **kw)
+    s2, U2, _ = run_case(factory, product, n, strict=True, force_generic_kernel=True, **kw)
+    assert identical(U1, U2)
+    assert s1.dt_history == s2.dt_history
+
+
 def test_step_failure_and_retry(product):
     """A time step that is far too large must come back as 'failed, state intact' and the
     host policy then retries with dt*0.2 (simcore_gasdynamic_step.d:995-999)."""
