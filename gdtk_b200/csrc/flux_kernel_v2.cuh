@@ -19,6 +19,9 @@
 #ifndef EB_V2_TY
 #define EB_V2_TY 8
 #endif
+#ifndef EB_V2_MIN_CTAS
+#define EB_V2_MIN_CTAS 2
+#endif
 
 namespace EB_NS {
 
@@ -66,13 +69,170 @@ struct Stencil {
     double aL, aR;
 };
 
-// Reconstruction + thermo + flux in the face frame.  Returns F in the face frame (momentum
-// components along n, t1, t2).  ROT: general-metric path (velocities rotate with `fr`).
+__device__ __forceinline__ double pick3(int d, double a0, double a1, double a2) { return d == 0 ? a0 : (d == 1 ? a1 : a2); }
+
+#ifdef EB_FAST_MATH
+// Component-form flux calculators for the uniform-Cartesian path of the throughput build:
+// velocities stay in (x, y, z); `d` names the face-normal component.  The tangential
+// momentum fluxes of these schemes have one common form, evaluated for all three components;
+// the normal component is then overwritten.  Sums are not in the reference's (n, t1, t2) order
+// (kinetic energy), so this is for the 1e-10 tolerance build only.
+template <int DIM>
+__device__ __forceinline__ void set_normal(int d, double fn, double* F)
+{
+    typedef Layout<DIM, 1> Lay;
+    F[Lay::iXMom] = (d == 0) ? fn : F[Lay::iXMom];
+    F[Lay::iYMom] = (d == 1) ? fn : F[Lay::iYMom];
+    if (DIM == 3) F[Lay::iZMom] = (d == 2) ? fn : F[Lay::iZMom];
+}
+
+template <int DIM, int FLUX>
+__device__ __forceinline__ void flux_components(const Prim<1>& L, const Prim<1>& R, int d, bool entropy_fix, double M_inf, double* F)
+{
+    typedef Layout<DIM, 1> Lay;
+    const double rL = L.rho, pL = L.p, rR = R.rho, pR = R.p, aL = L.a, aR = R.a;
+    const double uL = (DIM == 3) ? pick3(d, L.vx, L.vy, L.vz) : ((d == 0) ? L.vx : L.vy);
+    const double uR = (DIM == 3) ? pick3(d, R.vx, R.vy, R.vz) : ((d == 0) ? R.vx : R.vy);
+    const double rrL = eb_rcp(rL), rrR = eb_rcp(rR);
+    const double pLrL = pL * rrL, pRrR = pR * rrR;
+    const double keL = 0.5 * (L.vx * L.vx + L.vy * L.vy + ((DIM == 3) ? L.vz * L.vz : 0.0));
+    const double keR = 0.5 * (R.vx * R.vx + R.vy * R.vy + ((DIM == 3) ? R.vz * R.vz : 0.0));
+    const double HL = L.u + pLrL + keL, HR = R.u + pRrR + keR;
+    if (FLUX == EB200_FLUX_AUSMDV) {                 // fluxcalc.d:474-647
+        const double am = fmax(aL, aR);
+        const double duL = 0.5 * (uL + fabs(uL)), duR = 0.5 * (uR - fabs(uR));
+        const double rs = eb_rcp(pLrL + pRrR), ram = eb_rcp(am), qam = 0.25 * ram;
+        const double alphaL = 2.0 * pLrL * rs, alphaR = 2.0 * pRrR * rs;
+        const double ML = uL * ram, MR = uR * ram;
+        double pLplus, uLplus, pRminus, uRminus;
+        if (fabs(ML) <= 1.0) {
+            pLplus = pL * (ML + 1.0) * (ML + 1.0) * (2.0 - ML) * 0.25;
+            uLplus = alphaL * ((uL + am) * (uL + am) * qam - duL) + duL;
+        } else { pLplus = (uL > 0.0) ? pL : 0.0; uLplus = duL; }
+        if (fabs(MR) <= 1.0) {
+            pRminus = pR * (MR - 1.0) * (MR - 1.0) * (2.0 + MR) * 0.25;
+            uRminus = alphaR * (-(uR - am) * (uR - am) * qam - duR) + duR;
+        } else { pRminus = (uR < 0.0) ? pR : 0.0; uRminus = duR; }
+        const double ru_half = uLplus * rL + uRminus * rR;
+        const double p_half = pLplus + pRminus;
+        const double dp = 10.0 * fabs(pL - pR) * eb_rcp(fmin(pL, pR));
+        const double sw = 0.5 * fmin(1.0, dp);
+        const double ru2_AUSMV = uLplus * rL * uL + uRminus * rR * uR;
+        const double ru2_AUSMD = 0.5 * (ru_half * (uL + uR) - fabs(ru_half) * (uR - uL));
+        const double ru2_half = (0.5 + sw) * ru2_AUSMV + (0.5 - sw) * ru2_AUSMD;
+        const bool fromL = (ru_half >= 0.0);
+        F[Lay::iMass] = ru_half;
+        F[Lay::iXMom] = ru_half * (fromL ? L.vx : R.vx);
+        F[Lay::iYMom] = ru_half * (fromL ? L.vy : R.vy);
+        if (DIM == 3) F[Lay::iZMom] = ru_half * (fromL ? L.vz : R.vz);
+        set_normal<DIM>(d, ru2_half + p_half, F);
+        F[Lay::iEnergy] = ru_half * (fromL ? HL : HR);
+        if (entropy_fix) {
+            const bool caseA = ((uL - aL) < 0.0) && ((uR - aR) > 0.0);
+            const bool caseB = ((uL + aL) < 0.0) && ((uR + aR) > 0.0);
+            double d_ua = 0.0;
+            if (caseA && !caseB) d_ua = 0.125 * ((uR - aR) - (uL - aL));
+            if (caseB && !caseA) d_ua = 0.125 * ((uR + aR) - (uL + aL));
+            if (d_ua != 0.0) {
+                F[Lay::iMass] -= d_ua * (rR - rL);
+                F[Lay::iXMom] -= d_ua * (rR * R.vx - rL * L.vx);
+                F[Lay::iYMom] -= d_ua * (rR * R.vy - rL * L.vy);
+                if (DIM == 3) F[Lay::iZMom] -= d_ua * (rR * R.vz - rL * L.vz);
+                F[Lay::iEnergy] -= d_ua * (rR * HR - rL * HL);
+            }
+        }
+    } else if (FLUX == EB200_FLUX_HANEL) {           // fluxcalc.d:1028-1128
+        double pLplus, uLplus, pRminus, uRminus;
+        if (fabs(uL) <= aL) {
+            const double raL = eb_rcp(aL);
+            uLplus = 0.25 * raL * (uL + aL) * (uL + aL);
+            pLplus = pL * uLplus * (raL * (2.0 - uL * raL));
+        } else { uLplus = 0.5 * (uL + fabs(uL)); pLplus = (uL > 0.0) ? pL : 0.0; }
+        if (fabs(uR) <= aR) {
+            const double raR = eb_rcp(aR);
+            uRminus = -0.25 * raR * (uR - aR) * (uR - aR);
+            pRminus = pR * uRminus * (raR * (-2.0 - uR * raR));
+        } else { uRminus = 0.5 * (uR - fabs(uR)); pRminus = (uR < 0.0) ? pR : 0.0; }
+        const double mL = uLplus * rL, mR = uRminus * rR;
+        F[Lay::iMass] = mL + mR;
+        F[Lay::iXMom] = mL * L.vx + mR * R.vx;
+        F[Lay::iYMom] = mL * L.vy + mR * R.vy;
+        if (DIM == 3) F[Lay::iZMom] = mL * L.vz + mR * R.vz;
+        set_normal<DIM>(d, mL * uL + mR * uR + (pLplus + pRminus), F);
+        F[Lay::iEnergy] = mL * HL + mR * HR;
+    } else if (FLUX == EB200_FLUX_LDFSS0 || FLUX == EB200_FLUX_LDFSS2) {   // fluxcalc.d:819-1025
+        const double am = 0.5 * (aL + aR);
+        double ML, MR;
+        if (FLUX == EB200_FLUX_LDFSS0) { ML = uL * eb_rcp(aL); MR = uR * eb_rcp(aR); }
+        else { const double ram = eb_rcp(am); ML = uL * ram; MR = uR * ram; }
+        const double MpL = 0.25 * ((ML + 1.0) * (ML + 1.0));
+        const double MmR = -0.25 * ((MR - 1.0) * (MR - 1.0));
+        const double alphaL = 0.5 * (1.0 + sgn_d(ML)), alphaR = 0.5 * (1.0 - sgn_d(MR));
+        const double betaL = -fmax(0.0, 1.0 - floor(fabs(ML))), betaR = -fmax(0.0, 1.0 - floor(fabs(MR)));
+        const double PL = MpL * (2.0 - ML), PR = 0.25 * ((MR - 1.0) * (MR - 1.0)) * (2.0 + MR);
+        const double DL = alphaL * (1.0 + betaL) - betaL * PL, DR = alphaR * (1.0 + betaR) - betaR * PR;
+        const double sq = eb_sqrt(0.5 * (ML * ML + MR * MR)) - 1.0;
+        const double Mhalf = 0.25 * betaL * betaR * (sq * sq);
+        double cL, cR;
+        if (FLUX == EB200_FLUX_LDFSS0) {
+            cL = aL * rL * (alphaL * (1.0 + betaL) * ML - betaL * MpL - Mhalf);
+            cR = aR * rR * (alphaR * (1.0 + betaR) * MR - betaR * MmR + Mhalf);
+        } else {
+            const double t = (pL - pR) * eb_rcp(pL + pR), ad = fabs(pL - pR);
+            const double MhalfL = Mhalf * (1.0 - (t + 2.0 * (ad * eb_rcp(pL))));
+            const double MhalfR = Mhalf * (1.0 + (t - 2.0 * (ad * eb_rcp(pR))));
+            cL = am * rL * (alphaL * (1.0 + betaL) * ML - betaL * MpL - MhalfL);
+            cR = am * rR * (alphaR * (1.0 + betaR) * MR - betaR * MmR + MhalfR);
+        }
+        F[Lay::iMass] = cL + cR;
+        F[Lay::iXMom] = cL * L.vx + cR * R.vx;
+        F[Lay::iYMom] = cL * L.vy + cR * R.vy;
+        if (DIM == 3) F[Lay::iZMom] = cL * L.vz + cR * R.vz;
+        set_normal<DIM>(d, (cL * uL + cR * uR) + (DL * pL + DR * pR), F);
+        F[Lay::iEnergy] = cL * HL + cR * HR;
+    } else {                                          // ausm_plus_up, fluxcalc.d:1415-1602
+        const double a_half = 0.5 * (aR + aL), rah = eb_rcp(a_half);
+        const double ML = uL * rah, MR = uR * rah;
+        const double MbarSq = (uL * uL + uR * uR) * (0.5 * rah * rah);
+        const double M0Sq = fmin(1.0, fmax(MbarSq, M_inf * M_inf));
+        const double sqM0 = eb_sqrt(M0Sq);
+        const double fa = sqM0 * (2.0 - sqM0);
+        const double alpha = 0.1875 * (-4.0 + 5 * fa * fa);
+        const double beta = 0.125;
+        double M4p, P5p, M4m, P5m;
+        if (fabs(ML) >= 1.0) { M4p = M1plus(ML); P5p = (ML > 0.0) ? 1.0 : 0.0; }
+        else { const double a2 = M2plus(ML), b2 = M2minus(ML); M4p = a2 * (1.0 - 16.0 * beta * b2); P5p = a2 * ((2.0 - ML) - 16.0 * alpha * ML * b2); }
+        if (fabs(MR) >= 1.0) { M4m = M1minus(MR); P5m = (MR < 0.0) ? 1.0 : 0.0; }
+        else { const double a2 = M2plus(MR), b2 = M2minus(MR); M4m = b2 * (1.0 + 16.0 * beta * a2); P5m = b2 * ((-2.0 - MR) + 16.0 * alpha * MR * a2); }
+        const double r_half = 0.5 * (rL + rR);
+        const double Mp = -0.25 * eb_rcp(fa) * fmax((1.0 - MbarSq), 0.0) * (pR - pL) * eb_rcp(r_half * a_half * a_half);
+        const double Pu = -0.75 * P5p * P5m * (rL + rR) * fa * a_half * (uR - uL);
+        const double M_half = M4p + M4m + Mp;
+        const double ru_half = a_half * M_half * ((M_half > 0.0) ? rL : rR);
+        const double p_half = P5p * pL + P5m * pR + Pu;
+        const bool fromL = (ru_half >= 0.0);
+        F[Lay::iMass] = ru_half;
+        F[Lay::iXMom] = ru_half * (fromL ? L.vx : R.vx);
+        F[Lay::iYMom] = ru_half * (fromL ? L.vy : R.vy);
+        if (DIM == 3) F[Lay::iZMom] = ru_half * (fromL ? L.vz : R.vz);
+        set_normal<DIM>(d, ru_half * (fromL ? uL : uR) + p_half, F);
+        F[Lay::iEnergy] = ru_half * (fromL ? HL : HR);
+    }
+}
+#endif
+
+// Reconstruction + thermo + flux.  ROT: general-metric path, the stencil velocities are global and
+// rotate with `fr`, F comes back in the face frame.  !ROT: uniform-Cartesian path, the face frame is
+// a renaming of the components ((n,t1,t2) = (e_d, e_d+1, e_d+2) in 3D; 2D: i-face (x,-y), j-face
+// (y,x)): the components are reconstructed under their own names (each reconstruction is
+// independent, so this is bit-identical to reconstructing in the face frame), only the two
+// reconstructed velocities are renamed by d, and F comes back with momentum in (x,y,z) order.
 template <int DIM, int FLUX, bool CLIP, bool ROT>
 __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __restrict__ gas, const EbWeights& w,
-                                          Stencil& s, const Frame& fr, const double* __restrict__ prim_fallback,
+                                          Stencil& s, const Frame& fr, int d, const double* __restrict__ prim_fallback,
                                           long long cL0, long long cR0, double* F)
 {
+    typedef Layout<DIM, 1> Lay;
     Prim<1> L, R;
     if (ROT && P.local_frame) {
 #pragma unroll
@@ -104,12 +264,38 @@ __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __rest
         }
         to_local<DIM>(fr, L.vx, L.vy, L.vz); to_local<DIM>(fr, R.vx, R.vy, R.vz);
     }
+#ifdef EB_FAST_MATH
+    if (!ROT && FLUX != EB200_FLUX_ROE) {
+        // 2D i-faces have t1 = -y; the component form never looks at the sign of a tangential component
+        flux_components<DIM, FLUX>(L, R, d, P.entropy_fix != 0, P.M_inf, F);
+        return;
+    }
+#endif
+    if (ROT) {
+    } else if (DIM == 3) {
+        const double lx = L.vx, ly = L.vy, lz = L.vz, rx = R.vx, ry = R.vy, rz = R.vz;
+        L.vx = pick3(d, lx, ly, lz); L.vy = pick3(d, ly, lz, lx); L.vz = pick3(d, lz, lx, ly);
+        R.vx = pick3(d, rx, ry, rz); R.vy = pick3(d, ry, rz, rx); R.vz = pick3(d, rz, rx, ry);
+    } else {
+        const double lx = L.vx, ly = L.vy, rx = R.vx, ry = R.vy;
+        L.vx = (d == 0) ? lx : ly; L.vy = (d == 0) ? -ly : lx;
+        R.vx = (d == 0) ? rx : ry; R.vy = (d == 0) ? -ry : rx;
+    }
     if (FLUX == EB200_FLUX_AUSMDV) flux_ausmdv<DIM, 1>(L, R, P.entropy_fix != 0, F);
     else if (FLUX == EB200_FLUX_HANEL) flux_hanel<DIM, 1>(L, R, F);
     else if (FLUX == EB200_FLUX_LDFSS0) flux_ldfss<DIM, 1, 0>(L, R, F);
     else if (FLUX == EB200_FLUX_LDFSS2) flux_ldfss<DIM, 1, 2>(L, R, F);
     else if (FLUX == EB200_FLUX_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, 1>(L, R, P.M_inf, F);
     else flux_roe<DIM, 1>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
+    if (!ROT) {              // momentum flux back to (x, y, z) order
+        if (DIM == 3) {
+            const double f0 = F[Lay::iXMom], f1 = F[Lay::iYMom], f2 = F[Lay::iZMom];
+            F[Lay::iXMom] = pick3(d, f0, f2, f1); F[Lay::iYMom] = pick3(d, f1, f0, f2); F[Lay::iZMom] = pick3(d, f2, f1, f0);
+        } else {
+            const double f0 = F[Lay::iXMom], f1 = F[Lay::iYMom];
+            F[Lay::iXMom] = (d == 0) ? f0 : f1; F[Lay::iYMom] = (d == 0) ? -f1 : f0;
+        }
+    }
 }
 
 // Shared-memory tile of one k-plane: NF fields x ROWS x COLS doubles (halo of 2 on each side).
@@ -137,7 +323,7 @@ struct CartFrame {
 };
 
 template <int DIM, int FLUX, bool CART, bool CLIP, int TY>
-__global__ void __launch_bounds__(32 * TY, 2)
+__global__ void __launch_bounds__(32 * TY, EB_V2_MIN_CTAS)
 flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc* __restrict__ descs, int nblocks,
                       const EbArena A, const EbStageArgs S)
 {
@@ -146,11 +332,12 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
     constexpr int NCQ = Lay::NCQ;
     constexpr int NT = 32 * TY;
     extern __shared__ double smem[];
-    // layout: tile[2][SIZE] | fW[2][NCQ][TY][33] | fS[2][NCQ][TY+1][32] | desc
+    // layout: tile[2][SIZE] | fW[2][NCQ][TY][33] | fS[2][NCQ][TY+1][32] | fB[2][NCQ][TY][32] | desc
     double* tile = smem;
     double* fWs = tile + 2 * T::SIZE;
     double* fSs = fWs + 2 * NCQ * TY * 33;
-    EbBlockDesc& D = *reinterpret_cast<EbBlockDesc*>(fSs + 2 * NCQ * (TY + 1) * 32);
+    double* fBs = fSs + 2 * NCQ * (TY + 1) * 32;
+    EbBlockDesc& D = *reinterpret_cast<EbBlockDesc*>(fBs + 2 * NCQ * TY * 32);
     __shared__ int s_blk;
 
     const int lane = threadIdx.x, wy = threadIdx.y;
@@ -232,14 +419,14 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
         const double* tl = tile + buf * T::SIZE;
         double* fW = fWs + buf * NCQ * TY * 33;
         double* fS = fSs + buf * NCQ * (TY + 1) * 32;
+        double* fB = fBs + buf * NCQ * TY * 32;
         const long long c = D.cell0 + ((long long)(k + D.kg) * NJ + (j + EB_NG)) * NI + (i + EB_NG);
-        double FB[NCQ];
-#pragma unroll
-        for (int q = 0; q < NCQ; ++q) FB[q] = 0.0;
 
         // ---------------- the faces of this plane: one loop, ONE inlined copy of the face arithmetic -------
         // job 0: west face (d=0), job 1: south face (d=1), job 2: bottom face (d=2, 3D),
-        // job 3: second trip for warp 0 (faces east of lane 31) and warp 1 (south faces of row TY)
+        // job 3: second trip for warp 0 (faces east of lane 31) and warp 1 (south faces of row TY).
+        // Every flux goes straight to shared memory; the momentum components are put into their
+        // global-frame slots by address, not by moving values around.
 #pragma unroll 1
         for (int job = 0; job < 4; ++job) {
             if (job == 2 && DIM != 3) continue;
@@ -253,114 +440,82 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             else if (job == 2) active = cell_ok;
             else if (d == 0) { row = lane + 2; col = 34; fi = i0 + 32; fj = j0 + lane; active = extraE_ok; }
             else { row = TY + 2; fj = j0 + TY; active = extraN_ok; }
-            double F[NCQ];
+            if (!active) continue;
+            // where this face's flux goes: component q at out[q * qstride]
+            double* out;
+            int qstride;
+            if (d == 0) { out = fW + (row - 2) * 33 + (col - 2); qstride = TY * 33; }
+            else if (d == 1) { out = fS + (row - 2) * 32 + (col - 2); qstride = (TY + 1) * 32; }
+            else { out = fB + wy * 32 + lane; qstride = TY * 32; }
+            const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (fj + EB_NG)) * NI + (fi + EB_NG);
+            const long long st = (d == 0) ? 1 : ((d == 1) ? sj : sk);
+            int bcf = -1;
+            if (d == 0) { if (fi == 0) bcf = EB200_WEST; else if (fi == nic) bcf = EB200_EAST; }
+            else if (d == 1) { if (fj == 0) bcf = EB200_SOUTH; else if (fj == njc) bcf = EB200_NORTH; }
+            else { if (k == 0) bcf = EB200_BOTTOM; else if (k == nkc) bcf = EB200_TOP; }
+            if (bcf >= 0 && D.bc_kind[bcf] == EB200_BC_OUTFLOW_SIMPLE_FLUX) {
+                const int hi = bcf & 1;
+                Prim<1> fs;
+                load_prim<1>(fs, S.prim_in, total, hi ? cf - st : cf);
+                if (DIM == 2) fs.vz = 0.0;
+                double nx, ny, nz;
+                if (CART) { nx = D.nvec[d][0]; ny = D.nvec[d][1]; nz = D.nvec[d][2]; }
+                else { nx = ldg(A.face[d] + cf); ny = ldg(A.face[d] + total + cf); nz = (DIM == 3) ? ldg(A.face[d] + 2 * total + cf) : 0.0; }
+                double F[NCQ];
+                outflow_flux<DIM, 1>(fs, hi ? 1 : -1, nx, ny, nz, F);
 #pragma unroll
-            for (int q = 0; q < NCQ; ++q) F[q] = 0.0;
-            if (active) {
-                const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (fj + EB_NG)) * NI + (fi + EB_NG);
-                const long long st = (d == 0) ? 1 : ((d == 1) ? sj : sk);
-                int bcf = -1;
-                if (d == 0) { if (fi == 0) bcf = EB200_WEST; else if (fi == nic) bcf = EB200_EAST; }
-                else if (d == 1) { if (fj == 0) bcf = EB200_SOUTH; else if (fj == njc) bcf = EB200_NORTH; }
-                else { if (k == 0) bcf = EB200_BOTTOM; else if (k == nkc) bcf = EB200_TOP; }
-                if (bcf >= 0 && D.bc_kind[bcf] == EB200_BC_OUTFLOW_SIMPLE_FLUX) {
-                    const int hi = bcf & 1;
-                    Prim<1> fs;
-                    load_prim<1>(fs, S.prim_in, total, hi ? cf - st : cf);
-                    if (DIM == 2) fs.vz = 0.0;
-                    double nx, ny, nz;
-                    if (CART) { nx = D.nvec[d][0]; ny = D.nvec[d][1]; nz = D.nvec[d][2]; }
-                    else { nx = ldg(A.face[d] + cf); ny = ldg(A.face[d] + total + cf); nz = (DIM == 3) ? ldg(A.face[d] + 2 * total + cf) : 0.0; }
-                    outflow_flux<DIM, 1>(fs, hi ? 1 : -1, nx, ny, nz, F);
-                } else {
-                    const double* q0 = tl + row * T::COLS + col;     // own (R0) cell, field 0
-                    Stencil s;
-                    // ---- gather the stencil; velocities in (x, y, z) order first
-                    double vx[4], vy[4], vz[4];
-                    if (d < 2) {
-                        const int so = (d == 0) ? 1 : T::COLS;       // tile stride along d
-#pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const double* qm = q0 + (m - 2) * so;
-                            s.rho[m] = qm[T::F_RHO * T::FSZ]; s.u[m] = qm[T::F_U * T::FSZ];
-                            vx[m] = qm[(T::F_V + 0) * T::FSZ]; vy[m] = qm[(T::F_V + 1) * T::FSZ];
-                            vz[m] = (DIM == 3) ? qm[(T::F_V + 2) * T::FSZ] : 0.0;
-                        }
-                        s.aL = (q0 - so)[T::F_A * T::FSZ];
-                    } else {
-                        // own column: plane k from the tile, planes k-2, k-1, k+1 from global memory (L2)
-                        const double* pin = S.prim_in;
-#pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            if (m == 2) {
-                                s.rho[m] = q0[T::F_RHO * T::FSZ]; s.u[m] = q0[T::F_U * T::FSZ];
-                                vx[m] = q0[(T::F_V + 0) * T::FSZ]; vy[m] = q0[(T::F_V + 1) * T::FSZ];
-                                vz[m] = (DIM == 3) ? q0[(T::F_V + 2) * T::FSZ] : 0.0;
-                            } else {
-                                const long long cm = cf + (m - 2) * sk;
-                                s.rho[m] = ldg(pin + cm); s.u[m] = ldg(pin + total + cm);
-                                vx[m] = ldg(pin + 5 * total + cm); vy[m] = ldg(pin + 6 * total + cm); vz[m] = ldg(pin + 7 * total + cm);
-                            }
-                        }
-                        s.aL = ldg(pin + 4 * total + cf - sk);
-                    }
-                    s.aR = q0[T::F_A * T::FSZ];
-                    // ---- into the face frame: a renaming on the Cartesian path (CartFrame conventions)
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        if (!CART) { s.v0[m] = vx[m]; s.v1[m] = vy[m]; s.v2[m] = vz[m]; }
-                        else if (DIM == 3) {
-                            s.v0[m] = (d == 0) ? vx[m] : ((d == 1) ? vy[m] : vz[m]);
-                            s.v1[m] = (d == 0) ? vy[m] : ((d == 1) ? vz[m] : vx[m]);
-                            s.v2[m] = (d == 0) ? vz[m] : ((d == 1) ? vx[m] : vy[m]);
-                        } else {
-                            s.v0[m] = (d == 0) ? vx[m] : vy[m];
-                            s.v1[m] = (d == 0) ? -vy[m] : vx[m];
-                            s.v2[m] = 0.0;
-                        }
-                    }
-                    Frame fr;
-                    EbWeights wl;
-                    if (!CART) {
-                        load_frame<DIM>(fr, A.face[d], total, cf);
-                        const double* ln = A.len[d];
-                        l2r2_prepare(wl, ldg(ln + cf - 2 * st), ldg(ln + cf - st), ldg(ln + cf), ldg(ln + cf + st));
-                    }
-                    const EbWeights& w = CART ? D.w[d] : wl;
-                    double Fl[NCQ];
-                    face_core<DIM, FLUX, CLIP, !CART>(P, gas, w, s, fr, S.prim_in, cf - st, cf, Fl);
-                    // ---- momentum flux back to the global frame
-                    F[Lay::iMass] = Fl[Lay::iMass]; F[Lay::iEnergy] = Fl[Lay::iEnergy];
-                    if (!CART) {
-                        double fx = Fl[Lay::iXMom], fy = Fl[Lay::iYMom], fz = (DIM == 3) ? Fl[Lay::iZMom] : 0.0;
-                        to_global<DIM>(fr, fx, fy, fz);
-                        F[Lay::iXMom] = fx; F[Lay::iYMom] = fy;
-                        if (DIM == 3) F[Lay::iZMom] = fz;
-                    } else if (DIM == 3) {
-                        const double f0 = Fl[Lay::iXMom], f1 = Fl[Lay::iYMom], f2 = Fl[Lay::iZMom];
-                        F[Lay::iXMom] = (d == 0) ? f0 : ((d == 1) ? f2 : f1);
-                        F[Lay::iYMom] = (d == 0) ? f1 : ((d == 1) ? f0 : f2);
-                        F[Lay::iZMom] = (d == 0) ? f2 : ((d == 1) ? f1 : f0);
-                    } else {
-                        const double f0 = Fl[Lay::iXMom], f1 = Fl[Lay::iYMom];
-                        F[Lay::iXMom] = (d == 0) ? f0 : f1;
-                        F[Lay::iYMom] = (d == 0) ? -f1 : f0;
-                    }
-                }
+                for (int q = 0; q < NCQ; ++q) out[q * qstride] = F[q];
+                continue;
             }
-            // ---- publish
-            if (job == 2) {
+            const double* q0 = tl + row * T::COLS + col;     // own (R0) cell, field 0
+            Stencil s;
+            // ---- gather the stencil straight into its registers.  On the Cartesian path the face frame is a
+            //      renaming of the velocity components (CartFrame conventions): pick the fields by address.
+            if (d < 2) {
+                const int so = (d == 0) ? 1 : T::COLS;       // tile stride along d
 #pragma unroll
-                for (int q = 0; q < NCQ; ++q) FB[q] = F[q];
-            } else if (d == 0) {
-                if (job == 0 || lane < TY) {
-#pragma unroll
-                    for (int q = 0; q < NCQ; ++q) fW[(q * TY + (row - 2)) * 33 + (col - 2)] = F[q];
+                for (int m = 0; m < 4; ++m) {
+                    const double* qm = q0 + (m - 2) * so;
+                    s.rho[m] = qm[T::F_RHO * T::FSZ]; s.u[m] = qm[T::F_U * T::FSZ];
+                    s.v0[m] = qm[(T::F_V + 0) * T::FSZ]; s.v1[m] = qm[(T::F_V + 1) * T::FSZ];
+                    s.v2[m] = (DIM == 3) ? qm[(T::F_V + 2) * T::FSZ] : 0.0;
                 }
+                s.aL = (q0 - so)[T::F_A * T::FSZ];
             } else {
+                // own column: plane k from the tile, planes k-2, k-1, k+1 from global memory (L2)
+                const double* pin = S.prim_in;
 #pragma unroll
-                for (int q = 0; q < NCQ; ++q) fS[(q * (TY + 1) + (row - 2)) * 32 + (col - 2)] = F[q];
+                for (int m = 0; m < 4; ++m) {
+                    if (m == 2) {
+                        s.rho[m] = q0[T::F_RHO * T::FSZ]; s.u[m] = q0[T::F_U * T::FSZ];
+                        s.v0[m] = q0[(T::F_V + 0) * T::FSZ]; s.v1[m] = q0[(T::F_V + 1) * T::FSZ]; s.v2[m] = q0[(T::F_V + 2) * T::FSZ];
+                    } else {
+                        const double* pm = pin + cf + (m - 2) * sk;
+                        s.rho[m] = ldg(pm); s.u[m] = ldg(pm + total);
+                        s.v0[m] = ldg(pm + 5 * total); s.v1[m] = ldg(pm + 6 * total); s.v2[m] = ldg(pm + 7 * total);
+                    }
+                }
+                s.aL = ldg(pin + 4 * total + cf - sk);
             }
+            s.aR = q0[T::F_A * T::FSZ];
+            Frame fr;
+            EbWeights wl;
+            if (!CART) {
+                load_frame<DIM>(fr, A.face[d], total, cf);
+                const double* ln = A.len[d];
+                l2r2_prepare(wl, ldg(ln + cf - 2 * st), ldg(ln + cf - st), ldg(ln + cf), ldg(ln + cf + st));
+            }
+            const EbWeights& w = CART ? D.w[d] : wl;
+            double Fl[NCQ];
+            face_core<DIM, FLUX, CLIP, !CART>(P, gas, w, s, fr, d, S.prim_in, cf - st, cf, Fl);
+            if (!CART) {     // momentum flux back to the global frame (fluxcalc.d:169-175)
+                double fx = Fl[Lay::iXMom], fy = Fl[Lay::iYMom], fz = (DIM == 3) ? Fl[Lay::iZMom] : 0.0;
+                to_global<DIM>(fr, fx, fy, fz);
+                Fl[Lay::iXMom] = fx; Fl[Lay::iYMom] = fy;
+                if (DIM == 3) Fl[Lay::iZMom] = fz;
+            }
+#pragma unroll
+            for (int q = 0; q < NCQ; ++q) out[q * qstride] = Fl[q];
         }
 
         cp_async_wait_all();
@@ -373,7 +528,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             const double vol_inv = CART ? D.vol_inv : 1.0 / ldg(A.vol + cp);
             double dUdt[NCQ];
 #pragma unroll
-            for (int q = 0; q < NCQ; ++q) { double si = acc[q] - FB[q] * areaT; dUdt[q] = vol_inv * si + 0.0; }
+            for (int q = 0; q < NCQ; ++q) { double si = acc[q] - fB[(q * TY + wy) * 32 + lane] * areaT; dUdt[q] = vol_inv * si + 0.0; }
             finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, cp, dUdt, fail, n_invalid);
         }
 
@@ -393,7 +548,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
                 si = si - FE * aE;
                 si = si + FS * aS;
                 si = si - FN * aN;
-                if (DIM == 3) si = si + FB[q] * aB;
+                if (DIM == 3) si = si + fB[(q * TY + wy) * 32 + lane] * aB;
                 acc[q] = si;
             }
         }
@@ -428,7 +583,7 @@ constexpr size_t v2_smem_bytes()
 {
     typedef Tile<DIM, TY> T;
     constexpr int NCQ = Layout<DIM, 1>::NCQ;
-    return sizeof(double) * (2 * T::SIZE + 2 * NCQ * TY * 33 + 2 * NCQ * (TY + 1) * 32) + sizeof(EbBlockDesc);
+    return sizeof(double) * (2 * T::SIZE + 2 * NCQ * TY * 33 + 2 * NCQ * (TY + 1) * 32 + 2 * NCQ * TY * 32) + sizeof(EbBlockDesc);
 }
 
 template <int DIM, int FLUX, bool CART, bool CLIP>
