@@ -446,6 +446,9 @@ int eb200_init(const eb200_config* cfg)
     if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT && cfg->n_species != 5) {
         set_err("thermally perfect gas: kernels are built for 5 species (got %d)", cfg->n_species); return -1;
     }
+    if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT && cfg->dimensions != 3) {
+        set_err("thermally perfect gas: kernels are built for 3D only"); return -1;
+    }
     if (cfg->flux_calculator < 0 || cfg->flux_calculator > 5) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
     if (cfg->flux_calculator == EB200_FLUX_ROE && cfg->n_species > 1) { set_err("roe with multiple species is not on this path yet"); return -1; }
     if (!n_stages_for(cfg->update_scheme)) { set_err("unsupported update scheme %d", cfg->update_scheme); return -1; }

@@ -444,7 +444,7 @@ void launch_face_debug_impl(const EbParams& P, int gas_model, const EbGas* gas, 
     if (gas_model == EB200_GAS_IDEAL) { if (P.dims == 3) EB_DBG(3, EB200_GAS_IDEAL, 1); else EB_DBG(2, EB200_GAS_IDEAL, 1); }
     else {
 #if EB_FLUX_HAS_TPG
-        if (P.nsp == 5) { if (P.dims == 3) EB_DBG(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_DBG(2, EB200_GAS_THERMALLY_PERFECT, 5); }
+        if (P.nsp == 5 && P.dims == 3) EB_DBG(3, EB200_GAS_THERMALLY_PERFECT, 5);
 #endif
     }
 #undef EB_DBG
@@ -465,7 +465,7 @@ void launch_flux_update_impl(const EbParams& P, int gas_model, const EbGas* gas,
         if (P.dims == 3) EB_LAUNCH(3, EB200_GAS_IDEAL, 1); else EB_LAUNCH(2, EB200_GAS_IDEAL, 1);
     } else {
 #if EB_FLUX_HAS_TPG
-        if (P.nsp == 5) { if (P.dims == 3) EB_LAUNCH(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_LAUNCH(2, EB200_GAS_THERMALLY_PERFECT, 5); }
+        if (P.nsp == 5 && P.dims == 3) EB_LAUNCH(3, EB200_GAS_THERMALLY_PERFECT, 5);     // C5 is 3D; 2D TPG kernels are not built
 #endif
     }
 #undef EB_LAUNCH

@@ -101,7 +101,7 @@ void launch_decode(const EbParams& P, int gas_model, const EbGas* gas, const EbB
 #define EB_DEC(DIM, GASM, NSP) decode_kernel<DIM, GASM, NSP><<<blocks, threads, 0, st>>>(P, gas, hdesc, prim_in, prim_out, U, do_encode, status)
     if (gas_model == EB200_GAS_IDEAL) { if (P.dims == 3) EB_DEC(3, EB200_GAS_IDEAL, 1); else EB_DEC(2, EB200_GAS_IDEAL, 1); }
 #ifndef EB_NO_TPG
-    else if (P.nsp == 5) { if (P.dims == 3) EB_DEC(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_DEC(2, EB200_GAS_THERMALLY_PERFECT, 5); }
+    else if (P.nsp == 5 && P.dims == 3) EB_DEC(3, EB200_GAS_THERMALLY_PERFECT, 5);
 #endif
 #undef EB_DEC
 }

@@ -39,34 +39,29 @@ def quad_patch_grid(p00, p10, p11, p01, nic, njc):
 
 
 def uniform_box_geometry(dims, nic, njc, nkc, dx, dy, dz=1.0):
-    """BlockGeometry of a uniform Cartesian block without touching vertices.
+    """BlockGeometry of a uniform Cartesian block without touching every vertex.
 
-    For spacings that are exactly representable (dyadic fractions) every formula of
-    geometry_2d/geometry_3d is exact, so the constants below are what those functions
-    return (tests/test_geometry.py checks this); this is the fast set-up route for the
-    large benchmark grids.
+    The metrics of one cell are computed with the general formulas (geometry_2d / geometry_3d)
+    on a 2-cell-wide reference block and replicated.  For spacings and origins that are
+    dyadic fractions all coordinate differences are exact, so every cell of the real block
+    gets bit-identical metrics from the general formulas (tests/test_geometry.py checks this);
+    this is the fast set-up route for the large benchmark grids.
     """
+    from .geometry import geometry_2d, geometry_3d
     g = BlockGeometry(dims, nic, njc, nkc if dims == 3 else 1)
-    g.len[0][...] = dx
-    g.len[1][...] = dy
     if dims == 3:
-        g.len[2][...] = dz
-        g.vol[...] = dx * dy * dz
-        frames = [((1, 0, 0), (0, 1, 0), (0, 0, 1), dy * dz),
-                  ((0, 1, 0), (0, 0, 1), (1, 0, 0), dx * dz),
-                  ((0, 0, 1), (1, 0, 0), (0, 1, 0), dx * dy)]
+        ref = geometry_3d(*box_grid_3d((0.0, 0.0, 0.0), (2 * dx, 2 * dy, 2 * dz), 2, 2, 2))
+        c = (NG, NG, NG)
+        g.vol[...] = ref.vol[c]
     else:
-        g.vol[...] = dx * dy
-        g.areaxy[...] = dx * dy
-        # signed zeros as produced by FVInterface.update_2D_geometric_data
-        frames = [((1.0, -0.0, 0.0), (-0.0, -1.0, 0.0), (0, 0, 1), dy),
-                  ((0.0, 1.0, 0.0), (1.0, -0.0, 0.0), (0, 0, 1), dx)]
-    for d, (n, t1, t2, area) in enumerate(frames):
-        for m in range(3):
-            g.face[d][m][...] = n[m]
-            g.face[d][3 + m][...] = t1[m]
-            g.face[d][6 + m][...] = t2[m]
-        g.face[d][9][...] = area
+        ref = geometry_2d(*box_grid_2d(0.0, 2 * dx, 0.0, 2 * dy, 2, 2))
+        c = (0, NG, NG)
+        g.vol[...] = ref.vol[c]
+        g.areaxy[...] = ref.areaxy[c]
+    for d in range(dims):
+        g.len[d][...] = ref.len[d][c]
+        for m in range(10):
+            g.face[d][m][...] = ref.face[d][m][c]
     return g
 
 

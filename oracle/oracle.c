@@ -31,6 +31,9 @@
 #include <string.h>
 #include <stdarg.h>
 #include "../include/eb200.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define NG EB200_NGHOST
 #define MAXSP EB200_MAX_SPECIES
@@ -86,7 +89,15 @@ typedef struct {
     /* ideal gas: src/gas/ideal_gas.d:64-68 */
     double Rgas, Cv, Cvinv, Cp, gamma_ig;
     Curve curves[MAXSP]; double Rsp[MAXSP];
-    int nblk; Blk* blks[MAXBLK];
+    int nblk; Blk* blks[MAXBLK];          /* local blocks (owner == cfg.rank) */
+    int nrem; Blk* rem[MAXBLK];           /* blocks of other ranks: dimensions only */
+    eb200_exchange_fn exchange; void* exchange_user;
+    int npeers; int peer_rank[64];
+    long n_send[64], n_recv[64];
+    Blk** send_blk[64]; long* send_cell[64];   /* what peer p needs from me, in ITS ghost order */
+    Blk** recv_blk[64]; long* recv_cell[64];   /* my ghost cells filled by peer p */
+    double* send_buf[64]; double* recv_buf[64];
+    int lists_built;
     int mutate_cell_vel;     /* reproduce e4 onedinterp.d:766-769,983-986 in-place round trips */
     int n_stages;
 } Sim;
@@ -101,6 +112,7 @@ static Sim* get_sim(int h)
 static Blk* get_blk(Sim* s, int id)
 {
     for (int i = 0; i < s->nblk; ++i) if (s->blks[i]->id == id) return s->blks[i];
+    for (int i = 0; i < s->nrem; ++i) if (s->rem[i]->id == id) return s->rem[i];
     set_err("unknown block id %d", id); return NULL;
 }
 
@@ -1099,9 +1111,133 @@ static int map_full_face_source(const Sim* s, const Blk* me, int face, const Blk
     return 0;
 }
 
-/* e4 simcore_exchange.d:96-135 exchange_ghost_cell_boundary_data (all blocks in one process) */
+/* Halo lists for blocks owned by other ranks (replaces the MPI tags / buffers of
+ * full_face_copy.d:33-41,1629-1654): one packed buffer per peer; both sides order the face sets
+ * by (receiving block id, receiving face) and the cells of a face in the receiver's ghost order
+ * (in-face index t2 outer, t1 inner, then layer). */
+typedef struct { int blk, face; long first, count; } FaceSet;
+static int cmp_faceset(const void* a, const void* b)
+{
+    const FaceSet* x = (const FaceSet*)a; const FaceSet* y = (const FaceSet*)b;
+    if (x->blk != y->blk) return x->blk - y->blk;
+    return x->face - y->face;
+}
+
+static long face_ghost_count(const Sim* s, const Blk* b, int face)
+{
+    int n[3] = { b->nic, b->njc, b->nkc };
+    int d = face / 2;
+    return (long)NG * n[(d + 1) % 3] * n[(d + 2) % 3];
+}
+
+/* enumerate the ghost cells behind `face` of block b (t2 outer, t1 inner, layer); for each, the
+ * source interior cell in block ot.  dst/src receive padded cell indices. */
+static int enumerate_face(const Sim* s, const Blk* b, int face, const Blk* ot, int oface, long* dst, long* src)
+{
+    int n[3] = { b->nic, b->njc, b->nkc };
+    int off[3] = { NG, NG, b->kg };
+    int d = face / 2, hi = face & 1;
+    long st = b->stride[d];
+    int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+    long m = 0;
+    for (int a2 = 0; a2 < n[d2]; ++a2) for (int a1 = 0; a1 < n[d1]; ++a1) {
+        int idx[3]; idx[d] = hi ? n[d] : 0; idx[d1] = a1; idx[d2] = a2;
+        long cf = cidx(b, idx[0] + off[0], idx[1] + off[1], idx[2] + off[2]);
+        int t1 = s->threeD ? a1 : (d == 0 ? idx[1] : idx[0]);
+        for (int layer = 0; layer < NG; ++layer) {
+            long sc;
+            if (map_full_face_source(s, b, face, ot, oface, t1, a2, layer, &sc)) return -1;
+            if (dst) dst[m] = hi ? cf + layer * st : cf - (1 + layer) * st;
+            if (src) src[m] = sc;
+            ++m;
+        }
+    }
+    return 0;
+}
+
+static int build_exchange_lists(Sim* s)
+{
+    int nfaces = s->threeD ? 6 : 4;
+    s->npeers = 0;
+    /* collect peers */
+    for (int ib = 0; ib < s->nblk; ++ib) for (int f = 0; f < nfaces; ++f) {
+        BC* bc = &s->blks[ib]->bc[f];
+        if (bc->kind != EB200_BC_EXCHANGE_FULL_FACE) continue;
+        Blk* ot = get_blk(s, bc->other_blk); if (!ot) return -1;
+        if (ot->local) continue;
+        int p; for (p = 0; p < s->npeers; ++p) if (s->peer_rank[p] == ot->owner) break;
+        if (p == s->npeers) { if (p >= 64) { set_err("too many peers"); return -1; } s->peer_rank[s->npeers++] = ot->owner; }
+    }
+    for (int p = 0; p < s->npeers; ++p) {
+        FaceSet rs[6 * 64], ss[6 * 64]; int nr = 0;
+        long tot = 0;
+        for (int ib = 0; ib < s->nblk; ++ib) for (int f = 0; f < nfaces; ++f) {
+            Blk* b = s->blks[ib]; BC* bc = &b->bc[f];
+            if (bc->kind != EB200_BC_EXCHANGE_FULL_FACE) continue;
+            Blk* ot = get_blk(s, bc->other_blk);
+            if (ot->local || ot->owner != s->peer_rank[p]) continue;
+            if (nr >= 6 * 64) { set_err("too many remote faces"); return -1; }
+            rs[nr].blk = b->id; rs[nr].face = f; rs[nr].count = face_ghost_count(s, b, f);
+            ss[nr].blk = ot->id; ss[nr].face = bc->other_face; ss[nr].count = face_ghost_count(s, ot, bc->other_face);
+            tot += rs[nr].count; ++nr;
+        }
+        qsort(rs, nr, sizeof(FaceSet), cmp_faceset);
+        qsort(ss, nr, sizeof(FaceSet), cmp_faceset);
+        long nrecv = 0, nsend = 0;
+        for (int i = 0; i < nr; ++i) { nrecv += rs[i].count; nsend += ss[i].count; }
+        s->n_recv[p] = nrecv; s->n_send[p] = nsend;
+        s->recv_blk[p] = malloc(nrecv * sizeof(Blk*)); s->recv_cell[p] = malloc(nrecv * sizeof(long));
+        s->send_blk[p] = malloc(nsend * sizeof(Blk*)); s->send_cell[p] = malloc(nsend * sizeof(long));
+        s->recv_buf[p] = malloc((size_t)nrecv * s->nprim * sizeof(double));
+        s->send_buf[p] = malloc((size_t)nsend * s->nprim * sizeof(double));
+        long m = 0;
+        for (int i = 0; i < nr; ++i) {           /* my ghost cells, in my order */
+            Blk* b = get_blk(s, rs[i].blk); BC* bc = &b->bc[rs[i].face];
+            Blk* ot = get_blk(s, bc->other_blk);
+            if (enumerate_face(s, b, rs[i].face, ot, bc->other_face, s->recv_cell[p] + m, NULL)) return -1;
+            for (long t = 0; t < rs[i].count; ++t) s->recv_blk[p][m + t] = b;
+            m += rs[i].count;
+        }
+        m = 0;
+        for (int i = 0; i < nr; ++i) {           /* the peer's ghost cells: which of my cells feed them */
+            Blk* ot = get_blk(s, ss[i].blk);     /* remote block */
+            /* find my block connected to (ot, face) */
+            Blk* mine = NULL; int myface = -1;
+            for (int ib = 0; ib < s->nblk && !mine; ++ib) for (int f = 0; f < nfaces; ++f) {
+                BC* bc = &s->blks[ib]->bc[f];
+                if (bc->kind == EB200_BC_EXCHANGE_FULL_FACE && bc->other_blk == ot->id && bc->other_face == ss[i].face) { mine = s->blks[ib]; myface = f; break; }
+            }
+            if (!mine) { set_err("inconsistent block connections"); return -1; }
+            if (enumerate_face(s, ot, ss[i].face, mine, myface, NULL, s->send_cell[p] + m)) return -1;
+            for (long t = 0; t < ss[i].count; ++t) s->send_blk[p][m + t] = mine;
+            m += ss[i].count;
+        }
+        (void)tot;
+    }
+    s->lists_built = 1;
+    return 0;
+}
+
+/* e4 simcore_exchange.d:96-135 exchange_ghost_cell_boundary_data */
 static int exchange_ghost_cells(Sim* s)
 {
+    if (!s->lists_built && build_exchange_lists(s)) return -1;
+    if (s->npeers > 0) {
+        if (!s->exchange) { set_err("blocks on other ranks are connected but no exchange callback is installed"); return -1; }
+        long long sc[64], rc[64];
+        for (int p = 0; p < s->npeers; ++p) {
+            long n = s->n_send[p];
+            for (int v = 0; v < s->nprim; ++v) for (long t = 0; t < n; ++t)
+                s->send_buf[p][(long)v * n + t] = PR(s, s->send_blk[p][t], v)[s->send_cell[p][t]];
+            sc[p] = (long long)n * s->nprim; rc[p] = (long long)s->n_recv[p] * s->nprim;
+        }
+        if (s->exchange(s->exchange_user, s->npeers, s->peer_rank, s->send_buf, sc, s->recv_buf, rc, NULL)) { set_err("exchange callback failed"); return -1; }
+        for (int p = 0; p < s->npeers; ++p) {
+            long n = s->n_recv[p];
+            for (int v = 0; v < s->nprim; ++v) for (long t = 0; t < n; ++t)
+                PR(s, s->recv_blk[p][t], v)[s->recv_cell[p][t]] = s->recv_buf[p][(long)v * n + t];
+        }
+    }
     for (int ib = 0; ib < s->nblk; ++ib) {
         Blk* b = s->blks[ib];
         int n[3] = { b->nic, b->njc, b->nkc };
@@ -1111,6 +1247,7 @@ static int exchange_ghost_cells(Sim* s)
             BC* bc = &b->bc[face];
             if (bc->kind != EB200_BC_EXCHANGE_FULL_FACE) continue;
             Blk* ot = get_blk(s, bc->other_blk); if (!ot) return -1;
+            if (!ot->local) continue;
             int d = face / 2, hi = face & 1;
             long st = b->stride[d];
             int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
@@ -1358,6 +1495,11 @@ int orc_finalize(int sim)
 {
     Sim* s = get_sim(sim); if (!s) return -1;
     for (int i = 0; i < s->nblk; ++i) free_blk(s->blks[i]);
+    for (int i = 0; i < s->nrem; ++i) free(s->rem[i]);
+    for (int p = 0; p < s->npeers; ++p) {
+        free(s->send_blk[p]); free(s->send_cell[p]); free(s->recv_blk[p]); free(s->recv_cell[p]);
+        free(s->send_buf[p]); free(s->recv_buf[p]);
+    }
     s->used = 0; return 0;
 }
 
@@ -1368,11 +1510,13 @@ int orc_block_create(int sim, int blk_id, int nic, int njc, int nkc, int owner_r
     if (!s->threeD && nkc != 1) { set_err("nkc must be 1 in 2D"); return -1; }
     if (nic < NG || njc < NG || (s->threeD && nkc < NG)) { set_err("too few cells for ghost-cell copies"); return -1; }
     Blk* b = (Blk*)calloc(1, sizeof(Blk));
-    b->id = blk_id; b->nic = nic; b->njc = njc; b->nkc = nkc; b->owner = owner_rank; b->local = 1;
+    b->id = blk_id; b->nic = nic; b->njc = njc; b->nkc = nkc; b->owner = owner_rank;
+    b->local = (owner_rank == s->cfg.rank);
     b->NI = nic + 2 * NG; b->NJ = njc + 2 * NG; b->NK = s->threeD ? nkc + 2 * NG : 1;
     b->kg = s->threeD ? NG : 0;
     b->ncp = (long)b->NI * b->NJ * b->NK;
     b->stride[0] = 1; b->stride[1] = b->NI; b->stride[2] = (long)b->NI * b->NJ;
+    if (!b->local) { s->rem[s->nrem++] = b; return 0; }
     long n = b->ncp;
     b->vol = calloc(n, sizeof(double)); b->areaxy = calloc(n, sizeof(double));
     for (int d = 0; d < 3; ++d) {
@@ -1395,6 +1539,7 @@ int orc_block_set_geometry(int sim, int blk_id, const double* vol, const double*
 {
     Sim* s = get_sim(sim); if (!s) return -1;
     Blk* b = get_blk(s, blk_id); if (!b) return -1;
+    if (!b->local) { set_err("geometry given for non-local block %d", blk_id); return -1; }
     long n = b->ncp;
     memcpy(b->vol, vol, n * sizeof(double));
     if (areaxy) memcpy(b->areaxy, areaxy, n * sizeof(double));
@@ -1435,7 +1580,12 @@ int orc_block_set_bc(int sim, int blk_id, int face, int kind, const double* para
 }
 
 int orc_commit(int sim) { Sim* s = get_sim(sim); return s ? 0 : -1; }
-int orc_set_exchange(int sim, eb200_exchange_fn fn, void* user) { (void)sim; (void)fn; (void)user; return 0; }
+int orc_set_exchange(int sim, eb200_exchange_fn fn, void* user)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    s->exchange = fn; s->exchange_user = user;
+    return 0;
+}
 
 int orc_set_option(int sim, const char* name, int value)
 {
@@ -1547,17 +1697,24 @@ int orc_step(int sim, double t0, double dt, int* n_bad_cells)
         memcpy(saved[ib], b->prim, (size_t)s->nprim * b->ncp * sizeof(double));
     }
     int nd = s->threeD ? 3 : 2;
+    int nthreads = 1;          /* one block per thread, never more threads than blocks */
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+    if (nthreads > s->nblk) nthreads = s->nblk;
+    if (nthreads < 1) nthreads = 1;
+#endif
+    (void)nthreads;
     for (int stage = 1; stage <= s->n_stages && !step_failed; ++stage) {
         if (exchange_ghost_cells(s)) { step_failed = -1; break; }                    /* Phase 02 */
-        #pragma omp parallel for schedule(dynamic, 1)
+        #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
         for (int ib = 0; ib < s->nblk; ++ib) apply_pre_recon_bcs(s, s->blks[ib]);      /* Phase 03 */
         int fail_flux = 0;
-        #pragma omp parallel for schedule(dynamic, 1) reduction(|:fail_flux)
+        #pragma omp parallel for schedule(dynamic, 1) reduction(|:fail_flux) num_threads(nthreads)
         for (int ib = 0; ib < s->nblk; ++ib)                                           /* Phase 05a + 07 */
             for (int d = 0; d < nd; ++d) fail_flux |= flux_sweep(s, s->blks[ib], d);
         if (fail_flux) { step_failed = 1; break; }
         int fail_upd = 0; total_bad = 0;
-        #pragma omp parallel for schedule(dynamic, 1) reduction(|:fail_upd) reduction(+:total_bad)
+        #pragma omp parallel for schedule(dynamic, 1) reduction(|:fail_upd) reduction(+:total_bad) num_threads(nthreads)
         for (int ib = 0; ib < s->nblk; ++ib) {                                         /* Phase 13 */
             int inv = 0;
             fail_upd |= update_block(s, s->blks[ib], stage, dt, &inv);

@@ -1,0 +1,49 @@
+"""Writes tests/golden/flow_*.npz: conserved quantities and dt histories of small runs of the CPU
+oracle (oracle/oracle.c).  They freeze the oracle's output so that (a) any later change of the
+oracle shows up as a diff, (b) the GPU tests can compare against committed vectors as well as
+against a live oracle run.  NOTE: these vectors are produced by the restatement, not by a build of
+the reference (no D compiler in the build container); the reference-derived golden
+values are the gas-model unit-test numbers in tests/test_oracle_gas.py and the integration KATs
+in tests/test_oracle_kats.py.
+
+    python tests/golden/make_flow_fixtures.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CASES = {
+    "sod3d": ("sod", dict(dims=3, ncells=40, nj=3, nk=2, nblocks=2), 25),
+    "cone20_ausmdv": ("cone20", dict(nx0=6, nx1=14, ny=16), 40),
+    "box3d_sheared_roe": ("box3d", dict(n=8, nb=2, sheared=True, flux_calculator="roe"), 6),
+    "box3d_ausm_plus_up": ("box3d", dict(n=12, nb=1, flux_calculator="ausm_plus_up"), 6),
+    "ffs_hanel": ("ffs", dict(nx=60, ny=20, flux_calculator="hanel"), 20),
+    "box3d_ldfss2_rk3": ("box3d", dict(n=8, nb=1, flux_calculator="ldfss2", gasdynamic_update_scheme="tvd-rk3"), 5),
+}
+
+
+def run(lib, name):
+    from gdtk_b200 import cases
+    from util import run_case
+    fac, kw, nsteps = CASES[name]
+    sim, U, P = run_case(getattr(cases, fac), lib, nsteps, **kw)
+    out = {"dt_history": np.array(sim.dt_history)}
+    for bid, arrs in U.items():
+        for q, a in enumerate(arrs):
+            out[f"U_b{bid}_q{q}"] = a
+    sim.close()
+    return out
+
+
+if __name__ == "__main__":
+    from conftest import build_oracle
+    from gdtk_b200 import _abi
+    lib = _abi.load_library(build_oracle(), "orc_")
+    for name in CASES:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"flow_{name}.npz"), **run(lib, name))
+        print("wrote", name)

@@ -1,0 +1,49 @@
+"""Committed golden vectors (tests/golden/flow_*.npz, made by tests/golden/make_flow_fixtures.py):
+the oracle must keep reproducing them bit for bit (CPU), and the FMA-free CUDA build must match
+them bit for bit, the throughput build within 1e-10 (GPU)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_flow_fixtures as mk  # noqa: E402
+
+
+def load(name):
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", f"flow_{name}.npz")))
+
+
+@pytest.mark.parametrize("name", sorted(mk.CASES))
+def test_oracle_reproduces_golden(oracle, name):
+    got, ref = mk.run(oracle, name), load(name)
+    assert sorted(got) == sorted(ref)
+    for k in ref:
+        assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(mk.CASES))
+def test_cuda_matches_golden(product, name):
+    from gdtk_b200 import cases
+    from util import run_case
+    ref = load(name)
+    fac, kw, nsteps = mk.CASES[name]
+    for strict in (True, False):
+        sim, U, _ = run_case(getattr(cases, fac), product, nsteps, strict=strict, **kw)
+        assert sim.kernel_launches() > 0
+        for bid, arrs in U.items():
+            vscale = max(np.abs(ref[f"U_b{bid}_q{q}"]).max() for q in (1, 2))
+            for q, a in enumerate(arrs):
+                r = ref[f"U_b{bid}_q{q}"]
+                if strict:
+                    assert np.array_equal(a, r), (name, bid, q)
+                else:
+                    scale = vscale if q in (1, 2, 3) and len(arrs) == 5 or q in (1, 2) else np.abs(r).max()
+                    assert np.max(np.abs(a - r)) <= 1.0e-10 * max(scale, 1e-300), (name, bid, q)
+        dt = np.array(sim.dt_history)
+        assert np.max(np.abs(dt - ref["dt_history"]) / ref["dt_history"]) < 1.0e-9
+        sim.close()

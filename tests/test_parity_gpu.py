@@ -132,6 +132,15 @@ def test_tuned_and_generic_kernels_agree(product, case):
     assert s1.dt_history == s2.dt_history
 
 
+@pytest.mark.parametrize("flux", ["ausmdv", "hanel", "ldfss2", "ausm_plus_up"])
+@pytest.mark.parametrize("sheared", [False, True])
+def test_thermally_perfect_five_species(oracle, product, flux, sheared):
+    """C5 at test size: 5-species thermally perfect air, frozen chemistry; Newton temperature
+    solves at both sides of every face and in every decode.  Not bit-comparable (CUDA's log() and
+    glibc's differ in the last place), so both builds are held to the 1e-10 tolerance."""
+    _compare(cases.tpg_box3d, oracle, product, 5, expect_bitwise=False, n=12, nb=2, flux_calculator=flux, sheared=sheared)
+
+
 def test_step_failure_and_retry(product):
     """A time step that is far too large must come back as 'failed, state intact' and the
     host policy then retries with dt*0.2 (simcore_gasdynamic_step.d:995-999)."""
