@@ -629,21 +629,23 @@ int eb200_commit(int sim)
     }
     s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (s->cfg.reserved_i[1] ? 4 : 0);
     {
-        // k-chunking (3D): enough CTAs to fill 148 SMs several times over, else whole columns
+        // k-chunking (3D): a CTA marches over `chunk` planes of its tile.  Aim at >= 20 waves of CTAs
+        // (148 SMs x 2 resident CTAs) so that the last, partly filled wave costs little; every chunk
+        // adds one redundant k-face per column, so chunks are kept >= 16 planes.
         long long tiles_plane = 0;
         for (size_t n = 0; n < s->local.size(); ++n) {
             EbBlockDesc& D = s->hdesc[n];
             D.tiles_i = (D.nic + 31) / 32; D.tiles_j = (D.njc + EB_TILE_Y - 1) / EB_TILE_Y;
             tiles_plane += (long long)D.tiles_i * D.tiles_j;
         }
-        const long long want = 148LL * 8;
+        const long long want = 148LL * 2 * 20;
         long long tile0 = 0;
         for (size_t n = 0; n < s->local.size(); ++n) {
             EbBlockDesc& D = s->hdesc[n];
             int chunk = D.nkc;
             if (s->threeD && tiles_plane < want) {
                 long long nch = (want + tiles_plane - 1) / tiles_plane;
-                chunk = (int)std::max<long long>(8, (D.nkc + nch - 1) / nch);
+                chunk = (int)std::max<long long>(16, (D.nkc + nch - 1) / nch);
                 chunk = std::min(chunk, D.nkc);
             }
             D.chunk_m = s->threeD ? chunk : 1;
@@ -702,22 +704,28 @@ int eb200_commit(int sim)
                 Block* ot = get_blk(s, bc.other_blk);
                 if (!ot) { set_err("block %d face %d: neighbour block %d was not declared", b->id, f, bc.other_blk); return -1; }
                 std::vector<int> recv_list, send_list;
+                std::vector<std::pair<long long, int>> recv_keyed, send_keyed;   // (receiver's cell index in its block, arena index)
                 int err = 0;
                 for_face_ghosts(s, b, f, [&](int t1, int t2, int layer, long long, long long ghost, long long, long long) {
                     int ijk[3];
                     if (full_face_source(s, f, ot, bc.other_face, t1, t2, layer, ijk)) { err = 1; return; }
                     if (ot->local) copy.push_back({ (int)(b->cell0 + ghost), (int)(ot->cell0 + ot->cidx(ijk[0], ijk[1], ijk[2])) });
-                    else recv_list.push_back((int)(b->cell0 + ghost));
+                    else recv_keyed.push_back({ ghost, (int)(b->cell0 + ghost) });
                 });
                 if (err) return -1;
                 if (!ot->local) {
                     // what the neighbour needs from me: its ghost cells behind (ot, other_face), in ITS order
-                    for_face_ghosts(s, ot, bc.other_face, [&](int t1, int t2, int layer, long long, long long, long long, long long) {
+                    for_face_ghosts(s, ot, bc.other_face, [&](int t1, int t2, int layer, long long, long long ghost, long long, long long) {
                         int ijk[3];
                         if (full_face_source(s, bc.other_face, b, f, t1, t2, layer, ijk)) { err = 1; return; }
-                        send_list.push_back((int)(b->cell0 + b->cidx(ijk[0], ijk[1], ijk[2])));
+                        send_keyed.push_back({ ghost, (int)(b->cell0 + b->cidx(ijk[0], ijk[1], ijk[2])) });
                     });
                     if (err) return -1;
+                    // wire order of a face set: ascending cell index of the RECEIVING block (both sides can compute it)
+                    std::sort(recv_keyed.begin(), recv_keyed.end());
+                    std::sort(send_keyed.begin(), send_keyed.end());
+                    for (auto& e : recv_keyed) recv_list.push_back(e.second);
+                    for (auto& e : send_keyed) send_list.push_back(e.second);
                     recv_sets[ot->owner].push_back({ { b->id, f }, recv_list });
                     send_sets[ot->owner].push_back({ { ot->id, bc.other_face }, send_list });
                 }
@@ -738,6 +746,10 @@ int eb200_commit(int sim)
             }
         }
     }
+    // order the work by destination address: neighbouring threads then touch neighbouring ghost cells
+    std::sort(copy.begin(), copy.end(), [](const EbCopyItem& a, const EbCopyItem& b) { return a.dst < b.dst; });
+    std::sort(refl.begin(), refl.end(), [](const EbReflectItem& a, const EbReflectItem& b) { return a.dst < b.dst; });
+    std::sort(fill.begin(), fill.end(), [](const EbFillItem& a, const EbFillItem& b) { return a.dst < b.dst; });
     s->ncopy = (long long)copy.size(); s->nrefl = (long long)refl.size(); s->nfill = (long long)fill.size();
     if (dev_upload(s, &s->d_copy, copy)) return -100;
     if (dev_upload(s, &s->d_refl, refl)) return -100;
