@@ -336,7 +336,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        try:     # halo messages on a high-priority NCCL stream: they run beside the interior tiles
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+        except Exception:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     main_res = run_gpu_workload(args, args.workload, rank, world, local_rank, with_e2e=True)
     also = {}
     if world == 1 and args.workload == "box3d" and not args.no_also:

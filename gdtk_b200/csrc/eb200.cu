@@ -88,6 +88,11 @@ struct Sim {
     int* d_status = nullptr; int* h_status = nullptr;
     unsigned long long* d_red = nullptr; double* d_last = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;       // halo traffic of other ranks, overlapped with interior tiles
+    cudaStream_t bnd_stream = nullptr;        // boundary tiles: start when the halo is in, run under the interior launch's tail
+    cudaEvent_t ev_pack = nullptr, ev_comm = nullptr, ev_ghost = nullptr, ev_bnd = nullptr;
+    int* d_tiles_int = nullptr; long long n_tiles_int = 0;   // tiles that read no ghost cell of another rank
+    int* d_tiles_bnd = nullptr; long long n_tiles_bnd = 0;   // tiles that do
     int cur = 0;                              // index of the primitive buffer holding the current state
     int U0 = 0;                               // index of the U level that currently plays U[0]
     std::vector<int> Ulev;                    // permutation of U levels (swap at the end of a step)
@@ -352,29 +357,38 @@ int drain_flux_events(Sim* s)
         (s)->launches++;                                              \
     } while (0)
 
-// Ghost cells of the buffer that holds the current state: exchange with other processes,
-// then same-GPU copies and boundary conditions (phases 02 and 03 of the reference step).
-int fill_ghost_cells(Sim* s, double* prim)
+// Halo traffic with other processes (phase 02 of the reference step): pack on the main stream,
+// then callback + unpack on the communication stream so that the main stream can meanwhile work on
+// tiles that do not touch those ghost cells.  ev_comm is recorded when the ghost cells are in place.
+int exchange_remote(Sim* s, double* prim)
 {
-    if (!s->peers.empty()) {
-        if (!s->exchange) { set_err("blocks on other ranks are connected but no exchange callback is installed"); return -5; }
-        const int np = (int)s->peers.size();
-        std::vector<int> ranks(np);
-        std::vector<double*> sp(np), rp(np);
-        std::vector<long long> sc(np), rc(np);
-        for (int p = 0; p < np; ++p) {
-            Peer& pr = s->peers[p];
-            MODE_CALL(s, launch_pack, s->P, prim, pr.d_send_idx, (long long)pr.send_idx.size(), pr.d_send, s->stream);
-            ranks[p] = pr.rank; sp[p] = pr.d_send; rp[p] = pr.d_recv;
-            sc[p] = (long long)pr.send_idx.size() * s->P.nprim; rc[p] = (long long)pr.recv_idx.size() * s->P.nprim;
-        }
-        int rc_cb = s->exchange(s->exchange_user, np, ranks.data(), sp.data(), sc.data(), rp.data(), rc.data(), (void*)s->stream);
-        if (rc_cb != 0) { set_err("exchange callback failed (%d)", rc_cb); return -6; }
-        for (int p = 0; p < np; ++p) {
-            Peer& pr = s->peers[p];
-            MODE_CALL(s, launch_unpack, s->P, prim, pr.d_recv_idx, (long long)pr.recv_idx.size(), pr.d_recv, s->stream);
-        }
+    if (s->peers.empty()) return 0;
+    if (!s->exchange) { set_err("blocks on other ranks are connected but no exchange callback is installed"); return -5; }
+    const int np = (int)s->peers.size();
+    std::vector<int> ranks(np);
+    std::vector<double*> sp(np), rp(np);
+    std::vector<long long> sc(np), rc(np);
+    for (int p = 0; p < np; ++p) {
+        Peer& pr = s->peers[p];
+        MODE_CALL(s, launch_pack, s->P, prim, pr.d_send_idx, (long long)pr.send_idx.size(), pr.d_send, s->stream);
+        ranks[p] = pr.rank; sp[p] = pr.d_send; rp[p] = pr.d_recv;
+        sc[p] = (long long)pr.send_idx.size() * s->P.nprim; rc[p] = (long long)pr.recv_idx.size() * s->P.nprim;
     }
+    CUDA_OK(cudaEventRecord(s->ev_pack, s->stream));
+    CUDA_OK(cudaStreamWaitEvent(s->comm_stream, s->ev_pack, 0));
+    int rc_cb = s->exchange(s->exchange_user, np, ranks.data(), sp.data(), sc.data(), rp.data(), rc.data(), (void*)s->comm_stream);
+    if (rc_cb != 0) { set_err("exchange callback failed (%d)", rc_cb); return -6; }
+    for (int p = 0; p < np; ++p) {
+        Peer& pr = s->peers[p];
+        MODE_CALL(s, launch_unpack, s->P, prim, pr.d_recv_idx, (long long)pr.recv_idx.size(), pr.d_recv, s->comm_stream);
+    }
+    CUDA_OK(cudaEventRecord(s->ev_comm, s->comm_stream));
+    return 0;
+}
+
+// Same-GPU full-face copies and boundary conditions (phases 02/03 of the reference step).
+int fill_local_ghost_cells(Sim* s, double* prim)
+{
     if (s->ncopy + s->nrefl + s->nfill > 0)
         MODE_CALL(s, launch_ghosts, s->P, s->d_desc, s->A, prim, s->d_copy, s->ncopy, s->d_refl, s->nrefl, s->d_fill, s->nfill, s->d_params, s->stream);
     return 0;
@@ -391,7 +405,9 @@ int enqueue_step(Sim* s, double dt)
         const int out_buf = work[(stage - 1) & 1];
         double* prim_in = s->A.prim[in_buf];
         double* prim_out = s->A.prim[out_buf];
-        int rc = fill_ghost_cells(s, prim_in);
+        int rc = exchange_remote(s, prim_in);
+        if (rc) return rc;
+        rc = fill_local_ghost_cells(s, prim_in);
         if (rc) return rc;
         EbStageArgs S;
         memset(&S, 0, sizeof S);
@@ -407,9 +423,26 @@ int enqueue_step(Sim* s, double dt)
         cudaEvent_t e0, e1;
         if (record_flux_events(s, &e0, &e1)) return -100;
         if (e0) CUDA_OK(cudaEventRecord(e0, s->stream));
-        if (s->cfg.strict_fp) eb_strict::launch_flux_update(s->cfg.flux_calculator, s->cfg.gas_model, s->P, s->d_gas, s->d_desc, (int)s->hdesc.size(), s->ncta, s->A, S, s->which, s->stream);
-        else eb_fast::launch_flux_update(s->cfg.flux_calculator, s->cfg.gas_model, s->P, s->d_gas, s->d_desc, (int)s->hdesc.size(), s->ncta, s->A, S, s->which, s->stream);
-        s->launches += ((s->which & 1) ? 1 : 0) + ((s->which & 2) ? 1 : 0);
+        auto launch = [&](const int* tiles, long long n, cudaStream_t st) {
+            if (n <= 0) return;
+            S.tile_list = tiles;
+            if (s->cfg.strict_fp) eb_strict::launch_flux_update(s->cfg.flux_calculator, s->cfg.gas_model, s->P, s->d_gas, s->d_desc, (int)s->hdesc.size(), n, s->A, S, s->which, st);
+            else eb_fast::launch_flux_update(s->cfg.flux_calculator, s->cfg.gas_model, s->P, s->d_gas, s->d_desc, (int)s->hdesc.size(), n, s->A, S, s->which, st);
+            s->launches += ((s->which & 1) ? 1 : 0) + ((s->which & 2) ? 1 : 0);
+        };
+        if (s->peers.empty()) {
+            launch(nullptr, s->ncta, s->stream);
+        } else {
+            // interior tiles now (they overlap with the halo traffic); boundary tiles on their own stream as
+            // soon as the halo and the local ghost cells are in, so that they fill in under the interior tail
+            CUDA_OK(cudaEventRecord(s->ev_ghost, s->stream));
+            launch(s->d_tiles_int, s->n_tiles_int, s->stream);
+            CUDA_OK(cudaStreamWaitEvent(s->bnd_stream, s->ev_ghost, 0));
+            CUDA_OK(cudaStreamWaitEvent(s->bnd_stream, s->ev_comm, 0));
+            launch(s->d_tiles_bnd, s->n_tiles_bnd, s->bnd_stream);
+            CUDA_OK(cudaEventRecord(s->ev_bnd, s->bnd_stream));
+            CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_bnd, 0));
+        }
         if (e1) CUDA_OK(cudaEventRecord(e1, s->stream));
         CUDA_OK(cudaGetLastError());
         in_buf = out_buf;
@@ -499,6 +532,16 @@ int eb200_init(const eb200_config* cfg)
         }
     }
     CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;                       // halo traffic gets the highest stream priority
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_OK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, hi));
+    }
+    CUDA_OK(cudaStreamCreateWithFlags(&s->bnd_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&s->ev_ghost, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s->ev_bnd, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s->ev_pack, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
     for (int l = 0; l <= s->n_stages; ++l) s->Ulev.push_back(l);
     int h = -1;
     for (size_t i = 0; i < g_sims.size(); ++i) if (!g_sims[i]) { h = (int)i; break; }
@@ -515,6 +558,12 @@ int eb200_finalize(int sim)
     for (void* p : s->allocs) cudaFree(p);
     for (auto& e : s->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (s->h_status) cudaFreeHost(s->h_status);
+    if (s->comm_stream) { cudaStreamSynchronize(s->comm_stream); cudaStreamDestroy(s->comm_stream); }
+    if (s->bnd_stream) { cudaStreamSynchronize(s->bnd_stream); cudaStreamDestroy(s->bnd_stream); }
+    if (s->ev_ghost) cudaEventDestroy(s->ev_ghost);
+    if (s->ev_bnd) cudaEventDestroy(s->ev_bnd);
+    if (s->ev_pack) cudaEventDestroy(s->ev_pack);
+    if (s->ev_comm) cudaEventDestroy(s->ev_comm);
     if (s->stream) cudaStreamDestroy(s->stream);
     g_sims[sim].reset();
     return 0;
@@ -768,6 +817,27 @@ int eb200_commit(int sim)
         if (dev_alloc(s, &p.d_send, p.send_idx.size() * (size_t)nprim)) return -100;
         if (dev_alloc(s, &p.d_recv, p.recv_idx.size() * (size_t)nprim)) return -100;
         s->peers.push_back(std::move(p));
+    }
+    if (!s->peers.empty()) {
+        // tiles whose stencils reach ghost cells filled by another rank go last (after the halo arrived)
+        std::vector<int> t_int, t_bnd;
+        for (size_t n = 0; n < s->local.size(); ++n) {
+            const Block* b = s->local[n];
+            const EbBlockDesc& D = s->hdesc[n];
+            bool remote[6] = { false, false, false, false, false, false };
+            for (int f = 0; f < s->nfaces; ++f)
+                if (b->bc[f].kind == EB200_BC_EXCHANGE_FULL_FACE) { Block* ot = get_blk(s, b->bc[f].other_blk); remote[f] = ot && !ot->local; }
+            for (int tm = 0; tm < D.tiles_m; ++tm) for (int tj = 0; tj < D.tiles_j; ++tj) for (int ti = 0; ti < D.tiles_i; ++ti) {
+                const bool bnd = (remote[EB200_WEST] && ti == 0) || (remote[EB200_EAST] && ti == D.tiles_i - 1) ||
+                                 (remote[EB200_SOUTH] && tj == 0) || (remote[EB200_NORTH] && tj == D.tiles_j - 1) ||
+                                 (remote[EB200_BOTTOM] && tm == 0) || (remote[EB200_TOP] && tm == D.tiles_m - 1);
+                const int id = (int)(D.tile0 + ((long long)tm * D.tiles_j + tj) * D.tiles_i + ti);
+                (bnd ? t_bnd : t_int).push_back(id);
+            }
+        }
+        s->n_tiles_int = (long long)t_int.size(); s->n_tiles_bnd = (long long)t_bnd.size();
+        if (dev_upload(s, &s->d_tiles_int, t_int)) return -100;
+        if (dev_upload(s, &s->d_tiles_bnd, t_bnd)) return -100;
     }
     CUDA_OK(cudaStreamSynchronize(s->stream));
     // host geometry copies are no longer needed

@@ -91,6 +91,7 @@ struct EbStageArgs {
     double dt_g[4];                        // stage 1: dt*g0 ; stage>1: g[0..2] and dt in [3]
     int stage, n_stages;
     int* status;                           // [0] step-failed flag, [1..4] invalid-cell count per stage
+    const int* tile_list;                  // CTA -> tile id (nullptr: identity); used to run interior tiles first
 };
 
 // ghost-cell work lists (indices into the arena)

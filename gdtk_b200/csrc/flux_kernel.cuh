@@ -184,24 +184,31 @@ __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __rest
 
 // Stage update (simcore_gasdynamic_step.d:1250-1357) + decode_conserved (fvcell.d:586-821) +
 // check_data (fluidblock.d:607-675) for one cell whose residual dUdt[] is complete.
+// U0pre / d0pre: U0 and dUdt_prev[0] of the cell if the caller loaded them ahead of time (else nullptr)
 template <int DIM, int GASM, int NSP>
 __device__ __forceinline__ void finish_cell(const EbParams& P, const EbGas* __restrict__ gas, const EbStageArgs& S,
-                                            long long total, long long c, const double* dUdt, bool& fail, int& n_invalid)
+                                            long long total, long long c, const double* dUdt, bool& fail, int& n_invalid,
+                                            const double* U0pre = nullptr, const double* d0pre = nullptr)
 {
     constexpr int NCQ = Layout<DIM, NSP>::NCQ;
-    double U[NCQ];
+    double U[NCQ], U0[NCQ], d0[NCQ];
+#pragma unroll
+    for (int q = 0; q < NCQ; ++q) {
+        U0[q] = U0pre ? U0pre[q] : ldg(S.U0 + q * total + c);
+        d0[q] = (S.stage == 1) ? 0.0 : (d0pre ? d0pre[q] : ldg(S.dUdt_prev[0] + q * total + c));
+    }
     if (S.stage == 1) {
 #pragma unroll
-        for (int q = 0; q < NCQ; ++q) U[q] = ldg(S.U0 + q * total + c) + S.dt_g[0] * dUdt[q];
+        for (int q = 0; q < NCQ; ++q) U[q] = U0[q] + S.dt_g[0] * dUdt[q];
     } else if (S.stage == 2) {
 #pragma unroll
         for (int q = 0; q < NCQ; ++q)
-            U[q] = ldg(S.U0 + q * total + c) + S.dt_g[3] * (S.dt_g[0] * ldg(S.dUdt_prev[0] + q * total + c) + S.dt_g[1] * dUdt[q]);
+            U[q] = U0[q] + S.dt_g[3] * (S.dt_g[0] * d0[q] + S.dt_g[1] * dUdt[q]);
     } else {
 #pragma unroll
         for (int q = 0; q < NCQ; ++q)
-            U[q] = ldg(S.U0 + q * total + c) + S.dt_g[3] * (S.dt_g[0] * ldg(S.dUdt_prev[0] + q * total + c) +
-                                                             S.dt_g[1] * ldg(S.dUdt_prev[1] + q * total + c) + S.dt_g[2] * dUdt[q]);
+            U[q] = U0[q] + S.dt_g[3] * (S.dt_g[0] * d0[q] +
+                                        S.dt_g[1] * ldg(S.dUdt_prev[1] + q * total + c) + S.dt_g[2] * dUdt[q]);
     }
     if (S.dUdt_out) {
 #pragma unroll
@@ -236,7 +243,7 @@ flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBloc
 
     const int lane = threadIdx.x, wy = threadIdx.y;
     const int tid = wy * 32 + lane;
-    const long long cta = blockIdx.x;
+    const long long cta = S.tile_list ? (long long)S.tile_list[blockIdx.x] : (long long)blockIdx.x;
     if (tid == 0) {
         int lo = 0, hi = nblocks - 1;
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (descs[mid].tile0 <= cta) lo = mid; else hi = mid - 1; }

@@ -342,7 +342,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
 
     const int lane = threadIdx.x, wy = threadIdx.y;
     const int tid = wy * 32 + lane;
-    const long long cta = blockIdx.x;
+    const long long cta = S.tile_list ? (long long)S.tile_list[blockIdx.x] : (long long)blockIdx.x;
     if (tid == 0) {
         int lo = 0, hi = nblocks - 1;
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (descs[mid].tile0 <= cta) lo = mid; else hi = mid - 1; }
