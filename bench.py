@@ -188,11 +188,18 @@ def run_gpu_workload(args, workload, rank, world, local_rank, with_e2e):
     # dominant kernel: the fused flux+update kernel, 2 launches (stages) per step per rank
     flux_bytes = balg * ncells_local * args.steps            # algorithmic bytes this rank's launches moved
     achieved = flux_bytes / (flux_ms * 1e-3) / 1e9 if flux_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch: bytes per cell measured by `ncu --set full`
+    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json) x the cells one launch processes
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if workload == "box3d" and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["dram_bytes_per_cell_per_launch"] * ncells_local
     result = {
         "name": name, "value": value, "ms": ms, "ncells": ncells, "dt": dt, "launches": launches,
         "setup_s": t_setup, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "flux_update_kernel",
+                     "traffic": traffic, "traffic_note": "ncu dram bytes per cell (256^3 capture, profiles/r1_traffic.json) x cells per launch; algorithmic = 140 B per cell per launch (280 B per cell-update over the 2 stage launches)", "peak_source": peak_src, "kernel": "flux_update_kernel",
                      "algorithmic_bytes_per_cell_update": balg, "kernel_ms_per_launch": flux_ms / max(1, flux_n),
                      "kernel_share_of_step": flux_ms / ms if ms > 0 else None},
     }
