@@ -22,6 +22,7 @@ FACE_NAMES = ["west", "east", "south", "north", "bottom", "top"]
 # config.flux_calculator names (reference src/eilmer/globalconfig.d:293-345)
 FLUX_CALCULATORS = {
     "ausmdv": 0, "hanel": 1, "ldfss0": 2, "ldfss2": 3, "ausm_plus_up": 4, "roe": 5,
+    "adaptive_hanel_ausmdv": 6, "adaptive_hanel_ausm_plus_up": 7, "adaptive_ldfss0_ldfss2": 8,
 }
 # config.gasdynamic_update_scheme names (reference src/eilmer/globalconfig.d:126-200)
 UPDATE_SCHEMES = {
@@ -74,10 +75,12 @@ class Config(C.Structure):
         ("min_temp", C.c_double),
         ("suggested_low_T_value", C.c_double),
         ("ignore_low_T_thermo_update_failure", C.c_int),
-        ("reserved_j", C.c_int),
+        ("strict_shock_detector", C.c_int),
         ("ideal_mol_mass", C.c_double),
         ("ideal_gamma", C.c_double),
-        ("reserved_d", C.c_double * 6),
+        ("compression_tolerance", C.c_double),
+        ("shear_tolerance", C.c_double),
+        ("reserved_d", C.c_double * 4),
         ("species", Species * MAX_SPECIES),
     ]
 

@@ -370,9 +370,10 @@ int exchange_remote(Sim* s, double* prim)
     std::vector<long long> sc(np), rc(np);
     for (int p = 0; p < np; ++p) {
         Peer& pr = s->peers[p];
-        MODE_CALL(s, launch_pack, s->P, prim, pr.d_send_idx, (long long)pr.send_idx.size(), pr.d_send, s->stream);
+        MODE_CALL(s, launch_pack, s->P, prim, s->A.S, pr.d_send_idx, (long long)pr.send_idx.size(), pr.d_send, s->stream);
         ranks[p] = pr.rank; sp[p] = pr.d_send; rp[p] = pr.d_recv;
-        sc[p] = (long long)pr.send_idx.size() * s->P.nprim; rc[p] = (long long)pr.recv_idx.size() * s->P.nprim;
+        const int nv = s->P.nprim + (s->P.shock_detect ? 1 : 0);
+        sc[p] = (long long)pr.send_idx.size() * nv; rc[p] = (long long)pr.recv_idx.size() * nv;
     }
     CUDA_OK(cudaEventRecord(s->ev_pack, s->stream));
     CUDA_OK(cudaStreamWaitEvent(s->comm_stream, s->ev_pack, 0));
@@ -380,7 +381,7 @@ int exchange_remote(Sim* s, double* prim)
     if (rc_cb != 0) { set_err("exchange callback failed (%d)", rc_cb); return -6; }
     for (int p = 0; p < np; ++p) {
         Peer& pr = s->peers[p];
-        MODE_CALL(s, launch_unpack, s->P, prim, pr.d_recv_idx, (long long)pr.recv_idx.size(), pr.d_recv, s->comm_stream);
+        MODE_CALL(s, launch_unpack, s->P, prim, s->A.S, pr.d_recv_idx, (long long)pr.recv_idx.size(), pr.d_recv, s->comm_stream);
     }
     CUDA_OK(cudaEventRecord(s->ev_comm, s->comm_stream));
     return 0;
@@ -409,6 +410,14 @@ int enqueue_step(Sim* s, double dt)
         if (rc) return rc;
         rc = fill_local_ghost_cells(s, prim_in);
         if (rc) return rc;
+        if (s->P.shock_detect && stage == 1) {
+            // detect_shocks (phase 04) needs every ghost cell: wait for the halo of other ranks first
+            if (!s->peers.empty()) CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
+            for (Block* b : s->local) {
+                MODE_CALL(s, launch_detect_shocks, s->P, s->hdesc[b->local_index], s->A, prim_in, s->stream);
+                s->launches += s->P.strict_shock ? 2 : 1;
+            }
+        }
         EbStageArgs S;
         memset(&S, 0, sizeof S);
         S.prim_in = prim_in; S.prim_out = prim_out;
@@ -482,9 +491,14 @@ int eb200_init(const eb200_config* cfg)
     if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT && cfg->dimensions != 3) {
         set_err("thermally perfect gas: kernels are built for 3D only"); return -1;
     }
-    if (cfg->flux_calculator < 0 || cfg->flux_calculator > 5) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
+    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
     if (cfg->flux_calculator == EB200_FLUX_ROE && cfg->n_species > 1) { set_err("roe with multiple species is not on this path yet"); return -1; }
     if (!n_stages_for(cfg->update_scheme)) { set_err("unsupported update scheme %d", cfg->update_scheme); return -1; }
+    const bool adaptive = cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV;
+    if (adaptive && cfg->compression_tolerance > 0.0) { set_err("compression_tolerance should be negative!"); return -1; }
+    if (adaptive && cfg->n_species > 1 && cfg->flux_calculator != EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) {
+        set_err("thermally perfect gas: of the adaptive flux calculators only adaptive_hanel_ausmdv is built"); return -1;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_err("no CUDA device available: eb200 has no CPU fallback");
@@ -507,6 +521,8 @@ int eb200_init(const eb200_config* cfg)
     P.entropy_fix = cfg->apply_entropy_fix; P.ignore_low_T = cfg->ignore_low_T_thermo_update_failure;
     P.eps_va = cfg->epsilon_van_albada; P.M_inf = cfg->M_inf; P.max_velocity = cfg->max_velocity;
     P.max_temp = cfg->max_temp; P.min_temp = cfg->min_temp; P.low_T = cfg->suggested_low_T_value;
+    P.shock_detect = adaptive ? 1 : 0; P.strict_shock = cfg->strict_shock_detector;
+    P.comp_tol = cfg->compression_tolerance; P.shear_tol = cfg->shear_tolerance;
     EbGas& g = s->hgas; memset(&g, 0, sizeof g);
     g.model = cfg->gas_model; g.nsp = cfg->n_species;
     if (cfg->gas_model == EB200_GAS_IDEAL) {
@@ -708,6 +724,10 @@ int eb200_commit(int sim)
     for (int p = 0; p < 3; ++p) if (dev_alloc(s, &s->A.prim[p], (size_t)nprim * total)) return -100;
     for (int l = 0; l <= ns; ++l) if (dev_alloc(s, &s->A.U[l], (size_t)ncq * total)) return -100;
     for (int l = 0; l < ns - 1; ++l) if (dev_alloc(s, &s->A.dUdt[l], (size_t)ncq * total)) return -100;   // residuals needed by later stages
+    if (s->P.shock_detect) {
+        if (dev_alloc(s, &s->A.S, (size_t)total)) return -100;
+        for (int d = 0; d < dims; ++d) if (dev_alloc(s, &s->A.Sf[d], (size_t)total)) return -100;
+    }
     if (any_general) {
         if (dev_alloc(s, &s->A.vol, (size_t)total)) return -100;
         if (s->cfg.axisymmetric) if (dev_alloc(s, &s->A.areaxy, (size_t)total)) return -100;
@@ -814,8 +834,8 @@ int eb200_commit(int sim)
         for (auto& e : ss) p.send_idx.insert(p.send_idx.end(), e.second.begin(), e.second.end());
         if (dev_upload(s, &p.d_send_idx, p.send_idx)) return -100;
         if (dev_upload(s, &p.d_recv_idx, p.recv_idx)) return -100;
-        if (dev_alloc(s, &p.d_send, p.send_idx.size() * (size_t)nprim)) return -100;
-        if (dev_alloc(s, &p.d_recv, p.recv_idx.size() * (size_t)nprim)) return -100;
+        if (dev_alloc(s, &p.d_send, p.send_idx.size() * (size_t)(nprim + 1))) return -100;
+        if (dev_alloc(s, &p.d_recv, p.recv_idx.size() * (size_t)(nprim + 1))) return -100;
         s->peers.push_back(std::move(p));
     }
     if (!s->peers.empty()) {

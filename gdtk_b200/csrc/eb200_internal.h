@@ -72,7 +72,9 @@ struct EbParams {            // passed by value to kernels (kept small)
     int interpolation_order, apply_limiter, extrema_clipping, local_frame, entropy_fix;
     int ignore_low_T;
     int iZMom, iEnergy, iSpecies;
+    int shock_detect, strict_shock;       // adaptive flux calculators: PJ shock detector on
     double eps_va, M_inf, max_velocity, max_temp, min_temp, low_T;
+    double comp_tol, shear_tol;
     long long total;          // arena length (field stride)
 };
 
@@ -81,6 +83,8 @@ struct EbArena {             // device pointers
     double* U[5];
     double* dUdt[4];
     double* vol; double* areaxy; double* len[3]; double* face[3];
+    double* S;                 // FlowState.S of cells incl. ghost cells (shock detector), one copy
+    double* Sf[3];             // IFace.fs.S per direction
 };
 
 struct EbStageArgs {
@@ -119,10 +123,12 @@ struct EbFillItem { int dst, param; };
                        const EbCopyItem* copy, long long ncopy, const EbReflectItem* refl,               \
                        long long nrefl, const EbFillItem* fill, long long nfill, const double* params,   \
                        cudaStream_t st);                                                                 \
-    void launch_pack(const EbParams& P, const double* prim, const int* idx, long long n, double* buf,    \
-                     cudaStream_t st);                                                                   \
-    void launch_unpack(const EbParams& P, double* prim, const int* idx, long long n, const double* buf,  \
-                       cudaStream_t st);                                                                 \
+    void launch_pack(const EbParams& P, const double* prim, const double* S, const int* idx, long long n, \
+                     double* buf, cudaStream_t st);                                                      \
+    void launch_unpack(const EbParams& P, double* prim, double* S, const int* idx, long long n,          \
+                       const double* buf, cudaStream_t st);                                              \
+    void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A,             \
+                              const double* prim, cudaStream_t st);                                      \
     }
 
 EB_DECLARE_LAUNCHERS(eb_strict)

@@ -6,7 +6,8 @@
 #ifdef EB_NO_TPG
 #define EB_FLUX_HAS_TPG 0
 #else
-#define EB_FLUX_HAS_TPG (EB_FLUX != 5)   /* roe with several species is not on this path */
+#define EB_FLUX_HAS_TPG (EB_FLUX != 5 && EB_FLUX != 7 && EB_FLUX != 8)   /* roe with several species is not on this path;
+                                                                          of the adaptive ones only the default is built for TPG */
 #endif
 #include "flux_kernel.cuh"
 #include "flux_kernel_v2.cuh"

@@ -229,8 +229,8 @@ __device__ __forceinline__ void flux_components(const Prim<1>& L, const Prim<1>&
 // reconstructed velocities are renamed by d, and F comes back with momentum in (x,y,z) order.
 template <int DIM, int FLUX, bool CLIP, bool ROT>
 __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __restrict__ gas, const EbWeights& w,
-                                          Stencil& s, const Frame& fr, int d, const double* __restrict__ prim_fallback,
-                                          long long cL0, long long cR0, double* F)
+                                          Stencil& s, const Frame& fr, int d, double alpha,
+                                          const double* __restrict__ prim_fallback, long long cL0, long long cR0, double* F)
 {
     typedef Layout<DIM, 1> Lay;
     Prim<1> L, R;
@@ -267,7 +267,15 @@ __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __rest
 #ifdef EB_FAST_MATH
     if (!ROT && FLUX != EB200_FLUX_ROE) {
         // 2D i-faces have t1 = -y; the component form never looks at the sign of a tangential component
-        flux_components<DIM, FLUX>(L, R, d, P.entropy_fix != 0, P.M_inf, F);
+        if (FLUX <= EB200_FLUX_ROE) flux_components<DIM, FLUX>(L, R, d, P.entropy_fix != 0, P.M_inf, F);
+        else if (alpha > 0.0) {
+            if (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) flux_components<DIM, EB200_FLUX_LDFSS0>(L, R, d, false, P.M_inf, F);
+            else flux_components<DIM, EB200_FLUX_HANEL>(L, R, d, false, P.M_inf, F);
+        } else {
+            if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) flux_components<DIM, EB200_FLUX_AUSMDV>(L, R, d, P.entropy_fix != 0, P.M_inf, F);
+            else if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) flux_components<DIM, EB200_FLUX_AUSM_PLUS_UP>(L, R, d, false, P.M_inf, F);
+            else flux_components<DIM, EB200_FLUX_LDFSS2>(L, R, d, false, P.M_inf, F);
+        }
         return;
     }
 #endif
@@ -286,7 +294,15 @@ __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __rest
     else if (FLUX == EB200_FLUX_LDFSS0) flux_ldfss<DIM, 1, 0>(L, R, F);
     else if (FLUX == EB200_FLUX_LDFSS2) flux_ldfss<DIM, 1, 2>(L, R, F);
     else if (FLUX == EB200_FLUX_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, 1>(L, R, P.M_inf, F);
-    else flux_roe<DIM, 1>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
+    else if (FLUX == EB200_FLUX_ROE) flux_roe<DIM, 1>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
+    else if (alpha > 0.0) {   // adaptive calculators, fluxcalc.d:1332-1372 (alpha is 0 or 1 on this path)
+        if (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) flux_ldfss<DIM, 1, 0>(L, R, F);
+        else flux_hanel<DIM, 1>(L, R, F);
+    } else {
+        if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) flux_ausmdv<DIM, 1>(L, R, P.entropy_fix != 0, F);
+        else if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, 1>(L, R, P.M_inf, F);
+        else flux_ldfss<DIM, 1, 2>(L, R, F);
+    }
     if (!ROT) {              // momentum flux back to (x, y, z) order
         if (DIM == 3) {
             const double f0 = F[Lay::iXMom], f1 = F[Lay::iYMom], f2 = F[Lay::iZMom];
@@ -507,7 +523,8 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             }
             const EbWeights& w = CART ? D.w[d] : wl;
             double Fl[NCQ];
-            face_core<DIM, FLUX, CLIP, !CART>(P, gas, w, s, fr, d, S.prim_in, cf - st, cf, Fl);
+            const double alpha = (FLUX > EB200_FLUX_ROE) ? A.Sf[d][cf] : 0.0;
+            face_core<DIM, FLUX, CLIP, !CART>(P, gas, w, s, fr, d, alpha, S.prim_in, cf - st, cf, Fl);
             if (!CART) {     // momentum flux back to the global frame (fluxcalc.d:169-175)
                 double fx = Fl[Lay::iXMom], fy = Fl[Lay::iYMom], fz = (DIM == 3) ? Fl[Lay::iZMom] : 0.0;
                 to_global<DIM>(fr, fx, fy, fz);

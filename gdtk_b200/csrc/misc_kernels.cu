@@ -12,10 +12,12 @@ namespace EB_NS {
                                  int nblocks, long long ncta, const EbArena& A, const EbStageArgs& S,          \
                                  int tile_y, int which, cudaStream_t st);
 EB_DECL_FLUX(0) EB_DECL_FLUX(1) EB_DECL_FLUX(2) EB_DECL_FLUX(3) EB_DECL_FLUX(4) EB_DECL_FLUX(5)
+EB_DECL_FLUX(6) EB_DECL_FLUX(7) EB_DECL_FLUX(8)
 #define EB_DECL_DBG(k)                                                                                         \
     void launch_face_debug_k##k(const EbParams& P, int gas_model, const EbGas* gas, const EbArena& A,           \
                                 const double* prim, int nfaces, double* Fout, int* ok_out, cudaStream_t st);
 EB_DECL_DBG(0) EB_DECL_DBG(1) EB_DECL_DBG(2) EB_DECL_DBG(3) EB_DECL_DBG(4) EB_DECL_DBG(5)
+EB_DECL_DBG(6) EB_DECL_DBG(7) EB_DECL_DBG(8)
 
 void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* gas, const EbArena& A, const double* prim,
                        int nfaces, double* Fout, int* ok_out, cudaStream_t st)
@@ -27,6 +29,9 @@ void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* ga
     case 3: launch_face_debug_k3(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 4: launch_face_debug_k4(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 5: launch_face_debug_k5(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 6: launch_face_debug_k6(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 7: launch_face_debug_k7(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 8: launch_face_debug_k8(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     }
 }
 
@@ -43,6 +48,9 @@ void launch_flux_update(int flux_calc, int gm, const EbParams& P, const EbGas* g
     case 3: launch_flux_update_k3(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 4: launch_flux_update_k4(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 5: launch_flux_update_k5(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 6: launch_flux_update_k6(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 7: launch_flux_update_k7(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 8: launch_flux_update_k8(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     }
 }
 
@@ -205,6 +213,7 @@ __global__ void ghost_kernel(const EbParams P, const EbBlockDesc* __restrict__ d
     if (t < ncopy) {
         const EbCopyItem it = copy[t];
         for (int v = 0; v < nprim; ++v) prim[v * total + it.dst] = prim[v * total + it.src];
+        if (P.shock_detect) A.S[it.dst] = A.S[it.src];          // FlowState.S travels with the FlowState
     } else if (t < ncopy + nrefl) {
         const EbReflectItem it = refl[t - ncopy];
         for (int v = 0; v < nprim; ++v) {
@@ -223,9 +232,11 @@ __global__ void ghost_kernel(const EbParams P, const EbBlockDesc* __restrict__ d
             else { load_frame<2>(f, A.face[d], total, it.fidx); to_local<2>(f, x, y, z); x = -x; to_global<2>(f, x, y, z); }
         }
         prim[5 * total + it.dst] = x; prim[6 * total + it.dst] = y; prim[7 * total + it.dst] = z;
+        if (P.shock_detect) A.S[it.dst] = A.S[it.src];
     } else if (t < ncopy + nrefl + nfill) {
         const EbFillItem it = fill[t - ncopy - nrefl];
         for (int v = 0; v < nprim; ++v) prim[v * total + it.dst] = params[(long long)it.param * nprim + v];
+        if (P.shock_detect) A.S[it.dst] = 0.0;                  // S of a FlowState made in the job script
     }
 }
 
@@ -239,28 +250,116 @@ void launch_ghosts(const EbParams& P, const EbBlockDesc* desc, const EbArena& A,
     ghost_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(P, desc, A, prim, copy, ncopy, refl, nrefl, fill, nfill, params);
 }
 
-// halo pack / unpack for blocks owned by other processes: buf[v*n + t]
-__global__ void pack_kernel(long long total, int nprim, const double* __restrict__ prim, const int* __restrict__ idx, long long n, double* __restrict__ buf)
+// halo pack / unpack for blocks owned by other processes: buf[v*n + t]; with the shock detector on,
+// FlowState.S is variable number nprim
+__global__ void pack_kernel(long long total, int nprim, const double* __restrict__ prim, const double* __restrict__ S,
+                            const int* __restrict__ idx, long long n, double* __restrict__ buf)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const long long c = idx[t];
     for (int v = 0; v < nprim; ++v) buf[v * n + t] = prim[v * total + c];
+    if (S) buf[(long long)nprim * n + t] = S[c];
 }
-__global__ void unpack_kernel(long long total, int nprim, double* __restrict__ prim, const int* __restrict__ idx, long long n, const double* __restrict__ buf)
+__global__ void unpack_kernel(long long total, int nprim, double* __restrict__ prim, double* __restrict__ S,
+                              const int* __restrict__ idx, long long n, const double* __restrict__ buf)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const long long c = idx[t];
     for (int v = 0; v < nprim; ++v) prim[v * total + c] = buf[v * n + t];
+    if (S) S[c] = buf[(long long)nprim * n + t];
 }
-void launch_pack(const EbParams& P, const double* prim, const int* idx, long long n, double* buf, cudaStream_t st)
+void launch_pack(const EbParams& P, const double* prim, const double* S, const int* idx, long long n, double* buf, cudaStream_t st)
 {
-    if (n > 0) pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, P.nprim, prim, idx, n, buf);
+    if (n > 0) pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, P.nprim, prim, P.shock_detect ? S : nullptr, idx, n, buf);
 }
-void launch_unpack(const EbParams& P, double* prim, const int* idx, long long n, const double* buf, cudaStream_t st)
+void launch_unpack(const EbParams& P, double* prim, double* S, const int* idx, long long n, const double* buf, cudaStream_t st)
 {
-    if (n > 0) unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, P.nprim, prim, idx, n, buf);
+    if (n > 0) unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, P.nprim, prim, P.shock_detect ? S : nullptr, idx, n, buf);
+}
+
+// ---------------------------------------------------------------------------------------
+// detect_shocks (simcore_gasdynamic_step.d:3197-3224) with shock_detector_smoothing = 0, one block:
+//   pass 0  detect_shock_points  (fluidblock.d:479-520): PJ_ShockDetector (shockdetectors.d:22-93) on every face
+//   pass 1  shock_faces_to_cells (:573-583)
+//   pass 2  enforce_strict_shock_detector (:585-605); ghost-cell S is what the last ghost fill copied.
+// One thread per position of the block extended by one cell on the plus side of every direction.
+
+template <int DIM>
+__global__ void shock_kernel(const EbParams P, const EbBlockDesc D, const EbArena A, const double* __restrict__ prim, int pass)
+{
+    const int ei = D.nic + 1, ej = D.njc + 1, ek = (DIM == 3) ? D.nkc + 1 : 1;
+    const long long n = (long long)ei * ej * ek;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = (int)(t % ei), j = (int)((t / ei) % ej), k = (int)(t / ((long long)ei * ej));
+    const long long c = D.cell0 + ((long long)(k + D.kg) * D.NJ + (j + EB_NG)) * D.NI + (i + EB_NG);
+    const long long total = P.total;
+    const bool in_i = i < D.nic, in_j = j < D.njc, in_k = (DIM == 3) ? (k < D.nkc) : true;
+    if (pass == 1) {
+        if (!(in_i && in_j && in_k)) return;
+        double S = 0.0;                                    // iface order W,E,S,N,B,T
+        S = fmax(S, A.Sf[0][c]); S = fmax(S, A.Sf[0][c + 1]);
+        S = fmax(S, A.Sf[1][c]); S = fmax(S, A.Sf[1][c + D.stride[1]]);
+        if (DIM == 3) { S = fmax(S, A.Sf[2][c]); S = fmax(S, A.Sf[2][c + D.stride[2]]); }
+        A.S[c] = S;
+        return;
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        // the face on the minus-d side of this position exists if the other two indices are interior
+        const bool face_ok = (d == 0) ? (in_j && in_k) : ((d == 1) ? (in_i && in_k) : (in_i && in_j));
+        if (!face_ok) continue;
+        const long long st = D.stride[d];
+        if (pass == 0) {
+            const double vLx = ldg(prim + 5 * total + c - st), vLy = ldg(prim + 6 * total + c - st);
+            const double vLz = (DIM == 3) ? ldg(prim + 7 * total + c - st) : 0.0;
+            const double vRx = ldg(prim + 5 * total + c), vRy = ldg(prim + 6 * total + c);
+            const double vRz = (DIM == 3) ? ldg(prim + 7 * total + c) : 0.0;
+            const double aL = ldg(prim + 4 * total + c - st), aR = ldg(prim + 4 * total + c);
+            double n_[3], t1[3], t2[3];
+            if (D.cartesian) {
+                // reconstruct the exact +-1/0 frame of this direction from the descriptor
+                for (int m = 0; m < 3; ++m) { n_[m] = 0.0; t1[m] = 0.0; t2[m] = 0.0; }
+                n_[D.fr[d].perm[0]] = D.fr[d].neg[0] ? -1.0 : 1.0;
+                t1[D.fr[d].perm[1]] = D.fr[d].neg[1] ? -1.0 : 1.0;
+                t2[D.fr[d].perm[2]] = D.fr[d].neg[2] ? -1.0 : 1.0;
+            } else {
+                for (int m = 0; m < 3; ++m) {
+                    n_[m] = ldg(A.face[d] + m * total + c); t1[m] = ldg(A.face[d] + (3 + m) * total + c);
+                    t2[m] = ldg(A.face[d] + (6 + m) * total + c);
+                }
+            }
+            const double uL = vLx * n_[0] + vLy * n_[1] + vLz * n_[2];
+            const double uR = vRx * n_[0] + vRy * n_[1] + vRz * n_[2];
+            const double a_min = (aL < aR) ? aL : aR;
+            const double comp = ((uR - uL) / a_min);
+            const double vL = vLx * t1[0] + vLy * t1[1] + vLz * t1[2], vR = vRx * t1[0] + vRy * t1[1] + vRz * t1[2];
+            const double wL = vLx * t2[0] + vLy * t2[1] + vLz * t2[2], wR = vRx * t2[0] + vRy * t2[1] + vRz * t2[2];
+            const double sound_speed = 0.5 * (aL + aR);
+            const double shear_y = fabs(vL - vR) / sound_speed;
+            const double shear_z = fabs(wL - wR) / sound_speed;
+            const double shear = fmax(shear_y, shear_z);
+            A.Sf[d][c] = ((shear < P.shear_tol) && (comp < P.comp_tol)) ? 1.0 : 0.0;
+        } else {
+            double Sf = A.Sf[d][c];
+            if (Sf > 0.0 || A.S[c - st] > 0.0 || A.S[c] > 0.0) Sf = 1.0;
+            A.Sf[d][c] = Sf;
+        }
+    }
+}
+
+void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A, const double* prim, cudaStream_t st)
+{
+    const long long n = (long long)(hdesc.nic + 1) * (hdesc.njc + 1) * ((P.dims == 3) ? hdesc.nkc + 1 : 1);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    const int npass = P.strict_shock ? 3 : 2;
+    for (int pass = 0; pass < npass; ++pass) {
+        if (P.dims == 3) shock_kernel<3><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, pass);
+        else shock_kernel<2><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, pass);
+    }
 }
 
 }  // namespace EB_NS

@@ -42,6 +42,11 @@ class Config:
         self.apply_entropy_fix = True                      # :1088
         self.thermo_interpolator = "rhou"                  # :1073
         self.M_inf = 0.01                                  # :1114
+        self.compression_tolerance = -0.30                 # :1123 (PJ shock detector)
+        self.shear_tolerance = 0.20                        # :1108
+        self.strict_shock_detector = True                  # :1064
+        self.shock_detector = "PJ"                         # :1124
+        self.shock_detector_smoothing = 0                  # :1127
         self.gasdynamic_update_scheme = "predictor-corrector"  # :936
         self.cfl_value = 0.5
         self.cfl_count = 10                                # :1294
@@ -75,8 +80,12 @@ class Config:
         if fc not in _abi.FLUX_CALCULATORS:
             raise ValueError(
                 f"config.flux_calculator={fc!r} is not on the accelerated path; choose one of "
-                f"{sorted(_abi.FLUX_CALCULATORS)} (the reference default 'adaptive_hanel_ausmdv' needs the "
-                "shock detector, which is a 'next' row in SURVEY.md section 8f)")
+                f"{sorted(_abi.FLUX_CALCULATORS)}")
+        if fc.startswith("adaptive"):
+            if self.shock_detector != "PJ" or self.shock_detector_smoothing != 0:
+                raise ValueError("only the PJ shock detector without smoothing (the defaults) is on this path")
+            if self.compression_tolerance > 0.0:
+                raise ValueError("compression_tolerance should be negative!")
         if self.gasdynamic_update_scheme not in _abi.UPDATE_SCHEMES:
             raise ValueError(f"gasdynamic_update_scheme {self.gasdynamic_update_scheme!r} not supported")
         if self.interpolation_order not in (1, 2):
@@ -113,6 +122,9 @@ class Config:
         c.min_temp = self.flowstate_limits_min_temp
         c.suggested_low_T_value = self.suggested_low_T_value
         c.ignore_low_T_thermo_update_failure = int(self.ignore_low_T_thermo_update_failure)
+        c.strict_shock_detector = int(self.strict_shock_detector)
+        c.compression_tolerance = self.compression_tolerance
+        c.shear_tolerance = self.shear_tolerance
         gmodel.fill_config(c)
         return c
 

@@ -59,7 +59,14 @@ enum eb200_flux_calculator {
     EB200_FLUX_LDFSS0 = 2,        /* fluxcalc.d:819-914   */
     EB200_FLUX_LDFSS2 = 3,        /* fluxcalc.d:917-1025  */
     EB200_FLUX_AUSM_PLUS_UP = 4,  /* fluxcalc.d:1415-1602 */
-    EB200_FLUX_ROE = 5            /* fluxcalc.d:1929-2120 */
+    EB200_FLUX_ROE = 5,           /* fluxcalc.d:1929-2120 */
+    /* adaptive calculators (fluxcalc.d:1315-1412): the first scheme where the shock detector marks
+     * the face (IFace.fs.S = 1), the second elsewhere; they switch the shock detector on
+     * (configCheckPoint1, globalconfig.d:2676-2690; detect_shocks, simcore_gasdynamic_step.d:3197-3224,
+     * PJ_ShockDetector shockdetectors.d:22-93, fluidblock.d:479-605) */
+    EB200_FLUX_ADAPTIVE_HANEL_AUSMDV = 6,        /* the reference's default (globalconfig.d:1031) */
+    EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP = 7,
+    EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2 = 8
 };
 
 /* config.gasdynamic_update_scheme (src/eilmer/globalconfig.d:126-200);
@@ -152,11 +159,13 @@ typedef struct eb200_config {
     double min_temp;                /* 0 */
     double suggested_low_T_value;   /* 200; used when ignore_low_T_thermo_update_failure */
     int ignore_low_T_thermo_update_failure; /* 1 */
-    int reserved_j;
+    int strict_shock_detector;      /* 1 (globalconfig.d:1064); only read by the adaptive flux calculators */
     /* Ideal gas (src/gas/ideal_gas.d:43-69) */
     double ideal_mol_mass;          /* kg/mol */
     double ideal_gamma;
-    double reserved_d[6];
+    double compression_tolerance;   /* -0.30 (globalconfig.d:1123), PJ shock detector */
+    double shear_tolerance;         /* 0.20 (globalconfig.d:1108) */
+    double reserved_d[4];
     /* Thermally perfect gas mixture */
     eb200_species species[EB200_MAX_SPECIES];
 } eb200_config;

@@ -77,6 +77,8 @@ typedef struct {
     double *dUdt[MAXLEVELS];
     double *F[3];            /* face fluxes per direction, ncq arrays each */
     unsigned char *bad;      /* data_is_bad */
+    double *S;               /* FlowState.S of cells (incl. ghost cells), shock detector value */
+    double *Sf[3];           /* IFace.fs.S per direction */
     BC bc[6];
     int has_geometry, has_flow;
 } Blk;
@@ -98,6 +100,7 @@ typedef struct {
     Blk** recv_blk[64]; long* recv_cell[64];   /* my ghost cells filled by peer p */
     double* send_buf[64]; double* recv_buf[64];
     int lists_built;
+    int shock_detect;        /* do_shock_detect (set by the adaptive flux calculators) */
     int mutate_cell_vel;     /* reproduce e4 onedinterp.d:766-769,983-986 in-place round trips */
     int n_stages;
 } Sim;
@@ -907,7 +910,7 @@ static void roe(const Sim* s, const FS* Lft, const FS* Rght, double* F)
 
 /* fluxcalc.d:54-184 compute_interface_flux_interior (gvel = 0, omegaz = 0, no MHD).
  * Lft/Rght are tampered with, as in the reference.  F is in the global frame on return. */
-static void compute_interface_flux_interior(const Sim* s, FS* Lft, FS* Rght, const FaceGeo* g, double* F)
+static void compute_interface_flux_interior(const Sim* s, FS* Lft, FS* Rght, const FaceGeo* g, double alpha, double* F)
 {
     double gvx = 0.0, gvy = 0.0, gvz = 0.0;
     Lft->vx -= gvx; Lft->vy -= gvy; Lft->vz -= gvz;
@@ -922,6 +925,20 @@ static void compute_interface_flux_interior(const Sim* s, FS* Lft, FS* Rght, con
     case EB200_FLUX_LDFSS2: ldfss(s, Lft, Rght, F, 2); break;
     case EB200_FLUX_AUSM_PLUS_UP: ausm_plus_up(s, Lft, Rght, F); break;
     case EB200_FLUX_ROE: roe(s, Lft, Rght, F); break;
+    /* fluxcalc.d:1332-1372.  The detector on this path yields alpha = 0 or 1 (PJ, no smoothing), for which the
+     * `factor` argument of the reference's calculators is exactly 1. */
+    case EB200_FLUX_ADAPTIVE_HANEL_AUSMDV:
+        if (alpha > 0.0) hanel(s, Lft, Rght, F);
+        if (alpha < 1.0) ausmdv(s, Lft, Rght, F);
+        break;
+    case EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP:
+        if (alpha > 0.0) hanel(s, Lft, Rght, F);
+        if (alpha < 1.0) ausm_plus_up(s, Lft, Rght, F);
+        break;
+    case EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2:
+        if (alpha > 0.0) ldfss(s, Lft, Rght, F, 0);
+        if (alpha < 1.0) ldfss(s, Lft, Rght, F, 2);
+        break;
     }
     double v_sqr = gvx * gvx + gvy * gvy + gvz * gvz;
     F[s->iEnergy] += 0.5 * F[s->iMass] * v_sqr +
@@ -1004,7 +1021,7 @@ static int flux_sweep(const Sim* s, Blk* b, int d)
             FS inner; load_fs(s, b, on_hi ? c - st : c, &inner);
             compute_outflow_flux(s, &inner, outsign, &g, Fl);
         } else {
-            compute_interface_flux_interior(s, &Lft, &Rght, &g, Fl);
+            compute_interface_flux_interior(s, &Lft, &Rght, &g, b->Sf[d][c], Fl);
         }
         for (int q = 0; q < ncq; ++q) b->F[d][(long)q * b->ncp + c] = Fl[q];
     }
@@ -1041,17 +1058,19 @@ static void apply_pre_recon_bcs(const Sim* s, Blk* b)
                 if (hi) { src = cf - (1 + layer) * st; dst = cf + layer * st; }
                 else { src = cf + layer * st; dst = cf - (1 + layer) * st; }
                 FS fs;
+                double Sval = 0.0;       /* FlowState.S travels with the copied FlowState */
                 switch (bc->kind) {
                 case EB200_BC_WALL_WITH_SLIP:
-                    load_fs(s, b, src, &fs); reflect_normal_velocity(&fs, &g); break;
+                    load_fs(s, b, src, &fs); reflect_normal_velocity(&fs, &g); Sval = b->S[src]; break;
                 case EB200_BC_INFLOW_SUPERSONIC:
-                    fs = bc->fstate; break;
+                    fs = bc->fstate; Sval = 0.0; break;
                 case EB200_BC_OUTFLOW_SIMPLE_EXTRAPOLATE:
                 case EB200_BC_OUTFLOW_SIMPLE_FLUX:
-                    load_fs(s, b, hi ? cf - st : cf, &fs); break;
+                    load_fs(s, b, hi ? cf - st : cf, &fs); Sval = b->S[hi ? cf - st : cf]; break;
                 default: continue;
                 }
                 store_fs(s, b, dst, &fs);
+                b->S[dst] = Sval;
             }
         }
     }
@@ -1188,8 +1207,8 @@ static int build_exchange_lists(Sim* s)
         s->n_recv[p] = nrecv; s->n_send[p] = nsend;
         s->recv_blk[p] = malloc(nrecv * sizeof(Blk*)); s->recv_cell[p] = malloc(nrecv * sizeof(long));
         s->send_blk[p] = malloc(nsend * sizeof(Blk*)); s->send_cell[p] = malloc(nsend * sizeof(long));
-        s->recv_buf[p] = malloc((size_t)nrecv * s->nprim * sizeof(double));
-        s->send_buf[p] = malloc((size_t)nsend * s->nprim * sizeof(double));
+        s->recv_buf[p] = malloc((size_t)nrecv * (s->nprim + 1) * sizeof(double));
+        s->send_buf[p] = malloc((size_t)nsend * (s->nprim + 1) * sizeof(double));
         long m = 0;
         for (int i = 0; i < nr; ++i) {           /* my ghost cells, in my order */
             Blk* b = get_blk(s, rs[i].blk); BC* bc = &b->bc[rs[i].face];
@@ -1227,15 +1246,20 @@ static int exchange_ghost_cells(Sim* s)
         long long sc[64], rc[64];
         for (int p = 0; p < s->npeers; ++p) {
             long n = s->n_send[p];
+            const int nv = s->nprim + (s->shock_detect ? 1 : 0);     /* FlowState.S rides along when the detector is on */
             for (int v = 0; v < s->nprim; ++v) for (long t = 0; t < n; ++t)
                 s->send_buf[p][(long)v * n + t] = PR(s, s->send_blk[p][t], v)[s->send_cell[p][t]];
-            sc[p] = (long long)n * s->nprim; rc[p] = (long long)s->n_recv[p] * s->nprim;
+            if (s->shock_detect) for (long t = 0; t < n; ++t)
+                s->send_buf[p][(long)s->nprim * n + t] = s->send_blk[p][t]->S[s->send_cell[p][t]];
+            sc[p] = (long long)n * nv; rc[p] = (long long)s->n_recv[p] * nv;
         }
         if (s->exchange(s->exchange_user, s->npeers, s->peer_rank, s->send_buf, sc, s->recv_buf, rc, NULL)) { set_err("exchange callback failed"); return -1; }
         for (int p = 0; p < s->npeers; ++p) {
             long n = s->n_recv[p];
             for (int v = 0; v < s->nprim; ++v) for (long t = 0; t < n; ++t)
                 PR(s, s->recv_blk[p][t], v)[s->recv_cell[p][t]] = s->recv_buf[p][(long)v * n + t];
+            if (s->shock_detect) for (long t = 0; t < n; ++t)
+                s->recv_blk[p][t]->S[s->recv_cell[p][t]] = s->recv_buf[p][(long)s->nprim * n + t];
         }
     }
     for (int ib = 0; ib < s->nblk; ++ib) {
@@ -1261,6 +1285,7 @@ static int exchange_ghost_cells(Sim* s)
                     long src;
                     if (map_full_face_source(s, b, face, ot, bc->other_face, t1, a2, layer, &src)) return -1;
                     for (int v = 0; v < s->nprim; ++v) PR(s, b, v)[dst] = PR(s, ot, v)[src];
+                    b->S[dst] = ot->S[src];
                 }
             }
         }
@@ -1354,6 +1379,68 @@ static int check_data(const Sim* s, const FS* fs)
 
 #define FOR_INTERIOR(b) \
     for (int k = b->kg; k < b->kg + b->nkc; ++k) for (int j = NG; j < NG + b->njc; ++j) for (int i = NG; i < NG + b->nic; ++i)
+
+/* shockdetectors.d:22-93 PJ_ShockDetector, two-cell branch (every face on this path has a cell,
+ * ghost or interior, on both sides; gvel = 0) */
+static double PJ_ShockDetector(const FS* cL, const FS* cR, const FaceGeo* g, double comp_tol, double shear_tol)
+{
+    double uL = cL->vx * g->n[0] + cL->vy * g->n[1] + cL->vz * g->n[2];
+    double uR = cR->vx * g->n[0] + cR->vy * g->n[1] + cR->vz * g->n[2];
+    double aL = cL->gas.a, aR = cR->gas.a;
+    double a_min = (aL < aR) ? aL : aR;
+    double comp = ((uR - uL) / a_min);
+    double vL = cL->vx * g->t1[0] + cL->vy * g->t1[1] + cL->vz * g->t1[2];
+    double vR = cR->vx * g->t1[0] + cR->vy * g->t1[1] + cR->vz * g->t1[2];
+    double wL = cL->vx * g->t2[0] + cL->vy * g->t2[1] + cL->vz * g->t2[2];
+    double wR = cR->vx * g->t2[0] + cR->vy * g->t2[1] + cR->vz * g->t2[2];
+    double sound_speed = 0.5 * (aL + aR);
+    double shear_y = fabs(vL - vR) / sound_speed;
+    double shear_z = fabs(wL - wR) / sound_speed;
+    double shear = fmax(shear_y, shear_z);
+    if ((shear < shear_tol) && (comp < comp_tol)) return 1.0;
+    return 0.0;
+}
+
+/* detect_shocks (simcore_gasdynamic_step.d:3197-3224) for one block with shock_detector_smoothing = 0:
+ * detect_shock_points, shock_faces_to_cells, enforce_strict_shock_detector (fluidblock.d:479-605).
+ * Ghost-cell S values are whatever the last ghost fill copied (one exchange old, as in the reference). */
+static void detect_shocks_block(const Sim* s, Blk* b)
+{
+    int nd = s->threeD ? 3 : 2;
+    int n[3] = { b->nic, b->njc, b->nkc };
+    int off[3] = { NG, NG, b->kg };
+    for (int d = 0; d < nd; ++d) {
+        int ext[3] = { n[0], n[1], n[2] }; ext[d] += 1;
+        long st = b->stride[d];
+        for (int kk = 0; kk < ext[2]; ++kk) for (int jj = 0; jj < ext[1]; ++jj) for (int ii = 0; ii < ext[0]; ++ii) {
+            long c = cidx(b, ii + off[0], jj + off[1], kk + off[2]);
+            FaceGeo g; load_face(b, d, c, &g);
+            FS cL, cR; load_fs(s, b, c - st, &cL); load_fs(s, b, c, &cR);
+            b->Sf[d][c] = PJ_ShockDetector(&cL, &cR, &g, s->cfg.compression_tolerance, s->cfg.shear_tolerance);
+        }
+    }
+    for (int k = b->kg; k < b->kg + b->nkc; ++k) for (int j = NG; j < NG + b->njc; ++j) for (int i = NG; i < NG + b->nic; ++i) {
+        long c = cidx(b, i, j, k);
+        double S = 0.0;
+        for (int f = 0; f < 2 * nd; ++f) {     /* iface order W,E,S,N,B,T */
+            int d = f / 2; long cf = (f & 1) ? c + b->stride[d] : c;
+            S = fmax(S, b->Sf[d][cf]);
+        }
+        b->S[c] = S;
+    }
+    if (s->cfg.strict_shock_detector) {
+        for (int d = 0; d < nd; ++d) {
+            int ext[3] = { n[0], n[1], n[2] }; ext[d] += 1;
+            long st = b->stride[d];
+            for (int kk = 0; kk < ext[2]; ++kk) for (int jj = 0; jj < ext[1]; ++jj) for (int ii = 0; ii < ext[0]; ++ii) {
+                long c = cidx(b, ii + off[0], jj + off[1], kk + off[2]);
+                if (b->Sf[d][c] > 0.0) { b->Sf[d][c] = 1.0; continue; }
+                if (b->S[c - st] > 0.0) { b->Sf[d][c] = 1.0; continue; }
+                if (b->S[c] > 0.0) { b->Sf[d][c] = 1.0; continue; }
+            }
+        }
+    }
+}
 
 /* number_of_stages / gamma tables: simcore_gasdynamic_step.d:1235-1395 */
 static int n_stages_for(int scheme)
@@ -1464,6 +1551,9 @@ int orc_init(const eb200_config* cfg)
     s->ncq = s->iEnergy + 1;
     if (s->nsp > 1) { s->iSpecies = s->ncq; s->ncq += s->nsp; } else s->iSpecies = -1;
     s->nprim = EB200_NPRIM_BASE + (s->nsp > 1 ? 2 * s->nsp : 0);
+    s->shock_detect = (cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV);
+    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) { set_err("unknown flux calculator"); return -1; }
+    if (s->shock_detect && cfg->compression_tolerance > 0.0) { set_err("compression_tolerance should be negative!"); return -1; }
     s->n_stages = n_stages_for(cfg->update_scheme);
     if (!s->n_stages) { set_err("unsupported update scheme"); return -1; }
     if (cfg->gas_model == EB200_GAS_IDEAL) {
@@ -1488,7 +1578,7 @@ static void free_blk(Blk* b)
     free(b->vol); free(b->areaxy); for (int d = 0; d < 3; ++d) { free(b->len[d]); free(b->fgeo[d]); free(b->F[d]); }
     free(b->prim); for (int l = 0; l <= MAXLEVELS; ++l) free(b->U[l]);
     for (int l = 0; l < MAXLEVELS; ++l) free(b->dUdt[l]);
-    free(b->bad); free(b);
+    free(b->bad); free(b->S); for (int d = 0; d < 3; ++d) free(b->Sf[d]); free(b);
 }
 
 int orc_finalize(int sim)
@@ -1528,6 +1618,8 @@ int orc_block_create(int sim, int blk_id, int nic, int njc, int nkc, int owner_r
     for (int l = 0; l <= s->n_stages; ++l) b->U[l] = calloc((size_t)s->ncq * n, sizeof(double));
     for (int l = 0; l < s->n_stages; ++l) b->dUdt[l] = calloc((size_t)s->ncq * n, sizeof(double));
     b->bad = calloc(n, 1);
+    b->S = calloc(n, sizeof(double));
+    for (int d = 0; d < 3; ++d) b->Sf[d] = calloc(n, sizeof(double));
     for (int f = 0; f < 6; ++f) b->bc[f].kind = EB200_BC_WALL_WITH_SLIP;
     s->blks[s->nblk++] = b;
     return 0;
@@ -1708,6 +1800,10 @@ int orc_step(int sim, double t0, double dt, int* n_bad_cells)
         if (exchange_ghost_cells(s)) { step_failed = -1; break; }                    /* Phase 02 */
         #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
         for (int ib = 0; ib < s->nblk; ++ib) apply_pre_recon_bcs(s, s->blks[ib]);      /* Phase 03 */
+        if (s->shock_detect && stage == 1) {                                           /* Phase 04 */
+            #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+            for (int ib = 0; ib < s->nblk; ++ib) detect_shocks_block(s, s->blks[ib]);
+        }
         int fail_flux = 0;
         #pragma omp parallel for schedule(dynamic, 1) reduction(|:fail_flux) num_threads(nthreads)
         for (int ib = 0; ib < s->nblk; ++ib)                                           /* Phase 05a + 07 */
@@ -1819,6 +1915,6 @@ int orc_face_flux(int sim, const double* cells, const double* len, const double*
         }
     }
     for (int q = 0; q < s->ncq; ++q) F[q] = 0.0;
-    compute_interface_flux_interior(s, &Lft, &Rght, &g, F);
+    compute_interface_flux_interior(s, &Lft, &Rght, &g, 0.0, F);
     return 0;
 }

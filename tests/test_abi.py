@@ -58,8 +58,11 @@ def test_missing_library_fails_loudly(tmp_path):
 
 def test_config_rejects_options_outside_the_path():
     gm = cases.ideal_air()
-    with pytest.raises(ValueError, match="adaptive_hanel_ausmdv"):
-        Config().to_struct(gm)          # the reference default needs the shock detector
+    Config().to_struct(gm)              # the reference default (adaptive_hanel_ausmdv) is on the path
+    with pytest.raises(ValueError):
+        Config(flux_calculator="adaptive_efm_ausmdv").to_struct(gm)
+    with pytest.raises(ValueError):
+        Config(shock_detector_smoothing=2).to_struct(gm)
     with pytest.raises(ValueError):
         Config(flux_calculator="ausmdv", viscous=True).to_struct(gm)
     with pytest.raises(ValueError):

@@ -26,7 +26,8 @@ def _worker():
     ok = True
     for name, factory, kw, nsteps in (("box3d", cases.box3d, dict(n=16, nb=2), 12),
                                       ("ffs", cases.ffs, dict(nx=60, ny=20), 25),
-                                      ("cone20", cases.cone20, dict(), 30)):
+                                      ("cone20", cases.cone20, dict(), 30),
+                                      ("cone20-adaptive", cases.cone20, dict(flux_calculator="adaptive_hanel_ausmdv"), 60)):
         cfg, gm, blocks = factory(**kw)
         if name == "box3d":
             owner = octant_owner({v: next(b for b in blocks if b.id == k) for k, v in cfg.block_index.items()}, 2, world)
@@ -72,6 +73,7 @@ def test_two_ranks_match_one_rank_gloo():
     assert r.returncode == 0
     assert "box3d: 2 ranks == 1 rank: True" in r.stdout
     assert "cone20: 2 ranks == 1 rank: True" in r.stdout
+    assert "cone20-adaptive: 2 ranks == 1 rank: True" in r.stdout
 
 
 if __name__ == "__main__" and "--worker" in sys.argv:

@@ -26,7 +26,9 @@ def _worker():
     ok = True
     for name, factory, kw, nsteps in (("box3d", cases.box3d, dict(n=32, nb=2), 12),
                                       ("ffs", cases.ffs, dict(nx=120, ny=40), 30),
-                                      ("cone20", cases.cone20, dict(), 40)):
+                                      ("cone20", cases.cone20, dict(), 40),
+                                      ("cone20-adaptive", cases.cone20, dict(flux_calculator="adaptive_hanel_ausmdv"), 60),
+                                      ("sod-adaptive", cases.sod, dict(dims=3, ncells=64, nj=4, nk=4, nblocks=4, flux_calculator="adaptive_hanel_ausmdv"), 40)):
         for strict in (True, False):
             cfg, gm, blocks = factory(**kw)
             cfg.strict_fp = strict

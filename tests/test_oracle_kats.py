@@ -64,6 +64,22 @@ def test_cone20(oracle):
     sim.close()
 
 
+def test_cone20_with_the_reference_default_flux_calculator(oracle):
+    """cone20.lua does not set config.flux_calculator, so the reference's test runs
+    adaptive_hanel_ausmdv with the PJ shock detector: 833 +- 3 steps (cone20-test.rb:33)."""
+    cfg, gm, blocks = cases.cone20(flux_calculator="adaptive_hanel_ausmdv")
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    steps = sim.run()
+    assert abs(steps - 833) < 3
+    v = probe(sim, blocks, 0.4, 0.5)
+    assert abs(v["a"] - 666.0) < 1.0 and abs(v["p"] - 95.84e3) < 500.0 and abs(v["T"] - 1103.0) < 1.0
+    P = sim.download_flow(1)
+    p_surface = float(sim.interior(1, P[2])[0, 0, 20])
+    q_inf = 0.5 * (95.84e3 / (gm.Rgas * 1103.0)) * 1000.0 ** 2
+    assert abs(p_surface - (95.84e3 + 0.387 * q_inf)) < 1.0e3
+    sim.close()
+
+
 def test_mass_is_conserved_in_a_closed_box(oracle):
     """All-wall box: sum(rho*vol) must not drift (finite-volume telescoping of the face fluxes)."""
     cfg, gm, blocks = cases.sod(dims=2, ncells=60, nj=4, nblocks=3)
