@@ -35,16 +35,16 @@ __device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
 
 // Division and square root.  The FMA-free build uses IEEE division / sqrt in the reference's
 // operation order.  The throughput build (EB_FAST_MATH) replaces a/b by a * rcp(b) with a
-// branch-free Newton-refined reciprocal (MUFU.RCP64H + 4 DFMA, <= 2 ulp) and lets several
+// branch-free refined reciprocal (MUFU.RCP64H + 3 DFMA, <= 2 ulp) and lets several
 // quotients share one reciprocal; parity with the reference is then within 1e-10, not bitwise.
 #ifdef EB_FAST_MATH
 __device__ __forceinline__ double eb_rcp(double b)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    double e = fma(-b, r, 1.0); r = fma(r, e, r);
-    e = fma(-b, r, 1.0); r = fma(r, e, r);
-    return r;
+    // one third-order step: r (1 + e + e^2), e = 1 - b r; the seed is good to ~2^-23
+    const double e = fma(-b, r, 1.0);
+    return fma(r, fma(e, e, e), r);
 }
 __device__ __forceinline__ double eb_div(double a, double b) { return a * eb_rcp(b); }
 __device__ __forceinline__ double eb_sqrt(double x)

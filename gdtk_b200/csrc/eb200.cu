@@ -270,8 +270,13 @@ bool detect_cartesian(const Sim* s, const Block* b, const double* vol, const dou
         w.aR0 = 0.5 * l / (l + 2.0 * l + l);
         w.two_over_L0L1 = 2.0 / (l + l); w.two_over_R0L0 = 2.0 / (l + l); w.two_over_R1R0 = 2.0 / (l + l);
         w.two_L0_plus_L1 = (2.0 * l + l); w.two_R0_plus_R1 = (2.0 * l + l);
+        const double c = w.two_over_R0L0;
+        D.uq[d][0] = w.aL0 * w.two_L0_plus_L1 * c; D.uq[d][1] = w.aL0 * w.lenR0 * c;
+        D.uq[d][2] = w.aR0 * w.lenL0 * c; D.uq[d][3] = w.aR0 * w.two_R0_plus_R1 * c;
+        D.uq[d][4] = 1.0 / (c * c);
     }
     if (dims == 2) {
+        for (int m = 0; m < 5; ++m) D.uq[2][m] = D.uq[0][m];
         D.fr[2].perm[0] = 2; D.fr[2].perm[1] = 0; D.fr[2].perm[2] = 1; D.fr[2].neg[0] = D.fr[2].neg[1] = D.fr[2].neg[2] = 0;
         D.nvec[2][0] = 0; D.nvec[2][1] = 0; D.nvec[2][2] = 1; D.w[2] = D.w[0];
     }
@@ -687,7 +692,11 @@ int eb200_commit(int sim)
         if (b->cartesian) D = b->cartD; else memset(&D, 0, sizeof D);
         D.nic = b->nic; D.njc = b->njc; D.nkc = b->nkc; D.NI = b->NI; D.NJ = b->NJ; D.NK = b->NK; D.kg = b->kg;
         D.cell0 = b->cell0; for (int d = 0; d < 3; ++d) D.stride[d] = b->stride[d];
-        for (int f = 0; f < 6; ++f) D.bc_kind[f] = b->bc[f].kind;
+        D.outflow_flux_faces = 0;
+        for (int f = 0; f < 6; ++f) {
+            D.bc_kind[f] = b->bc[f].kind;
+            if (b->bc[f].kind == EB200_BC_OUTFLOW_SIMPLE_FLUX) D.outflow_flux_faces |= (1 << f);
+        }
         D.cartesian = b->cartesian ? 1 : 0;
         (b->cartesian ? any_cart : any_general) = true;
         cells_total += (long long)b->nic * b->njc * b->nkc;

@@ -49,6 +49,12 @@ struct EbBlockDesc {
     EbWeights w[3];
     EbAxisFrame fr[3];
     double nvec[3][3];        // face normal per direction (exact +-1/0), used by flux BCs and CFL
+    // throughput build, uniform spacing: reconstruction on raw differences.  With c = 2/(2*len):
+    // uq[d] = { aL0*two_L0_plus_L1*c, aL0*lenR0*c, aR0*lenL0*c, aR0*two_R0_plus_R1*c, 1/c^2 }
+    // (van Albada's epsilon is rescaled by 1/c^2 so that the limiter value is the same number)
+    double uq[3][5];
+    int outflow_flux_faces;   // bit f set: face f has EB200_BC_OUTFLOW_SIMPLE_FLUX
+    int pad0;
 };
 
 struct EbCurve {             // reference src/gas/thermo/cea_thermo_curves.d

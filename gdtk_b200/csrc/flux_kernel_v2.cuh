@@ -221,6 +221,81 @@ __device__ __forceinline__ void flux_components(const Prim<1>& L, const Prim<1>&
 }
 #endif
 
+#ifdef EB_FAST_MATH
+// ---- throughput build, uniform-Cartesian blocks ---------------------------------------------------
+// Reconstruction on raw differences with the constants of EbBlockDesc::uq (same limiter value as
+// interp_v2: numerator and denominator are both scaled by 1/c^2, and so is epsilon).  Extrema
+// clipping (limiters.d:43-51) is only *detected* here: inc*(inc - del) > 0 says the reconstructed
+// value left the interval of its two neighbours; the caller then redoes the face with the
+// clipping reconstruction.  With van Albada on uniform spacing that only happens at local
+// extrema, where the limiter value is ~epsilon.
+__device__ __forceinline__ void interp_uniform(const double* __restrict__ K, double eps2, double qL1, double qL0,
+                                               double qR0, double qR1, double& qL, double& qR, int& outside)
+{
+    const double a = qL0 - qL1, b = qR0 - qL0, c = qR1 - qR0;
+    const double ab = a * b, bc = b * c, b2 = b * b;
+    const double nL = ab + fabs(ab) + eps2, dL = a * a + b2 + eps2;
+    const double nR = bc + fabs(bc) + eps2, dR = c * c + b2 + eps2;
+    const double rr = eb_rcp(dL * dR);
+    const double iL = (nL * dR * rr) * (b * K[0] + a * K[1]);
+    const double iR = (nR * dL * rr) * (c * K[2] + b * K[3]);
+    qL = qL0 + iL;
+    qR = qR0 - iR;
+    outside = max(outside, max(__double2hiint(iL * (iL - b)), __double2hiint(iR * (iR - b))));
+}
+
+// Stencil velocities are (normal, t1, t2) by the way they were loaded (a renaming of the
+// components, CartFrame conventions); F comes back as (mass, normal, t1, t2, energy).
+template <int DIM, int FLUX, bool CLIP>
+__device__ __forceinline__ void face_core_uniform(const EbParams& P, const EbGas* __restrict__ gas,
+                                                  const double* __restrict__ K, const Stencil& s, double alpha,
+                                                  const double* __restrict__ prim_fallback, long long cL0, long long cR0, double* F)
+{
+    Prim<1> L, R;
+    const double eps2 = P.eps_va * K[4];
+    const double gm1 = gas->Rgas * gas->Cvinv;
+    int outside = 0;
+    interp_uniform(K, eps2, s.v0[0], s.v0[1], s.v0[2], s.v0[3], L.vx, R.vx, outside);
+    interp_uniform(K, eps2, s.v1[0], s.v1[1], s.v1[2], s.v1[3], L.vy, R.vy, outside);
+    if (DIM == 3) interp_uniform(K, eps2, s.v2[0], s.v2[1], s.v2[2], s.v2[3], L.vz, R.vz, outside);
+    else { L.vz = 0.0; R.vz = 0.0; }
+    interp_uniform(K, eps2, s.rho[0], s.rho[1], s.rho[2], s.rho[3], L.rho, R.rho, outside);
+    interp_uniform(K, eps2, s.u[0], s.u[1], s.u[2], s.u[3], L.u, R.u, outside);
+    if (CLIP && outside > 0) {     // rare (local extrema): clip_to_limits, limiters.d:43-51
+        L.vx = clip_to_limits(L.vx, s.v0[1], s.v0[2]); R.vx = clip_to_limits(R.vx, s.v0[1], s.v0[2]);
+        L.vy = clip_to_limits(L.vy, s.v1[1], s.v1[2]); R.vy = clip_to_limits(R.vy, s.v1[1], s.v1[2]);
+        if (DIM == 3) { L.vz = clip_to_limits(L.vz, s.v2[1], s.v2[2]); R.vz = clip_to_limits(R.vz, s.v2[1], s.v2[2]); }
+        L.rho = clip_to_limits(L.rho, s.rho[1], s.rho[2]); R.rho = clip_to_limits(R.rho, s.rho[1], s.rho[2]);
+        L.u = clip_to_limits(L.u, s.u[1], s.u[2]); R.u = clip_to_limits(R.u, s.u[1], s.u[2]);
+    }
+    L.a = s.aL; R.a = s.aR;
+    L.p = L.rho * L.u * gm1;
+    R.p = R.rho * R.u * gm1;
+    if (!(fmin(fmin(L.u, L.rho), fmin(R.u, R.rho)) > 0.0)) {
+        // rare: first-order fall-back of a side whose reconstructed state is not physical (onedinterp.d:45-74)
+        const long long total = P.total;
+        if (L.u <= 0.0 || L.rho <= 0.0) {
+            L.rho = s.rho[1]; L.u = s.u[1]; L.vx = s.v0[1]; L.vy = s.v1[1]; L.vz = s.v2[1];
+            L.p = ldg(prim_fallback + 2 * total + cL0);
+        }
+        if (R.u <= 0.0 || R.rho <= 0.0) {
+            R.rho = s.rho[2]; R.u = s.u[2]; R.vx = s.v0[2]; R.vy = s.v1[2]; R.vz = s.v2[2];
+            R.p = ldg(prim_fallback + 2 * total + cR0);
+        }
+    }
+    if (FLUX == EB200_FLUX_ROE) { L.massf[0] = 1.0; R.massf[0] = 1.0; flux_roe<DIM, 1>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F); }
+    else if (FLUX < EB200_FLUX_ROE) flux_components<DIM, FLUX>(L, R, 0, P.entropy_fix != 0, P.M_inf, F);
+    else if (alpha > 0.0) {
+        if (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) flux_components<DIM, EB200_FLUX_LDFSS0>(L, R, 0, false, P.M_inf, F);
+        else flux_components<DIM, EB200_FLUX_HANEL>(L, R, 0, false, P.M_inf, F);
+    } else {
+        if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) flux_components<DIM, EB200_FLUX_AUSMDV>(L, R, 0, P.entropy_fix != 0, P.M_inf, F);
+        else if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) flux_components<DIM, EB200_FLUX_AUSM_PLUS_UP>(L, R, 0, false, P.M_inf, F);
+        else flux_components<DIM, EB200_FLUX_LDFSS2>(L, R, 0, false, P.M_inf, F);
+    }
+}
+#endif
+
 // Reconstruction + thermo + flux.  ROT: general-metric path, the stencil velocities are global and
 // rotate with `fr`, F comes back in the face frame.  !ROT: uniform-Cartesian path, the face frame is
 // a renaming of the components ((n,t1,t2) = (e_d, e_d+1, e_d+2) in 3D; 2D: i-face (x,-y), j-face
@@ -387,9 +462,11 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
     const int k1 = (DIM == 3) ? min(nkc, k0 + D.chunk_m) : 1;
 
     const bool cell_ok = (i < nic) && (j < njc);
-    // second trip: warp 0 -> faces east of lane 31 (row = lane), warp 1 -> south faces of row TY
-    const bool extraE_ok = (wy == 0) && (lane < TY) && (i0 + 32 <= nic) && (j0 + lane < njc);
-    const bool extraN_ok = (wy == 1) && (j0 + TY <= njc) && (i < nic);
+    // second trip, for two warps of the CTA: one does the faces east of lane 31 (row = lane), the other
+    // the south faces of row TY.  The pair rotates from plane to plane so that the four schedulers of
+    // the SM see the same load.
+    const bool extraE_can = (lane < TY) && (i0 + 32 <= nic) && (j0 + lane < njc);
+    const bool extraN_can = (j0 + TY <= njc) && (i < nic);
 
     // cp.async work list of this thread: tile positions tid and tid + NT (of ROWS*COLS)
     int pos_s[2], pos_g[2];
@@ -443,19 +520,20 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
         // job 3: second trip for warp 0 (faces east of lane 31) and warp 1 (south faces of row TY).
         // Every flux goes straight to shared memory; the momentum components are put into their
         // global-frame slots by address, not by moving values around.
+        const int xw = (TY >= 8) ? ((2 * (k - k0)) & (TY - 1)) : 0;   // warps xw, xw+1 do the second trip on this plane
 #pragma unroll 1
         for (int job = 0; job < 4; ++job) {
             if (job == 2 && DIM != 3) continue;
-            if (job == 3 && (wy > 1 || !plane_has_cells)) break;
-            const int d = (job < 3) ? job : wy;
+            if (job == 3 && ((unsigned)(wy - xw) > 1u || !plane_has_cells)) break;
+            const int d = (job < 3) ? job : (wy - xw);
             int row = wy + 2, col = lane + 2;            // tile coordinates of the plus-side cell of the face
             int fi = i, fj = j;                          // its interior indices
             bool active;
             if (job == 0) active = plane_has_cells && (i <= nic) && (j < njc);
             else if (job == 1) active = plane_has_cells && (i < nic) && (j <= njc);
             else if (job == 2) active = cell_ok;
-            else if (d == 0) { row = lane + 2; col = 34; fi = i0 + 32; fj = j0 + lane; active = extraE_ok; }
-            else { row = TY + 2; fj = j0 + TY; active = extraN_ok; }
+            else if (d == 0) { row = lane + 2; col = 34; fi = i0 + 32; fj = j0 + lane; active = extraE_can; }
+            else { row = TY + 2; fj = j0 + TY; active = extraN_can; }
             if (!active) continue;
             // where this face's flux goes: component q at out[q * qstride]
             double* out;
@@ -463,12 +541,14 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             if (d == 0) { out = fW + (row - 2) * 33 + (col - 2); qstride = TY * 33; }
             else if (d == 1) { out = fS + (row - 2) * 32 + (col - 2); qstride = (TY + 1) * 32; }
             else { out = fB + wy * 32 + lane; qstride = TY * 32; }
-            const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (fj + EB_NG)) * NI + (fi + EB_NG);
+            const long long cf = (job < 3) ? c : c + (long long)(fj - j) * NI + (fi - i);
             const long long st = (d == 0) ? 1 : ((d == 1) ? sj : sk);
             int bcf = -1;
-            if (d == 0) { if (fi == 0) bcf = EB200_WEST; else if (fi == nic) bcf = EB200_EAST; }
-            else if (d == 1) { if (fj == 0) bcf = EB200_SOUTH; else if (fj == njc) bcf = EB200_NORTH; }
-            else { if (k == 0) bcf = EB200_BOTTOM; else if (k == nkc) bcf = EB200_TOP; }
+            if (D.outflow_flux_faces) {
+                if (d == 0) { if (fi == 0) bcf = EB200_WEST; else if (fi == nic) bcf = EB200_EAST; }
+                else if (d == 1) { if (fj == 0) bcf = EB200_SOUTH; else if (fj == njc) bcf = EB200_NORTH; }
+                else { if (k == 0) bcf = EB200_BOTTOM; else if (k == nkc) bcf = EB200_TOP; }
+            }
             if (bcf >= 0 && D.bc_kind[bcf] == EB200_BC_OUTFLOW_SIMPLE_FLUX) {
                 const int hi = bcf & 1;
                 Prim<1> fs;
@@ -487,16 +567,42 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             Stencil s;
             // ---- gather the stencil straight into its registers.  On the Cartesian path the face frame is a
             //      renaming of the velocity components (CartFrame conventions): pick the fields by address.
+#ifdef EB_FAST_MATH
+            constexpr bool UNIFORM = CART;       // velocities loaded as (normal, t1, t2): a renaming by address
+#else
+            constexpr bool UNIFORM = false;
+#endif
+            // 3D: (d, d+1, d+2) mod 3;  2D: (d, 1-d) -- the sign of t1 on 2D i-faces plays no role in
+            // the component form of the flux
+            const int c0 = UNIFORM ? d : 0;
+            const int c1 = UNIFORM ? ((DIM == 3) ? ((d == 2) ? 0 : d + 1) : 1 - d) : 1;
+            const int c2 = UNIFORM ? ((DIM == 3) ? ((d == 0) ? 2 : d - 1) : 2) : 2;
             if (d < 2) {
                 const int so = (d == 0) ? 1 : T::COLS;       // tile stride along d
+                const int o0 = (T::F_V + c0) * T::FSZ, o1 = (T::F_V + c1) * T::FSZ, o2 = (T::F_V + c2) * T::FSZ;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     const double* qm = q0 + (m - 2) * so;
                     s.rho[m] = qm[T::F_RHO * T::FSZ]; s.u[m] = qm[T::F_U * T::FSZ];
-                    s.v0[m] = qm[(T::F_V + 0) * T::FSZ]; s.v1[m] = qm[(T::F_V + 1) * T::FSZ];
-                    s.v2[m] = (DIM == 3) ? qm[(T::F_V + 2) * T::FSZ] : 0.0;
+                    s.v0[m] = qm[o0]; s.v1[m] = qm[o1];
+                    s.v2[m] = (DIM == 3) ? qm[o2] : 0.0;
                 }
                 s.aL = (q0 - so)[T::F_A * T::FSZ];
+            } else if (UNIFORM) {
+                // own column: plane k from the tile, planes k-2, k-1, k+1 from global memory (L2); d == 2: (z, x, y)
+                const double* pin = S.prim_in;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    if (m == 2) {
+                        s.rho[m] = q0[T::F_RHO * T::FSZ]; s.u[m] = q0[T::F_U * T::FSZ];
+                        s.v0[m] = q0[(T::F_V + 2) * T::FSZ]; s.v1[m] = q0[(T::F_V + 0) * T::FSZ]; s.v2[m] = q0[(T::F_V + 1) * T::FSZ];
+                    } else {
+                        const double* pm = pin + cf + (m - 2) * sk;
+                        s.rho[m] = ldg(pm); s.u[m] = ldg(pm + total);
+                        s.v0[m] = ldg(pm + 7 * total); s.v1[m] = ldg(pm + 5 * total); s.v2[m] = ldg(pm + 6 * total);
+                    }
+                }
+                s.aL = ldg(pin + 4 * total + cf - sk);
             } else {
                 // own column: plane k from the tile, planes k-2, k-1, k+1 from global memory (L2)
                 const double* pin = S.prim_in;
@@ -524,6 +630,17 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             const EbWeights& w = CART ? D.w[d] : wl;
             double Fl[NCQ];
             const double alpha = (FLUX > EB200_FLUX_ROE) ? A.Sf[d][cf] : 0.0;
+#ifdef EB_FAST_MATH
+            if (UNIFORM) {
+                face_core_uniform<DIM, FLUX, CLIP>(P, gas, D.uq[d], s, alpha, S.prim_in, cf - st, cf, Fl);
+                out[0] = Fl[Lay::iMass];
+                out[(Lay::iXMom + c0) * qstride] = Fl[Lay::iXMom];
+                out[(Lay::iXMom + c1) * qstride] = Fl[Lay::iYMom];
+                if (DIM == 3) out[(Lay::iXMom + c2) * qstride] = Fl[Lay::iZMom];
+                out[Lay::iEnergy * qstride] = Fl[Lay::iEnergy];
+                continue;
+            }
+#endif
             face_core<DIM, FLUX, CLIP, !CART>(P, gas, w, s, fr, d, alpha, S.prim_in, cf - st, cf, Fl);
             if (!CART) {     // momentum flux back to the global frame (fluxcalc.d:169-175)
                 double fx = Fl[Lay::iXMom], fy = Fl[Lay::iYMom], fz = (DIM == 3) ? Fl[Lay::iZMom] : 0.0;
