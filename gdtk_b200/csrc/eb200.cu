@@ -4,6 +4,7 @@
 // work lists and the stage loop of gasdynamic_explicit_increment_with_fixed_grid
 // (reference src/eilmer/simcore_gasdynamic_step.d:906-1575).  Every numerical operation
 // of a time step runs in the CUDA kernels of this directory; there is no CPU fallback.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -77,6 +78,7 @@ struct Sim {
     std::vector<void*> allocs;
     std::vector<EbBlockDesc> hdesc;
     EbBlockDesc* d_desc = nullptr;
+    CUtensorMap* d_tmaps = nullptr;        // [3 prim buffers][local blocks], nullptr when TMA staging is not used
     long long ncta = 0;
     int which = 0;
     EbCopyItem* d_copy = nullptr; long long ncopy = 0;
@@ -392,6 +394,43 @@ int exchange_remote(Sim* s, double* prim)
     return 0;
 }
 
+// TMA descriptors for the tile staging of the tuned flux kernel: per prim buffer and local block a
+// 4D tensor (i, j, k, field) in the padded block layout; one box = (36, TY+4, 1, 2 fields).
+// TMA wants 16-byte multiples for the strides, i.e. an even NI; otherwise the kernel stages with cp.async.
+int build_tensor_maps(Sim* s)
+{
+    s->d_tmaps = nullptr;
+    if (s->cfg.reserved_i[2]) return 0;                 // testing knob: never use TMA
+    for (Block* b : s->local) if (b->NI % 2) return 0;
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    EncodeTiled encode = (EncodeTiled)fn;
+    const size_t nl = s->local.size();
+    std::vector<CUtensorMap> maps(3 * nl);
+    for (int p = 0; p < 3; ++p) {
+        for (size_t n = 0; n < nl; ++n) {
+            const Block* b = s->local[n];
+            cuuint64_t gdim[4] = { (cuuint64_t)b->NI, (cuuint64_t)b->NJ, (cuuint64_t)b->NK, (cuuint64_t)s->P.nprim };
+            cuuint64_t gstride[3] = { (cuuint64_t)b->NI * 8, (cuuint64_t)b->NI * b->NJ * 8, (cuuint64_t)s->P.total * 8 };
+            cuuint32_t box[4] = { EB_V2_COLS, EB_V2_TY + 4, 1, 2 };
+            cuuint32_t estr[4] = { 1, 1, 1, 1 };
+            CUresult r = encode(&maps[p * nl + n], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, s->A.prim[p] + b->cell0, gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return 0;            // fall back to cp.async staging
+        }
+    }
+    return dev_upload(s, &s->d_tmaps, maps);
+}
+
 // Same-GPU full-face copies and boundary conditions (phases 02/03 of the reference step).
 int fill_local_ghost_cells(Sim* s, double* prim)
 {
@@ -426,6 +465,7 @@ int enqueue_step(Sim* s, double dt)
         EbStageArgs S;
         memset(&S, 0, sizeof S);
         S.prim_in = prim_in; S.prim_out = prim_out;
+        S.tmaps = s->d_tmaps ? (const void*)(s->d_tmaps + (size_t)in_buf * s->local.size()) : nullptr;
         S.U0 = s->A.U[s->Ulev[0]];
         S.U_out = (stage == ns) ? s->A.U[s->Ulev[ns]] : nullptr;
         for (int m = 0; m < 3; ++m) S.dUdt_prev[m] = (m < stage - 1) ? s->A.dUdt[m] : nullptr;
@@ -758,6 +798,7 @@ int eb200_commit(int sim)
         }
     }
     if (dev_upload(s, &s->d_desc, s->hdesc)) return -100;
+    if (build_tensor_maps(s)) return -100;
     {
         std::vector<EbGas> gv(1, s->hgas);
         if (dev_upload(s, &s->d_gas, gv)) return -100;

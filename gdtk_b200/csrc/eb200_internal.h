@@ -21,6 +21,11 @@
 #define EB_MAXSEG EB200_MAX_SEGMENTS
 
 // l2r2_prepare() results (reference src/eilmer/onedinterp.d:338-354)
+#ifndef EB_V2_TY
+#define EB_V2_TY 8            // rows of cells per CTA tile of the tuned kernel (CTA = 32 x EB_V2_TY threads)
+#endif
+#define EB_V2_COLS 36         // tile width with its two-cell halo
+
 struct EbWeights {
     double aL0, aR0, lenL0, lenR0;
     double two_over_L0L1, two_over_R0L0, two_over_R1R0;
@@ -102,6 +107,7 @@ struct EbStageArgs {
     int stage, n_stages;
     int* status;                           // [0] step-failed flag, [1..4] invalid-cell count per stage
     const int* tile_list;                  // CTA -> tile id (nullptr: identity); used to run interior tiles first
+    const void* tmaps;                     // CUtensorMap[local block] over prim_in (i, j, k, field), or nullptr: stage with cp.async
 };
 
 // ghost-cell work lists (indices into the arena)

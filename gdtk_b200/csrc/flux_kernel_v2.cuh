@@ -31,6 +31,32 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+
+// TMA (cp.async.bulk.tensor) + mbarrier, used to stage the tile of a k-plane: one thread issues three
+// box loads per plane, all threads wait on the barrier's phase.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, unsigned long long* bar, int x0, int x1, int x2, int x3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // van Albada-limited l2r2 reconstruction of one scalar with precomputed weights; LIM/CLIP are
@@ -392,15 +418,12 @@ __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __rest
 // Shared-memory tile of one k-plane: NF fields x ROWS x COLS doubles (halo of 2 on each side).
 template <int DIM, int TY>
 struct Tile {
-    static constexpr int NF = (DIM == 3) ? 6 : 5;          // rho, u, vx, vy, [vz], a
-    static constexpr int ROWS = TY + 4, COLS = 36;
+    static constexpr int NF = 6;                           // rho, u, a, vx, vy, vz: prim fields (0,1), (4,5), (6,7) = three TMA boxes
+    static constexpr int ROWS = TY + 4, COLS = EB_V2_COLS;
     static constexpr int FSZ = ROWS * COLS;                // doubles per field
     static constexpr int SIZE = NF * FSZ;
-    static constexpr int F_RHO = 0, F_U = 1, F_V = 2, F_A = (DIM == 3) ? 5 : 4;
-    __device__ static constexpr int prim_index(int f)
-    {
-        return (f == 0) ? 0 : (f == 1) ? 1 : (f == F_A) ? 4 : 5 + (f - 2);
-    }
+    static constexpr int F_RHO = 0, F_U = 1, F_A = 2, F_V = 3;
+    __device__ static constexpr int prim_index(int f) { return (f < 2) ? f : f + 2; }
 };
 
 // Frame conventions of the uniform-Cartesian path (the frames Eilmer builds for a box grid:
@@ -422,7 +445,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
     typedef Tile<DIM, TY> T;
     constexpr int NCQ = Lay::NCQ;
     constexpr int NT = 32 * TY;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(128) double smem[];
     // layout: tile[2][SIZE] | fW[2][NCQ][TY][33] | fS[2][NCQ][TY+1][32] | fB[2][NCQ][TY][32] | desc
     double* tile = smem;
     double* fWs = tile + 2 * T::SIZE;
@@ -430,14 +453,17 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
     double* fBs = fSs + 2 * NCQ * (TY + 1) * 32;
     EbBlockDesc& D = *reinterpret_cast<EbBlockDesc*>(fBs + 2 * NCQ * TY * 32);
     __shared__ int s_blk;
+    __shared__ __align__(8) unsigned long long s_bar[2];      // tile[buf] has landed (TMA staging)
 
     const int lane = threadIdx.x, wy = threadIdx.y;
     const int tid = wy * 32 + lane;
     const long long cta = S.tile_list ? (long long)S.tile_list[blockIdx.x] : (long long)blockIdx.x;
+    const bool use_tma = (S.tmaps != nullptr);
     if (tid == 0) {
         int lo = 0, hi = nblocks - 1;
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (descs[mid].tile0 <= cta) lo = mid; else hi = mid - 1; }
         s_blk = lo;
+        if (use_tma) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     }
     __syncthreads();
     {
@@ -468,29 +494,37 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
     const bool extraE_can = (lane < TY) && (i0 + 32 <= nic) && (j0 + lane < njc);
     const bool extraN_can = (j0 + TY <= njc) && (i < nic);
 
-    // cp.async work list of this thread: tile positions tid and tid + NT (of ROWS*COLS)
-    int pos_s[2], pos_g[2];
-    bool pos_ok[2];
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-        const int p = tid + n * NT;
-        const int r = p / T::COLS, c = p % T::COLS;
-        pos_ok[n] = (p < T::ROWS * T::COLS) && (j0 + r < NJ) && (i0 + c < NI);
-        pos_s[n] = r * T::COLS + c;
-        pos_g[n] = (j0 + r) * NI + (i0 + c);             // offset within a padded k-plane
-    }
+    // plane k (interior index; padded k + kg) -> tile[buf]: three TMA boxes issued by one thread, or (odd NI,
+    // no driver entry point) cp.async by everybody, tile positions tid and tid + NT of ROWS*COLS
     auto stage_plane = [&](int k, int buf) {
-        // plane k (interior index; padded k + kg) -> tile[buf]
-        const long long plane = D.cell0 + (long long)(k + D.kg) * NJ * NI;
         double* dst = tile + buf * T::SIZE;
+        if (use_tma) {
+            if (tid == 0) {
+                const void* tm = reinterpret_cast<const char*>(S.tmaps) + (size_t)s_blk * 128;
+                mbar_expect_tx(&s_bar[buf], (unsigned)(T::SIZE * sizeof(double)));
+                tma_load_4d(dst, tm, &s_bar[buf], i0, j0, k + D.kg, 0);
+                tma_load_4d(dst + 2 * T::FSZ, tm, &s_bar[buf], i0, j0, k + D.kg, 4);
+                tma_load_4d(dst + 4 * T::FSZ, tm, &s_bar[buf], i0, j0, k + D.kg, 6);
+            }
+            return;
+        }
+        const long long plane = D.cell0 + (long long)(k + D.kg) * NJ * NI;
 #pragma unroll
-        for (int f = 0; f < T::NF; ++f) {
-            const double* src = S.prim_in + (long long)T::prim_index(f) * total + plane;
+        for (int n = 0; n < 2; ++n) {
+            const int p = tid + n * NT;
+            const int r = p / T::COLS, cc = p % T::COLS;
+            if ((p < T::ROWS * T::COLS) && (j0 + r < NJ) && (i0 + cc < NI)) {
+                const double* src = S.prim_in + plane + (long long)(j0 + r) * NI + (i0 + cc);
 #pragma unroll
-            for (int n = 0; n < 2; ++n)
-                if (pos_ok[n]) cp_async8(dst + f * T::FSZ + pos_s[n], src + pos_g[n]);
+                for (int f = 0; f < T::NF; ++f) cp_async8(dst + f * T::FSZ + p, src + (long long)T::prim_index(f) * total);
+            }
         }
         cp_async_commit();
+    };
+    // m = k - k0 counts the planes of this CTA: plane m lives in tile[m & 1], its barrier is in phase (m >> 1) & 1
+    auto wait_plane = [&](int m) {
+        if (use_tma) mbar_wait(&s_bar[m & 1], (unsigned)((m >> 1) & 1));
+        else cp_async_wait_all();
     };
 
     double acc[NCQ];
@@ -501,7 +535,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
 
     const int kend = (DIM == 3) ? k1 : 0;
     stage_plane(k0, 0);
-    cp_async_wait_all();
+    wait_plane(0);
     __syncthreads();
 
     for (int k = k0; k <= kend; ++k) {
@@ -652,7 +686,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             for (int q = 0; q < NCQ; ++q) out[q * qstride] = Fl[q];
         }
 
-        cp_async_wait_all();
+        if (DIM == 3 && k < kend) wait_plane(k + 1 - k0);
         __syncthreads();
 
         // finish the cell of the previous plane: its top face is this plane's bottom face

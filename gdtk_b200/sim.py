@@ -69,6 +69,7 @@ class Config:
         # Not an Eilmer option: testing knob, never use the uniform-Cartesian fast path.
         self.force_general_path = False
         self.force_generic_kernel = False  # testing knob: never use the tuned flux kernel
+        self.no_tma = False                # testing knob: stage tiles with cp.async instead of TMA
         self.block_index = None          # optional {block id: (ib, jb, kb)} left by the case factories
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -113,6 +114,7 @@ class Config:
         c.strict_fp = int(self.strict_fp)
         c.reserved_i[0] = int(self.force_general_path)
         c.reserved_i[1] = int(self.force_generic_kernel)
+        c.reserved_i[2] = int(self.no_tma)
         c.rank = rank
         c.device = device
         c.epsilon_van_albada = self.epsilon_van_albada

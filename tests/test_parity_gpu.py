@@ -132,6 +132,27 @@ def test_tuned_and_generic_kernels_agree(product, case):
     assert s1.dt_history == s2.dt_history
 
 
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("case", ["box3d", "box3d_sheared", "ffs", "cone20"])
+def test_tma_and_cp_async_staging_agree(product, case, strict):
+    """The k-plane tiles are staged by TMA (even NI) or by cp.async (odd NI, or the no_tma knob):
+    two ways of moving the same bytes, so the results are identical in both builds."""
+    factory, kw, n = {"box3d": (cases.box3d, dict(n=32, nb=2), 6),
+                      "box3d_sheared": (cases.box3d, dict(n=16, nb=2, sheared=True), 6),
+                      "ffs": (cases.ffs, dict(nx=120, ny=40), 30),
+                      "cone20": (cases.cone20, dict(), 60)}[case]
+    s1, U1, _ = run_case(factory, product, n, strict=strict, **kw)
+    s2, U2, _ = run_case(factory, product, n, strict=strict, no_tma=True, **kw)
+    assert identical(U1, U2)
+    assert s1.dt_history == s2.dt_history
+
+
+def test_odd_block_width_uses_cp_async_path(oracle, product):
+    # nic = 7 -> NI = 11: strides are not 16-byte multiples, TMA is not used
+    _compare(cases.box3d, oracle, product, 6, n=14, nb=2)
+    _compare(cases.box3d, oracle, product, 6, n=14, nb=2, sheared=True)
+
+
 @pytest.mark.parametrize("flux", ["ausmdv", "hanel", "ldfss2", "ausm_plus_up"])
 @pytest.mark.parametrize("sheared", [False, True])
 def test_thermally_perfect_five_species(oracle, product, flux, sheared):
