@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -81,7 +82,9 @@ struct Sim {
     CUtensorMap* d_tmaps = nullptr;        // [3 prim buffers][local blocks], nullptr when TMA staging is not used
     long long ncta = 0;
     int which = 0;
-    EbCopyItem* d_copy = nullptr; long long ncopy = 0;
+    EbCopyItem* d_copy = nullptr; long long ncopy = 0;   // ncopy: items every stage needs
+    long long ncopy_full = 0;              // + the copies the flux kernel does itself (push); needed after an upload
+    bool ghosts_stale = true;              // FlowStates came from the host: the pushed ghost cells are not filled
     EbReflectItem* d_refl = nullptr; long long nrefl = 0;
     EbFillItem* d_fill = nullptr; long long nfill = 0;
     double* d_params = nullptr;
@@ -432,11 +435,32 @@ int build_tensor_maps(Sim* s)
 }
 
 // Same-GPU full-face copies and boundary conditions (phases 02/03 of the reference step).
-int fill_local_ghost_cells(Sim* s, double* prim)
+int fill_local_ghost_cells(Sim* s, double* prim, bool all_copies)
 {
-    if (s->ncopy + s->nrefl + s->nfill > 0)
-        MODE_CALL(s, launch_ghosts, s->P, s->d_desc, s->A, prim, s->d_copy, s->ncopy, s->d_refl, s->nrefl, s->d_fill, s->nfill, s->d_params, s->stream);
+    const long long ncopy = all_copies ? s->ncopy_full : s->ncopy;
+    if (ncopy + s->nrefl + s->nfill > 0)
+        MODE_CALL(s, launch_ghosts, s->P, s->d_desc, s->A, prim, s->d_copy, ncopy, s->d_refl, s->nrefl, s->d_fill, s->nfill, s->d_params, s->stream);
     return 0;
+}
+
+// Does face f of local block b push its two cell layers into the ghost cells of its neighbour?
+// Same GPU, opposite faces, equal block sizes (then one constant index offset maps cell to ghost cell),
+// at least four cells per direction (a cell has at most one target per direction).
+bool face_pushes(const Sim* s, const Block* b, int f, const Block** other)
+{
+    if (s->cfg.reserved_i[3] || s->P.shock_detect) return false;
+    const BC& bc = b->bc[f];
+    if (bc.kind != EB200_BC_EXCHANGE_FULL_FACE) return false;
+    const Block* ot = nullptr;
+    for (auto& q : s->blocks) if (q->id == bc.other_blk) ot = q.get();
+    if (!ot || !ot->local || !b->local || ot == b) return false;
+    if (bc.other_face != (f ^ 1)) return false;
+    const BC& back = ot->bc[f ^ 1];
+    if (back.kind != EB200_BC_EXCHANGE_FULL_FACE || back.other_blk != b->id || back.other_face != f) return false;
+    if (ot->nic != b->nic || ot->njc != b->njc || ot->nkc != b->nkc) return false;
+    if (b->nic < 4 || b->njc < 4 || (s->threeD && b->nkc < 4)) return false;
+    if (other) *other = ot;
+    return true;
 }
 
 // All stages of one step, enqueued on the stream (no host synchronisation).
@@ -452,8 +476,9 @@ int enqueue_step(Sim* s, double dt)
         double* prim_out = s->A.prim[out_buf];
         int rc = exchange_remote(s, prim_in);
         if (rc) return rc;
-        rc = fill_local_ghost_cells(s, prim_in);
+        rc = fill_local_ghost_cells(s, prim_in, stage == 1 && s->ghosts_stale);
         if (rc) return rc;
+        if (stage == 1) s->ghosts_stale = false;
         if (s->P.shock_detect && stage == 1) {
             // detect_shocks (phase 04) needs every ghost cell: wait for the halo of other ranks first
             if (!s->peers.empty()) CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
@@ -737,6 +762,16 @@ int eb200_commit(int sim)
             D.bc_kind[f] = b->bc[f].kind;
             if (b->bc[f].kind == EB200_BC_OUTFLOW_SIMPLE_FLUX) D.outflow_flux_faces |= (1 << f);
         }
+        D.push_mask = 0;
+        for (int f = 0; f < 6; ++f) D.push_off[f] = 0;
+        for (int f = 0; f < s->nfaces; ++f) {
+            const Block* ot = nullptr;
+            if (!face_pushes(s, b, f, &ot)) continue;
+            const int d = f / 2;
+            const long long nd = (d == 0) ? b->nic : (d == 1) ? b->njc : b->nkc;
+            D.push_mask |= (1 << f);
+            D.push_off[f] = (ot->cell0 - b->cell0) + ((f & 1) ? -nd : nd) * b->stride[d];
+        }
         D.cartesian = b->cartesian ? 1 : 0;
         (b->cartesian ? any_cart : any_general) = true;
         cells_total += (long long)b->nic * b->njc * b->nkc;
@@ -804,11 +839,11 @@ int eb200_commit(int sim)
         if (dev_upload(s, &s->d_gas, gv)) return -100;
     }
     if (dev_alloc(s, &s->d_status, 8)) return -100;
-    if (dev_alloc(s, &s->d_red, 2)) return -100;
-    if (dev_alloc(s, &s->d_last, 1)) return -100;
+    if (dev_alloc(s, &s->d_red, 2 * s->local.size())) return -100;
+    if (dev_alloc(s, &s->d_last, s->local.size())) return -100;
     CUDA_OK(cudaMallocHost((void**)&s->h_status, 8 * sizeof(int)));
     // 4. ghost-cell work lists
-    std::vector<EbCopyItem> copy; std::vector<EbReflectItem> refl; std::vector<EbFillItem> fill;
+    std::vector<EbCopyItem> copy, copy_pushed; std::vector<EbReflectItem> refl; std::vector<EbFillItem> fill;
     std::vector<double> params;
     std::map<int, Peer> peers;
     struct Key { int blk, face; };
@@ -825,10 +860,12 @@ int eb200_commit(int sim)
                 std::vector<int> recv_list, send_list;
                 std::vector<std::pair<long long, int>> recv_keyed, send_keyed;   // (receiver's cell index in its block, arena index)
                 int err = 0;
+                // the neighbour's flux kernel writes these ghost cells itself when it pushes through its face
+                std::vector<EbCopyItem>& copies = (ot->local && face_pushes(s, ot, bc.other_face, nullptr)) ? copy_pushed : copy;
                 for_face_ghosts(s, b, f, [&](int t1, int t2, int layer, long long, long long ghost, long long, long long) {
                     int ijk[3];
                     if (full_face_source(s, f, ot, bc.other_face, t1, t2, layer, ijk)) { err = 1; return; }
-                    if (ot->local) copy.push_back({ (int)(b->cell0 + ghost), (int)(ot->cell0 + ot->cidx(ijk[0], ijk[1], ijk[2])) });
+                    if (ot->local) copies.push_back({ (int)(b->cell0 + ghost), (int)(ot->cell0 + ot->cidx(ijk[0], ijk[1], ijk[2])) });
                     else recv_keyed.push_back({ ghost, (int)(b->cell0 + ghost) });
                 });
                 if (err) return -1;
@@ -867,9 +904,15 @@ int eb200_commit(int sim)
     }
     // order the work by destination address: neighbouring threads then touch neighbouring ghost cells
     std::sort(copy.begin(), copy.end(), [](const EbCopyItem& a, const EbCopyItem& b) { return a.dst < b.dst; });
+    std::sort(copy_pushed.begin(), copy_pushed.end(), [](const EbCopyItem& a, const EbCopyItem& b) { return a.dst < b.dst; });
     std::sort(refl.begin(), refl.end(), [](const EbReflectItem& a, const EbReflectItem& b) { return a.dst < b.dst; });
     std::sort(fill.begin(), fill.end(), [](const EbFillItem& a, const EbFillItem& b) { return a.dst < b.dst; });
     s->ncopy = (long long)copy.size(); s->nrefl = (long long)refl.size(); s->nfill = (long long)fill.size();
+    copy.insert(copy.end(), copy_pushed.begin(), copy_pushed.end());
+    s->ncopy_full = (long long)copy.size();
+    if (getenv("EB200_DEBUG"))
+        fprintf(stderr, "[eb200] rank %d: ghost work per stage: %lld copies (+%lld pushed by the flux kernel), %lld reflections, %lld fills; tma=%d\n",
+                s->cfg.rank, s->ncopy, s->ncopy_full - s->ncopy, s->nrefl, s->nfill, s->d_tmaps ? 1 : 0);
     if (dev_upload(s, &s->d_copy, copy)) return -100;
     if (dev_upload(s, &s->d_refl, refl)) return -100;
     if (dev_upload(s, &s->d_fill, fill)) return -100;
@@ -929,6 +972,7 @@ int eb200_upload_flow(int sim, int blk_id, const double* const* prims, int nprim
     CUDA_OK(cudaSetDevice(s->cfg.device));
     const size_t bytes = (size_t)b->ncp * sizeof(double);
     double* prim = s->A.prim[s->cur];
+    s->ghosts_stale = true;
     for (int v = 0; v < nprims; ++v)
         CUDA_OK(cudaMemcpyAsync(prim + (long long)v * s->P.total + b->cell0, prims[v], bytes, cudaMemcpyHostToDevice, s->stream));
     CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
@@ -978,20 +1022,27 @@ int eb200_compute_dt(int sim, double dt_current, double cfl_value, int check_cfl
     switch (s->n_stages) { case 1: cfl_allow = 0.9; break; case 2: cfl_allow = 1.2; break; case 3: cfl_allow = 1.6; break; default: cfl_allow = 0.9; }
     const double cfl_adjust = 0.5;
     double dt_allow_g = 1.7976931348623157e308, cfl_max_g = 0.0;
-    const unsigned long long init[2] = { 0x7ff0000000000000ULL, 0ULL };
-    for (Block* b : s->local) {
-        CUDA_OK(cudaMemcpyAsync(s->d_red, init, sizeof init, cudaMemcpyHostToDevice, s->stream));
-        MODE_CALL(s, launch_signal, s->P, s->hdesc[b->local_index], s->A, s->A.prim[s->cur], dt_current, cfl_value, s->d_red, s->d_last, s->stream);
-        CUDA_OK(cudaGetLastError());
-        unsigned long long red[2]; double last_signal;
-        CUDA_OK(cudaMemcpyAsync(red, s->d_red, sizeof red, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_OK(cudaMemcpyAsync(&last_signal, s->d_last, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        CUDA_OK(cudaStreamSynchronize(s->stream));
+    // one launch for all local blocks; per-block results so that the reference's per-block clamp applies
+    const size_t nl = s->local.size();
+    std::vector<unsigned long long> red(2 * nl);
+    std::vector<double> last(nl);
+    long long max_cells = 0;
+    for (size_t n = 0; n < nl; ++n) {
+        red[2 * n] = 0x7ff0000000000000ULL; red[2 * n + 1] = 0ULL;
+        max_cells = std::max(max_cells, (long long)s->local[n]->nic * s->local[n]->njc * s->local[n]->nkc);
+    }
+    CUDA_OK(cudaMemcpyAsync(s->d_red, red.data(), 2 * nl * sizeof(unsigned long long), cudaMemcpyHostToDevice, s->stream));
+    MODE_CALL(s, launch_signal, s->P, s->d_desc, (int)nl, max_cells, s->A, s->A.prim[s->cur], dt_current, cfl_value, s->d_red, s->d_last, s->stream);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(red.data(), s->d_red, 2 * nl * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaMemcpyAsync(last.data(), s->d_last, nl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    for (size_t n = 0; n < nl; ++n) {
         double dt_allow, cfl_max;
-        memcpy(&dt_allow, &red[0], 8); memcpy(&cfl_max, &red[1], 8);
+        memcpy(&dt_allow, &red[2 * n], 8); memcpy(&cfl_max, &red[2 * n + 1], 8);
         if (check_cfl && (cfl_max < 0.0 || cfl_max > cfl_allow)) {        // fluidblock.d:1072-1082
             cfl_max = cfl_adjust * cfl_allow;
-            dt_allow = cfl_max / last_signal;
+            dt_allow = cfl_max / last[n];
         }
         dt_allow_g = std::min(dt_allow_g, dt_allow);
         cfl_max_g = std::max(cfl_max_g, cfl_max);

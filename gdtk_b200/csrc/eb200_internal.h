@@ -59,7 +59,12 @@ struct EbBlockDesc {
     // (van Albada's epsilon is rescaled by 1/c^2 so that the limiter value is the same number)
     double uq[3][5];
     int outflow_flux_faces;   // bit f set: face f has EB200_BC_OUTFLOW_SIMPLE_FLUX
-    int pad0;
+    // Same-GPU full-face neighbours behind opposite, equally sized faces get their ghost cells written by
+    // the kernel that produces the FlowStates ("push"): a cell within two layers of face f is also stored
+    // at arena index c + push_off[f], the ghost cell of the neighbour that mirrors it (full_face_copy.d
+    // semantics for aligned blocks).  bit f of push_mask: face f pushes.
+    int push_mask;
+    long long push_off[6];
 };
 
 struct EbCurve {             // reference src/gas/thermo/cea_thermo_curves.d
@@ -128,9 +133,9 @@ struct EbFillItem { int dst, param; };
     void launch_decode(const EbParams& P, int gas_model, const EbGas* gas, const EbBlockDesc& hdesc,     \
                        const double* prim_in, double* prim_out, double* U, int do_encode, int* status,   \
                        cudaStream_t st);                                                                 \
-    void launch_signal(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A, const double* prim, \
-                       double dt_current, double cfl_value, unsigned long long* red, double* last_signal, \
-                       cudaStream_t st);                                                                 \
+    void launch_signal(const EbParams& P, const EbBlockDesc* descs, int nblocks, long long max_cells,   \
+                       const EbArena& A, const double* prim, double dt_current, double cfl_value,        \
+                       unsigned long long* red, double* last_signal, cudaStream_t st);                   \
     void launch_ghosts(const EbParams& P, const EbBlockDesc* desc, const EbArena& A, double* prim,       \
                        const EbCopyItem* copy, long long ncopy, const EbReflectItem* refl,               \
                        long long nrefl, const EbFillItem* fill, long long nfill, const double* params,   \

@@ -195,13 +195,28 @@ __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __rest
     return ok;
 }
 
+// Where else the FlowState of interior cell (i, j, k) at arena index c has to be stored: one ghost cell
+// per direction at most (blocks that push have at least four cells in every direction).
+template <int DIM>
+__device__ __forceinline__ void push_targets(const EbBlockDesc& D, int i, int j, int k, long long c,
+                                             long long& p0, long long& p1, long long& p2)
+{
+    p0 = p1 = p2 = -1;
+    const int m = D.push_mask;
+    if (!m) return;
+    if ((m & 1) && i < 2) p0 = c + D.push_off[0]; else if ((m & 2) && i >= D.nic - 2) p0 = c + D.push_off[1];
+    if ((m & 4) && j < 2) p1 = c + D.push_off[2]; else if ((m & 8) && j >= D.njc - 2) p1 = c + D.push_off[3];
+    if (DIM == 3) { if ((m & 16) && k < 2) p2 = c + D.push_off[4]; else if ((m & 32) && k >= D.nkc - 2) p2 = c + D.push_off[5]; }
+}
+
 // Stage update (simcore_gasdynamic_step.d:1250-1357) + decode_conserved (fvcell.d:586-821) +
 // check_data (fluidblock.d:607-675) for one cell whose residual dUdt[] is complete.
 // U0pre / d0pre: U0 and dUdt_prev[0] of the cell if the caller loaded them ahead of time (else nullptr)
 template <int DIM, int GASM, int NSP>
 __device__ __forceinline__ void finish_cell(const EbParams& P, const EbGas* __restrict__ gas, const EbStageArgs& S,
                                             long long total, long long c, const double* dUdt, bool& fail, int& n_invalid,
-                                            const double* U0pre = nullptr, const double* d0pre = nullptr)
+                                            const double* U0pre = nullptr, const double* d0pre = nullptr,
+                                            long long push0 = -1, long long push1 = -1, long long push2 = -1)
 {
     constexpr int NCQ = Layout<DIM, NSP>::NCQ;
     double U[NCQ], U0[NCQ], d0[NCQ];
@@ -234,6 +249,10 @@ __device__ __forceinline__ void finish_cell(const EbParams& P, const EbGas* __re
     if (rc) fail = true;
     else {
         store_prim<NSP>(Q, S.prim_out, total, c);
+        // ghost cells of same-GPU neighbours that mirror this cell (EbBlockDesc::push_off)
+        if (push0 >= 0) store_prim<NSP>(Q, S.prim_out, total, push0);
+        if (push1 >= 0) store_prim<NSP>(Q, S.prim_out, total, push1);
+        if (push2 >= 0) store_prim<NSP>(Q, S.prim_out, total, push2);
         if (!check_data<NSP>(P, Q)) n_invalid++;
     }
     if (S.U_out) {
@@ -367,7 +386,9 @@ flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBloc
             double dUdt[NCQ];
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) { double si = acc[q] - FB[q] * areaT; dUdt[q] = vol_inv * si + 0.0; }
-            finish_cell<DIM, GASM, NSP>(P, gas, S, total, cp, dUdt, fail, n_invalid);
+            long long p0, p1, p2;
+            push_targets<DIM>(D, i, j, k - 1, cp, p0, p1, p2);
+            finish_cell<DIM, GASM, NSP>(P, gas, S, total, cp, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
         }
 
         if (plane_has_cells) {
@@ -411,7 +432,9 @@ flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBloc
             double dUdt[NCQ];
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) dUdt[q] = vol_inv * acc[q] + ((q == Lay::iYMom) ? Qy : 0.0);
-            finish_cell<DIM, GASM, NSP>(P, gas, S, total, c, dUdt, fail, n_invalid);
+            long long p0, p1, p2;
+            push_targets<DIM>(D, i, j, 0, c, p0, p1, p2);
+            finish_cell<DIM, GASM, NSP>(P, gas, S, total, c, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
         }
     }
 

@@ -697,7 +697,9 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             double dUdt[NCQ];
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) { double si = acc[q] - fB[(q * TY + wy) * 32 + lane] * areaT; dUdt[q] = vol_inv * si + 0.0; }
-            finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, cp, dUdt, fail, n_invalid);
+            long long p0, p1, p2;
+            push_targets<DIM>(D, i, j, k - 1, cp, p0, p1, p2);
+            finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, cp, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
         }
 
         if (plane_has_cells && cell_ok) {
@@ -732,7 +734,9 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             double dUdt[NCQ];
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) dUdt[q] = vol_inv * acc[q] + ((q == Lay::iYMom) ? Qy : 0.0);
-            finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, c, dUdt, fail, n_invalid);
+            long long p0, p1, p2;
+            push_targets<DIM>(D, i, j, 0, c, p0, p1, p2);
+            finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, c, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
         }
     }
 

@@ -120,9 +120,19 @@ void launch_decode(const EbParams& P, int gas_model, const EbGas* gas, const EbB
 // red[0] = min dt_local, red[1] = max cfl_local as bit patterns of non-negative doubles.
 
 template <int DIM>
-__global__ void signal_kernel(const EbParams P, const EbBlockDesc D, const EbArena A, const double* __restrict__ prim,
-                              double dt_current, double cfl_value, unsigned long long* red, double* last_signal)
+__global__ void signal_kernel(const EbParams P, const EbBlockDesc* __restrict__ descs, const EbArena A, const double* __restrict__ prim,
+                              double dt_current, double cfl_value, unsigned long long* red_all, double* last_all)
 {
+    // blockIdx.y = local block; red_all[2*b], red_all[2*b+1], last_all[b] belong to block b
+    __shared__ EbBlockDesc D;
+    {
+        const int* src = reinterpret_cast<const int*>(&descs[blockIdx.y]);
+        int* dst = reinterpret_cast<int*>(&D);
+        for (int m = threadIdx.x; m < (int)(sizeof(EbBlockDesc) / sizeof(int)); m += blockDim.x) dst[m] = src[m];
+    }
+    __syncthreads();
+    unsigned long long* red = red_all + 2 * blockIdx.y;
+    double* last_signal = last_all + blockIdx.y;
     const long long n = (long long)D.nic * D.njc * D.nkc;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = P.total;
@@ -187,14 +197,14 @@ __global__ void signal_kernel(const EbParams P, const EbBlockDesc D, const EbAre
     }
 }
 
-void launch_signal(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A, const double* prim,
+// all local blocks in one launch; max_cells = cells of the largest block
+void launch_signal(const EbParams& P, const EbBlockDesc* descs, int nblocks, long long max_cells, const EbArena& A, const double* prim,
                    double dt_current, double cfl_value, unsigned long long* red, double* last_signal, cudaStream_t st)
 {
-    const long long n = (long long)hdesc.nic * hdesc.njc * hdesc.nkc;
     const int threads = 256;
-    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    if (P.dims == 3) signal_kernel<3><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, dt_current, cfl_value, red, last_signal);
-    else signal_kernel<2><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, dt_current, cfl_value, red, last_signal);
+    const dim3 grid((unsigned)((max_cells + threads - 1) / threads), (unsigned)nblocks);
+    if (P.dims == 3) signal_kernel<3><<<grid, threads, 0, st>>>(P, descs, A, prim, dt_current, cfl_value, red, last_signal);
+    else signal_kernel<2><<<grid, threads, 0, st>>>(P, descs, A, prim, dt_current, cfl_value, red, last_signal);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -211,16 +221,30 @@ __global__ void ghost_kernel(const EbParams P, const EbBlockDesc* __restrict__ d
     const long long total = P.total;
     const int nprim = P.nprim;
     if (t < ncopy) {
+        // sources are interior cells, destinations ghost cells: disjoint, so all loads of a batch can be
+        // in flight before the first store (the compiler cannot know that, prim is read and written)
         const EbCopyItem it = copy[t];
-        for (int v = 0; v < nprim; ++v) prim[v * total + it.dst] = prim[v * total + it.src];
+        const double* __restrict__ src = prim + it.src;
+        for (int v0 = 0; v0 < nprim; v0 += 8) {
+            double tmp[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) if (v0 + m < nprim) tmp[m] = __ldg(src + (long long)(v0 + m) * total);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) if (v0 + m < nprim) prim[(long long)(v0 + m) * total + it.dst] = tmp[m];
+        }
         if (P.shock_detect) A.S[it.dst] = A.S[it.src];          // FlowState.S travels with the FlowState
     } else if (t < ncopy + nrefl) {
         const EbReflectItem it = refl[t - ncopy];
-        for (int v = 0; v < nprim; ++v) {
-            if (v >= 5 && v <= 7) continue;
-            prim[v * total + it.dst] = prim[v * total + it.src];
+        const double* __restrict__ src = prim + it.src;
+        double x = __ldg(src + 5 * total), y = __ldg(src + 6 * total), z = __ldg(src + 7 * total);
+        {
+            double tmp[5];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) tmp[m] = __ldg(src + (long long)m * total);
+#pragma unroll
+            for (int m = 0; m < 5; ++m) prim[(long long)m * total + it.dst] = tmp[m];
         }
-        double x = prim[5 * total + it.src], y = prim[6 * total + it.src], z = prim[7 * total + it.src];
+        for (int v = 8; v < nprim; ++v) prim[v * total + it.dst] = __ldg(src + (long long)v * total);
         const int blk = it.meta >> 2, d = it.meta & 3;
         const EbBlockDesc& D = descs[blk];
         if (D.cartesian) {

@@ -75,13 +75,20 @@ def make_exchange(device_buffers):
     import torch
     import torch.distributed as dist
 
+    views = {}        # the library's halo buffers never move: wrap each (pointer, length) once
+
     def wrap(ptr, n):
         if n == 0:
             return None
-        if device_buffers:
-            return torch.as_tensor(_DevArray(ptr, n), device="cuda")
-        buf = (C.c_double * n).from_address(ptr)
-        return torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
+        t = views.get((ptr, n))
+        if t is None:
+            if device_buffers:
+                t = torch.as_tensor(_DevArray(ptr, n), device="cuda")
+            else:
+                buf = (C.c_double * n).from_address(ptr)
+                t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
+            views[(ptr, n)] = t
+        return t
 
     def exchange(user, npeers, peers, send, send_count, recv, recv_count, stream):
         try:

@@ -70,6 +70,7 @@ class Config:
         self.force_general_path = False
         self.force_generic_kernel = False  # testing knob: never use the tuned flux kernel
         self.no_tma = False                # testing knob: stage tiles with cp.async instead of TMA
+        self.no_push = False               # testing knob: all ghost cells are filled by the ghost-cell kernel
         self.block_index = None          # optional {block id: (ib, jb, kb)} left by the case factories
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -115,6 +116,7 @@ class Config:
         c.reserved_i[0] = int(self.force_general_path)
         c.reserved_i[1] = int(self.force_generic_kernel)
         c.reserved_i[2] = int(self.no_tma)
+        c.reserved_i[3] = int(self.no_push)
         c.rank = rank
         c.device = device
         c.epsilon_van_albada = self.epsilon_van_albada

@@ -152,7 +152,9 @@ typedef struct eb200_config {
     int device;                     /* CUDA device ordinal used by this process */
     int reserved_i[5];              /* testing knobs: [0] != 0 never use the uniform-Cartesian fast path;
                                        [1] != 0 always use the generic flux kernel;
-                                       [2] != 0 stage tiles with cp.async even where TMA could be used */
+                                       [2] != 0 stage tiles with cp.async even where TMA could be used;
+                                       [3] != 0 fill every ghost cell with the ghost-cell kernel (no stores into
+                                       neighbouring blocks from the flux kernel) */
     double epsilon_van_albada;      /* 1e-12 */
     double M_inf;                   /* 0.01 (ausm_plus_up) */
     double max_velocity;            /* flowstate_limits: 30000 */

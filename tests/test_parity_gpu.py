@@ -147,6 +147,21 @@ def test_tma_and_cp_async_staging_agree(product, case, strict):
     assert s1.dt_history == s2.dt_history
 
 
+@pytest.mark.parametrize("case", ["box3d", "box3d_sheared", "ffs", "sod3d", "tpg"])
+def test_pushed_and_copied_ghost_cells_agree(product, case):
+    """Ghost cells behind same-GPU block connections are written by the flux kernel itself (push) or by the
+    ghost-cell kernel (no_push): the same values either way, also across a failed step and a fresh upload."""
+    factory, kw, n = {"box3d": (cases.box3d, dict(n=32, nb=2), 8),
+                      "box3d_sheared": (cases.box3d, dict(n=16, nb=2, sheared=True), 6),
+                      "ffs": (cases.ffs, dict(nx=120, ny=40), 30),
+                      "sod3d": (cases.sod, dict(dims=3, ncells=48, nj=4, nk=4, nblocks=3), 20),
+                      "tpg": (cases.tpg_box3d, dict(n=12, nb=2), 4)}[case]
+    s1, U1, P1 = run_case(factory, product, n, strict=True, **kw)
+    s2, U2, P2 = run_case(factory, product, n, strict=True, no_push=True, **kw)
+    assert identical(U1, U2) and identical(P1, P2)
+    assert s1.dt_history == s2.dt_history
+
+
 def test_odd_block_width_uses_cp_async_path(oracle, product):
     # nic = 7 -> NI = 11: strides are not 16-byte multiples, TMA is not used
     _compare(cases.box3d, oracle, product, 6, n=14, nb=2)
