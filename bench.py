@@ -110,6 +110,11 @@ def build_case(args, workload):
         cfg, gm, blocks = cases.ffs(nx=args.ffs_nx, ny=args.ffs_ny, flux_calculator=args.flux)
         name = f"synthetic 2D Mach-3 forward-facing step {args.ffs_nx}x{args.ffs_ny}, 3 blocks, ideal air, l2r2+van Albada, {args.flux}, pc"
         balg = 224.0
+    elif workload == "tpg":
+        cfg, gm, blocks = cases.tpg_box3d(n=args.n, nb=args.nb, flux_calculator=args.flux)
+        name = (f"synthetic 3D {args.n}^3 thermally perfect 5-species air box (frozen chemistry), {args.nb ** 3} blocks of "
+                f"{args.n // args.nb}^3, l2r2+van Albada, {args.flux}, pc")
+        balg = 560.0
     else:
         cfg, gm, blocks = cases.box3d(n=args.n, nb=args.nb, flux_calculator=args.flux)
         name = (f"synthetic 3D {args.n}^3 ideal-air box, {args.nb ** 3} blocks of {args.n // args.nb}^3, uniform Cartesian, "
@@ -118,10 +123,10 @@ def build_case(args, workload):
     return cfg, gm, blocks, name, balg
 
 
-def cfl_dt(sim):
+def cfl_dt(sim, scale=1.0):
     dt_allow, _ = sim.compute_dt(False)
     dt_allow, _ = sim.reduce_dt(dt_allow, 0.0)
-    return dt_allow
+    return dt_allow * scale
 
 
 def run_gpu_workload(args, workload, rank, world, local_rank, with_e2e):
@@ -147,7 +152,7 @@ def run_gpu_workload(args, workload, rank, world, local_rank, with_e2e):
         t = torch.tensor([ncells_local], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         ncells = int(t.item())
-    dt = cfl_dt(sim)
+    dt = cfl_dt(sim, args.dt_scale)
     ext = torch.cuda.ExternalStream(int(lib.cuda_stream(h)))
 
     def barrier():
@@ -191,18 +196,29 @@ def run_gpu_workload(args, workload, rank, world, local_rank, with_e2e):
     # DRAM traffic of the dominant kernel per launch: bytes per cell measured by `ncu --set full`
     # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json) x the cells one launch processes
     traffic = None
+    fp64 = None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if workload == "box3d" and os.path.exists(tpath):
+    if workload == "box3d" and args.flux == "ausmdv" and os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f)["dram_bytes_per_cell_per_launch"] * ncells_local
+            prof = json.load(f)
+        traffic = prof["dram_bytes_per_cell_per_launch"] * ncells_local
+        # the kernel is bound by the FP64 pipe / instruction issue, not by HBM: place it against the FP64 pipe too.
+        # FP64-pipe instructions per cell and launch come from the same ncu capture, the pipe's peak from
+        # profiles/micro/fp64_peak.cu run on this pool's B200 (thread-level DFMA/s).
+        inst = prof["fp64_pipe_inst_per_cell_per_launch"] * ncells_local * args.steps * 2
+        fp64 = {"achieved": inst / (flux_ms * 1e-3) / 1e12, "peak": prof["fp64_pipe_peak_tinst_s"], "unit": "T inst/s (thread-level FP64-pipe instructions)",
+                "frac": inst / (flux_ms * 1e-3) / 1e12 / prof["fp64_pipe_peak_tinst_s"],
+                "note": "instructions per cell from the ncu capture in profiles/ (DFMA+DMUL+DADD+DSETP); peak measured with profiles/micro/fp64_peak.cu"}
     result = {
         "name": name, "value": value, "ms": ms, "ncells": ncells, "dt": dt, "launches": launches,
         "setup_s": t_setup, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_note": "ncu dram bytes per cell (256^3 capture, profiles/r1_traffic.json) x cells per launch; algorithmic = 140 B per cell per launch (280 B per cell-update over the 2 stage launches)", "peak_source": peak_src, "kernel": "flux_update_kernel",
+                     "traffic": traffic, "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per cell (256^3 capture, profiles/r1_traffic.json) x cells per launch; algorithmic = 140 B per cell per launch (280 B per cell-update over the 2 stage launches)", "peak_source": peak_src, "kernel": "flux_update_kernel",
                      "algorithmic_bytes_per_cell_update": balg, "kernel_ms_per_launch": flux_ms / max(1, flux_n),
                      "kernel_share_of_step": flux_ms / ms if ms > 0 else None},
     }
+    if fp64:
+        result["fp64_pipe"] = fp64
     if with_e2e:
         result["e2e"] = run_e2e(args, sim, dt, ncells, world)
     sim.close()
@@ -300,12 +316,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="box3d", choices=["box3d", "ffs"])
+    ap.add_argument("--workload", default="box3d", choices=["box3d", "ffs", "tpg"])
     ap.add_argument("--size", dest="n", type=int, default=512)
     ap.add_argument("--blocks-per-dim", dest="nb", type=int, default=4)
     ap.add_argument("--ffs-nx", type=int, default=4096)
     ap.add_argument("--ffs-ny", type=int, default=1024)
     ap.add_argument("--flux", default="ausmdv")
+    ap.add_argument("--dt-scale", type=float, default=1.0,
+                    help="fraction of the CFL time step to run at (ausm_plus_up is not stable at the full CFL step on the noisy box)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-n", type=int, default=128)
     ap.add_argument("--cpu-nb", type=int, default=4)
@@ -372,6 +390,8 @@ def main():
             "gpu_launches": main_res["launches"],
             "clocks": main_res["clocks"],
         }
+        if main_res.get("fp64_pipe"):
+            line["fp64_pipe"] = main_res["fp64_pipe"]
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if also:

@@ -17,11 +17,13 @@ for k in keys:
 rows = list(csv.reader(open(src)))
 h = None
 R = []
+nsec = 0
 for r in rows:
     if r and r[0] == 'Address':
         h = r
+        nsec += 1
         continue
-    if h and r and r[0].startswith('0x'):
+    if nsec == 1 and h and r and r[0].startswith('0x'):     # first kernel of the report only
         R.append(r)
 ie, isrc, ismp = h.index('Instructions Executed'), h.index('Source'), h.index('# Samples')
 tot = 0
