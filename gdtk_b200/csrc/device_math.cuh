@@ -226,17 +226,18 @@ __device__ __forceinline__ bool tpg_dzdT(const EbGas* __restrict__ g, const doub
 }
 
 // nm.newton.solve; Q.T / Q.u are written by every function evaluation like the reference's zeroFn.
-// rc: 0 root found, 1 NumericalMethodException, 2 GasModelException inside f
-template <int NSP>
-__device__ int tpg_newton(const EbGas* __restrict__ g, const double* massf, double e_tgt, double x0,
-                          double xMin, double xMax, double tol, double& root, double& Qu)
+// rc: 0 root found, 1 NumericalMethodException, 2 GasModelException inside f, 3 (evaluator) use the other evaluator
+// Eval: bool energy(T, u) and bool energy_and_slope(T, u, dfdT) with f = e_tgt - u(T), dfdT = -Cv(T)
+template <class Eval>
+__device__ __forceinline__ int newton_rtsafe(Eval& ev, double e_tgt, double x0, double xMin, double xMax, double tol,
+                                             double& root, double& Qu)
 {
     double xL = xMin, xH = xMax, u;
-    bool ok = tpg_energy<NSP>(g, massf, xL, u); Qu = u;
+    bool ok = ev.energy(xL, u); Qu = u;
     double fL = e_tgt - u;
-    ok &= tpg_energy<NSP>(g, massf, xH, u); Qu = u;
+    ok &= ev.energy(xH, u); Qu = u;
     double fH = e_tgt - u;
-    if (!ok) return 2;
+    if (!ok) return ev.failure_code();
     if ((fL > 0.0 && fH > 0.0) || (fL < 0.0 && fH < 0.0)) return 1;
     if (fL == 0.0) { root = xMin; return 0; }
     if (fH == 0.0) { root = xMax; return 0; }
@@ -244,11 +245,10 @@ __device__ int tpg_newton(const EbGas* __restrict__ g, const double* massf, doub
     double rts = x0;
     double dxold = (xMax - xMin);
     double dx = dxold;
-    ok &= tpg_energy<NSP>(g, massf, rts, u); Qu = u;
-    double f0 = e_tgt - u;
-    double df0;
-    ok &= tpg_dzdT<NSP>(g, massf, rts, df0);
-    if (!ok) return 2;
+    double f0, df0;
+    ok &= ev.energy_and_slope(rts, u, df0); Qu = u;
+    f0 = e_tgt - u;
+    if (!ok) return ev.failure_code();
     for (int j = 0; j < 30; ++j) {
         if ((((rts - xH) * df0 - f0) * ((rts - xL) * df0 - f0) > 0.0) || (fabs(2.0 * f0) > fabs(dxold * df0))) {
             dxold = dx;
@@ -257,20 +257,121 @@ __device__ int tpg_newton(const EbGas* __restrict__ g, const double* massf, doub
             if (xL == rts) { root = rts; return 0; }
         } else {
             dxold = dx;
-            dx = f0 / df0;
+            dx = eb_div(f0, df0);
             double tmp = rts;
             rts -= dx;
             if (tmp == rts) { root = rts; return 0; }
         }
         if (fabs(dx) < tol) { root = rts; return 0; }
-        ok &= tpg_energy<NSP>(g, massf, rts, u); Qu = u;
+        ok &= ev.energy_and_slope(rts, u, df0); Qu = u;
         f0 = e_tgt - u;
-        ok &= tpg_dzdT<NSP>(g, massf, rts, df0);
-        if (!ok) return 2;
+        if (!ok) return ev.failure_code();
         if (f0 < 0.0) xL = rts; else xH = rts;
     }
     return 1;
 }
+
+// species by species, in the reference's order of operations
+template <int NSP>
+struct SpeciesEval {
+    const EbGas* __restrict__ g;
+    const double* massf;
+    __device__ __forceinline__ bool energy(double T, double& u) const { return tpg_energy<NSP>(g, massf, T, u); }
+    __device__ __forceinline__ bool energy_and_slope(double T, double& u, double& df) const
+    {
+        bool ok = tpg_energy<NSP>(g, massf, T, u);
+        ok &= tpg_dzdT<NSP>(g, massf, T, df);
+        return ok;
+    }
+    __device__ __forceinline__ int failure_code() const { return 2; }
+};
+
+template <int NSP>
+__device__ __forceinline__ int tpg_newton(const EbGas* __restrict__ g, const double* massf, double e_tgt, double x0,
+                                          double xMin, double xMax, double tol, double& root, double& Qu)
+{
+    SpeciesEval<NSP> ev{ g, massf };
+    return newton_rtsafe(ev, e_tgt, x0, xMin, xMax, tol, root, Qu);
+}
+
+#ifdef EB_FAST_MATH
+// Throughput build: the mixture as one polynomial.  With common break points the NASA/CEA forms
+// (cea_thermo_curves.d:56-181) summed over the species give, with A_k = sum_i massf_i R_i a_ik,
+//   u(T)  = -A0/T + A1 ln T + (A2 - Rmix) T + A3 T^2/2 + A4 T^3/3 + A5 T^4/4 + A6 T^5/5 + A7
+//   Cv(T) =  A0/T^2 + A1/T + (A2 - Rmix) + A3 T + A4 T^2 + A5 T^3 + A6 T^4
+// inside a segment; in a blend zone the coefficients of the two segments are mixed with the
+// reference's weights.  Outside [T_low, T_high] (linear extrapolation there) the evaluator
+// says so and the caller takes the species-by-species route.
+template <int NSP>
+struct MixEval {
+    const EbGas* __restrict__ g;
+    const double* massf;
+    double A[8], B[8];          // lower / upper segment of the cached region
+    double Rmix;
+    int region;                 // 2 s: inside segment s; 2 i - 1: blend zone around break i; -1: nothing cached
+    bool left;                  // an evaluation fell outside the curves
+    __device__ __forceinline__ void init(const EbGas* __restrict__ g_, const double* massf_)
+    {
+        g = g_; massf = massf_; region = -1; left = false;
+        double r = 0.0;
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) r += massf[i] * g->Rsp[i];
+        Rmix = r;
+    }
+    __device__ __forceinline__ void mix(int seg, double* out) const
+    {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < NSP; ++i) a += massf[i] * g->RA[seg][k][i];
+            out[k] = a;
+        }
+    }
+    // region of T as cea_coeffs finds it, wB = weight of the upper segment
+    __device__ __forceinline__ int classify(double T, double& wB) const
+    {
+        const EbCurve& c = g->curves[0];
+        const int nb = c.nbreaks;
+        wB = 0.0;
+        if (T < c.T_low || T > c.T_high) return -1;
+        if (T < (c.T_breaks[1] - 0.5 * c.T_blends[0])) return 0;
+        if (T > (c.T_breaks[nb - 2] + 0.5 * c.T_blends[c.nseg - 2])) return 2 * (c.nseg - 1);
+        for (int i = 1; i < nb - 1; ++i) {
+            const double lo = c.T_breaks[i] - 0.5 * c.T_blends[i - 1], hi = c.T_breaks[i] + 0.5 * c.T_blends[i - 1];
+            if (T >= lo && T <= hi) { wB = (1. / c.T_blends[i - 1]) * (T - lo); return 2 * i - 1; }
+            if (T > hi && T < (c.T_breaks[i + 1] - 0.5 * c.T_blends[i])) return 2 * i;
+        }
+        return -1;
+    }
+    __device__ __forceinline__ bool energy_and_slope(double T, double& u, double& df)
+    {
+        double wB;
+        const int r = classify(T, wB);
+        if (r < 0) { left = true; u = 0.0; df = -1.0; return false; }
+        if (r != region) {
+            region = r;
+            if (r & 1) { mix((r - 1) >> 1, A); mix((r + 1) >> 1, B); }
+            else mix(r >> 1, A);
+        }
+        double a[8];
+        if (r & 1) {
+            const double wA = 1.0 - wB;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = wA * A[k] + wB * B[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = A[k];
+        }
+        const double rT = eb_rcp(T), lnT = log(T), a2 = a[2] - Rmix;
+        u = -a[0] * rT + a[1] * lnT + a[7] + T * (a2 + T * (0.5 * a[3] + T * ((1.0 / 3.0) * a[4] + T * (0.25 * a[5] + T * (0.2 * a[6])))));
+        df = -(rT * (a[0] * rT + a[1]) + a2 + T * (a[3] + T * (a[4] + T * (a[5] + T * a[6]))));
+        return true;
+    }
+    __device__ __forceinline__ bool energy(double T, double& u) { double df; return energy_and_slope(T, u, df); }
+    __device__ __forceinline__ int failure_code() const { return left ? 3 : 2; }
+};
+#endif
 
 // gmodel.update_thermo_from_rhou: T is the starting guess on entry (TPG).  Returns false where the
 // reference throws GasModelException.
@@ -287,8 +388,20 @@ __device__ __forceinline__ bool thermo_from_rhou(const EbGas* __restrict__ g, Pr
         double T1 = fmax(Q.T - 0.5 * 1000.0, 10.0);
         double T2 = T1 + 1000.0;
         double root, Qu = Q.u;
-        int rc = tpg_newton<NSP>(g, Q.massf, e_tgt, Tsave, T1, T2, 1.0e-6, root, Qu);
-        if (rc == 1) rc = tpg_newton<NSP>(g, Q.massf, e_tgt, Tsave, 10.0, 100000.0, 1.0e-6, root, Qu);
+        int rc = 3;
+#ifdef EB_FAST_MATH
+        if (g->uniform_curves) {
+            MixEval<NSP> ev;
+            ev.init(g, Q.massf);
+            rc = newton_rtsafe(ev, e_tgt, Tsave, T1, T2, 1.0e-6, root, Qu);
+            // (the second, wide bracket [10, 100000] K leaves the curves at both ends: species route)
+        }
+#endif
+        if (rc == 3 || rc == 1) {
+            Qu = Q.u;
+            rc = tpg_newton<NSP>(g, Q.massf, e_tgt, Tsave, T1, T2, 1.0e-6, root, Qu);
+            if (rc == 1) rc = tpg_newton<NSP>(g, Q.massf, e_tgt, Tsave, 10.0, 100000.0, 1.0e-6, root, Qu);
+        }
         if (rc == 2) { Q.u = Qu; return false; }
         if (rc == 1) { Q.T = Tsave; tpg_energy<NSP>(g, Q.massf, Tsave, Q.u); return false; }
         Q.T = root; Q.u = Qu;
@@ -326,6 +439,18 @@ __device__ __forceinline__ bool sound_speed(const EbGas* __restrict__ g, Prim<NS
         Q.a = eb_sqrt(g->gamma * g->Rgas * Q.T);
         return true;
     } else {                                // therm_perf_gas.d:394-430, gas_model.d:205
+#ifdef EB_FAST_MATH
+        if (g->uniform_curves) {
+            MixEval<NSP> ev;
+            ev.init(g, Q.massf);
+            double u, df;
+            if (ev.energy_and_slope(Q.T, u, df)) {
+                const double Cv = -df, Cp = Cv + ev.Rmix;
+                Q.a = eb_sqrt(Cp * eb_rcp(Cv) * (ev.Rmix * Q.T));
+                return true;
+            }
+        }
+#endif
         double Cp = 0.0, Cv = 0.0, R = 0.0;
         bool ok = true;
         double cps[NSP];

@@ -616,6 +616,16 @@ int eb200_init(const eb200_config* cfg)
             c.Cp_low = h_Cp(c, c.T_low); c.Cp_high = h_Cp(c, c.T_high);
             c.h_low = h_h(c, c.T_low); c.h_high = h_h(c, c.T_high);
         }
+        g.uniform_curves = (g.curves[0].nseg >= 2) ? 1 : 0;
+        for (int i = 1; i < g.nsp; ++i) {
+            const EbCurve& a = g.curves[0]; const EbCurve& b = g.curves[i];
+            if (a.nseg != b.nseg) { g.uniform_curves = 0; break; }
+            for (int k = 0; k <= a.nseg; ++k) if (a.T_breaks[k] != b.T_breaks[k]) g.uniform_curves = 0;
+            for (int k = 0; k < a.nseg; ++k) if (a.T_blends[k] != b.T_blends[k]) g.uniform_curves = 0;
+        }
+        for (int i = 0; i < g.nsp; ++i)
+            for (int sg = 0; sg < g.curves[i].nseg; ++sg)
+                for (int k = 0; k < 8; ++k) g.RA[sg][k][i] = g.curves[i].R * g.curves[i].coeffs[sg][k];
     }
     CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     {

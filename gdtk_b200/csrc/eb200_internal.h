@@ -81,6 +81,10 @@ struct EbGas {
     double Rgas, gamma, Cv, Cvinv, Cp, gamma_CpCv;
     double Rsp[EB_MAXSP];
     EbCurve curves[EB_MAXSP];
+    // throughput build: when all species share break points and blend ranges, the mixture's energy and
+    // Cv are ONE polynomial in T whose coefficients are sum_i massf_i * RA[seg][k][i], RA = R_i * a_i[seg][k]
+    int uniform_curves, pad1;
+    double RA[EB_MAXSEG][8][EB_MAXSP];
 };
 
 struct EbParams {            // passed by value to kernels (kept small)
