@@ -116,8 +116,9 @@ def build_case(args, workload):
                 f"{args.n // args.nb}^3, l2r2+van Albada, {args.flux}, pc")
         balg = 560.0
     else:
-        cfg, gm, blocks = cases.box3d(n=args.n, nb=args.nb, flux_calculator=args.flux)
-        name = (f"synthetic 3D {args.n}^3 ideal-air box, {args.nb ** 3} blocks of {args.n // args.nb}^3, uniform Cartesian, "
+        cfg, gm, blocks = cases.box3d(n=args.n, nb=args.nb, flux_calculator=args.flux, sheared=args.sheared)
+        name = (f"synthetic 3D {args.n}^3 ideal-air box, {args.nb ** 3} blocks of {args.n // args.nb}^3, "
+                f"{'k-lines sheared by 10 degrees (general-metric path)' if args.sheared else 'uniform Cartesian'}, "
                 f"l2r2+van Albada, {args.flux}, pc")
         balg = 280.0
     return cfg, gm, blocks, name, balg
@@ -322,6 +323,7 @@ def main():
     ap.add_argument("--ffs-nx", type=int, default=4096)
     ap.add_argument("--ffs-ny", type=int, default=1024)
     ap.add_argument("--flux", default="ausmdv")
+    ap.add_argument("--sheared", action="store_true", help="box3d on a sheared grid: every block takes the general-metric path")
     ap.add_argument("--dt-scale", type=float, default=1.0,
                     help="fraction of the CFL time step to run at (ausm_plus_up is not stable at the full CFL step on the noisy box)")
     ap.add_argument("--e2e-steps", type=int, default=2)

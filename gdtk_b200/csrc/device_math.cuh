@@ -516,11 +516,11 @@ __device__ __forceinline__ void interp_scalar(const EbWeights& w, bool limiter, 
 __device__ __forceinline__ void l2r2_prepare(EbWeights& w, double lenL1, double lenL0, double lenR0, double lenR1)
 {
     w.lenL0 = lenL0; w.lenR0 = lenR0;
-    w.aL0 = 0.5 * lenL0 / (lenL1 + 2.0 * lenL0 + lenR0);
-    w.aR0 = 0.5 * lenR0 / (lenL0 + 2.0 * lenR0 + lenR1);
-    w.two_over_L0L1 = 2.0 / (lenL0 + lenL1);
-    w.two_over_R0L0 = 2.0 / (lenR0 + lenL0);
-    w.two_over_R1R0 = 2.0 / (lenR1 + lenR0);
+    w.aL0 = eb_div(0.5 * lenL0, (lenL1 + 2.0 * lenL0 + lenR0));
+    w.aR0 = eb_div(0.5 * lenR0, (lenL0 + 2.0 * lenR0 + lenR1));
+    w.two_over_L0L1 = eb_div(2.0, (lenL0 + lenL1));
+    w.two_over_R0L0 = eb_div(2.0, (lenR0 + lenL0));
+    w.two_over_R1R0 = eb_div(2.0, (lenR1 + lenR0));
     w.two_L0_plus_L1 = (2.0 * lenL0 + lenL1);
     w.two_R0_plus_R1 = (2.0 * lenR0 + lenR1);
 }

@@ -382,7 +382,7 @@ flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBloc
         if (DIM == 3 && k > k0 && cell_ok) {
             const long long cp = c - sk;
             const double areaT = CART ? D.area[2] : ldg(A.face[2] + 9 * total + c);
-            const double vol_inv = CART ? D.vol_inv : 1.0 / ldg(A.vol + cp);
+            const double vol_inv = CART ? D.vol_inv : eb_div(1.0, ldg(A.vol + cp));
             double dUdt[NCQ];
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) { double si = acc[q] - FB[q] * areaT; dUdt[q] = vol_inv * si + 0.0; }
@@ -423,7 +423,7 @@ flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBloc
 
         if (DIM == 2 && cell_ok) {
             const double vol = CART ? D.vol : ldg(A.vol + c);
-            const double vol_inv = CART ? D.vol_inv : 1.0 / vol;
+            const double vol_inv = CART ? D.vol_inv : eb_div(1.0, vol);
             double Qy = 0.0;
             if (P.axisymmetric) {      // fvcell.d:1161-1165
                 const double axy = CART ? D.areaxy : ldg(A.areaxy + c);

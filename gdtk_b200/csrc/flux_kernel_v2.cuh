@@ -367,10 +367,15 @@ __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __rest
         R.p = ldg(prim_fallback + 2 * total + cR0); R.T = ldg(prim_fallback + 3 * total + cR0);
     } else { R.T = R.u * gas->Cvinv; R.p = R.rho * gas->Rgas * R.T; }
     if (ROT) {
+#ifdef EB_FAST_MATH
+        // the reference's trip back to the global frame and into the face frame again is the identity
+        if (!P.local_frame) { to_local<DIM>(fr, L.vx, L.vy, L.vz); to_local<DIM>(fr, R.vx, R.vy, R.vz); }
+#else
         if (P.local_frame) {   // reference: back to global (onedinterp.d:979-987), then into the face frame again
             to_global<DIM>(fr, L.vx, L.vy, L.vz); to_global<DIM>(fr, R.vx, R.vy, R.vz);
         }
         to_local<DIM>(fr, L.vx, L.vy, L.vz); to_local<DIM>(fr, R.vx, R.vy, R.vz);
+#endif
     }
 #ifdef EB_FAST_MATH
     if (!ROT && FLUX != EB200_FLUX_ROE) {
@@ -700,7 +705,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
         if (DIM == 3 && k > k0 && cell_ok) {
             const long long cp = c - sk;
             const double areaT = CART ? D.area[2] : ldg(A.face[2] + 9 * total + c);
-            const double vol_inv = CART ? D.vol_inv : 1.0 / ldg(A.vol + cp);
+            const double vol_inv = CART ? D.vol_inv : eb_div(1.0, ldg(A.vol + cp));
             double dUdt[NCQ];
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) { double si = acc[q] - fB[(q * TY + wy) * 32 + lane] * areaT; dUdt[q] = vol_inv * si + 0.0; }
@@ -732,7 +737,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
 
         if (DIM == 2 && cell_ok) {
             const double vol = CART ? D.vol : ldg(A.vol + c);
-            const double vol_inv = CART ? D.vol_inv : 1.0 / vol;
+            const double vol_inv = CART ? D.vol_inv : eb_div(1.0, vol);
             double Qy = 0.0;
             if (P.axisymmetric) {      // fvcell.d:1161-1165
                 const double axy = CART ? D.areaxy : ldg(A.areaxy + c);
