@@ -458,12 +458,18 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
     constexpr int NCQ = Lay::NCQ;
     constexpr int NT = 32 * TY;
     extern __shared__ __align__(128) double smem[];
-    // layout: tile[2][SIZE] | fW[2][NCQ][TY][33] | fS[2][NCQ][TY+1][32] | fB[2][NCQ][TY][32] | desc
+    // layout: tile[2][SIZE] | fW[NCQ][TY][32] | fX[2][NCQ][TY] | fS[2][NCQ][TY+1][32] | fB[NCQ][TY][32] | ring[2][6][TY][32] | desc
+    //   fW: west-face fluxes, exchanged inside a warp only (single buffer + __syncwarp); fX: the faces east of
+    //   lane 31, written by another warp (double buffered like fS); fB: bottom-face flux, private to its thread;
+    //   ring (3D): the thread's own cell values (rho, u, a, vx, vy, vz) of the two planes below, for the k-stencil.
     double* tile = smem;
     double* fWs = tile + 2 * T::SIZE;
-    double* fSs = fWs + 2 * NCQ * TY * 33;
+    double* fXs = fWs + NCQ * TY * 32;
+    double* fSs = fXs + 2 * NCQ * TY;
     double* fBs = fSs + 2 * NCQ * (TY + 1) * 32;
-    EbBlockDesc& D = *reinterpret_cast<EbBlockDesc*>(fBs + 2 * NCQ * TY * 32);
+    double* ring = fBs + NCQ * TY * 32;
+    constexpr int RING = (DIM == 3) ? 2 * 6 * TY * 32 : 0;
+    EbBlockDesc& D = *reinterpret_cast<EbBlockDesc*>(ring + RING);
     __shared__ int s_blk;
     __shared__ __align__(8) unsigned long long s_bar[2];      // tile[buf] has landed (TMA staging)
 
@@ -547,6 +553,17 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
 
     const int kend = (DIM == 3) ? k1 : 0;
     stage_plane(k0, 0);
+    double* const myring = ring + wy * 32 + lane;           // [slot][field] at stride TY*32
+    if (DIM == 3 && cell_ok) {
+        // own cell values of the planes k0-2 (slot of even/odd plane parity) and k0-1
+        const long long c0 = D.cell0 + ((long long)(k0 + D.kg) * NJ + (j + EB_NG)) * NI + (i + EB_NG);
+#pragma unroll
+        for (int m = 1; m <= 2; ++m) {
+            double* r = myring + ((k0 - m) & 1) * 6 * TY * 32;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) r[f * TY * 32] = ldg(S.prim_in + (long long)T::prim_index(f) * total + c0 - m * sk);
+        }
+    }
     wait_plane(0);
     __syncthreads();
 
@@ -556,10 +573,12 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
         // prefetch the next plane (its own cells are needed for the top face of the chunk too)
         if (DIM == 3 && k < kend) stage_plane(k + 1, buf ^ 1);
         const double* tl = tile + buf * T::SIZE;
-        double* fW = fWs + buf * NCQ * TY * 33;
+        double* fW = fWs;
+        double* fX = fXs + buf * NCQ * TY;
         double* fS = fSs + buf * NCQ * (TY + 1) * 32;
-        double* fB = fBs + buf * NCQ * TY * 32;
+        double* fB = fBs;
         const long long c = D.cell0 + ((long long)(k + D.kg) * NJ + (j + EB_NG)) * NI + (i + EB_NG);
+        __syncwarp();          // fW is reused: every lane has read the previous plane's west fluxes
 
         // ---------------- the faces of this plane: one loop, ONE inlined copy of the face arithmetic -------
         // job 0: west face (d=0), job 1: south face (d=1), job 2: bottom face (d=2, 3D),
@@ -584,7 +603,8 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             // where this face's flux goes: component q at out[q * qstride]
             double* out;
             int qstride;
-            if (d == 0) { out = fW + (row - 2) * 33 + (col - 2); qstride = TY * 33; }
+            if (job == 3 && d == 0) { out = fX + (row - 2); qstride = TY; }
+            else if (d == 0) { out = fW + wy * 32 + lane; qstride = TY * 32; }
             else if (d == 1) { out = fS + (row - 2) * 32 + (col - 2); qstride = (TY + 1) * 32; }
             else { out = fB + wy * 32 + lane; qstride = TY * 32; }
             const long long cf = (job < 3) ? c : c + (long long)(fj - j) * NI + (fi - i);
@@ -635,35 +655,44 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
                 }
                 s.aL = (q0 - so)[T::F_A * T::FSZ];
             } else if (UNIFORM) {
-                // own column: plane k from the tile, planes k-2, k-1, k+1 from global memory (L2); d == 2: (z, x, y)
+                // own column: plane k from the tile, planes k-2 and k-1 from the thread's ring, plane k+1 from
+                // global memory (it is still on its way into the other tile buffer); d == 2: (z, x, y)
                 const double* pin = S.prim_in;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     if (m == 2) {
                         s.rho[m] = q0[T::F_RHO * T::FSZ]; s.u[m] = q0[T::F_U * T::FSZ];
                         s.v0[m] = q0[(T::F_V + 2) * T::FSZ]; s.v1[m] = q0[(T::F_V + 0) * T::FSZ]; s.v2[m] = q0[(T::F_V + 1) * T::FSZ];
-                    } else {
-                        const double* pm = pin + cf + (m - 2) * sk;
+                    } else if (m == 3) {
+                        const double* pm = pin + cf + sk;
                         s.rho[m] = ldg(pm); s.u[m] = ldg(pm + total);
                         s.v0[m] = ldg(pm + 7 * total); s.v1[m] = ldg(pm + 5 * total); s.v2[m] = ldg(pm + 6 * total);
+                    } else {
+                        const double* r = myring + ((k + m) & 1) * 6 * TY * 32;      // plane k-2+m has the parity of k+m
+                        s.rho[m] = r[T::F_RHO * TY * 32]; s.u[m] = r[T::F_U * TY * 32];
+                        s.v0[m] = r[(T::F_V + 2) * TY * 32]; s.v1[m] = r[(T::F_V + 0) * TY * 32]; s.v2[m] = r[(T::F_V + 1) * TY * 32];
                     }
                 }
-                s.aL = ldg(pin + 4 * total + cf - sk);
+                s.aL = (myring + ((k + 1) & 1) * 6 * TY * 32)[T::F_A * TY * 32];
             } else {
-                // own column: plane k from the tile, planes k-2, k-1, k+1 from global memory (L2)
+                // own column: plane k from the tile, planes k-2 and k-1 from the thread's ring, plane k+1 from global memory
                 const double* pin = S.prim_in;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     if (m == 2) {
                         s.rho[m] = q0[T::F_RHO * T::FSZ]; s.u[m] = q0[T::F_U * T::FSZ];
                         s.v0[m] = q0[(T::F_V + 0) * T::FSZ]; s.v1[m] = q0[(T::F_V + 1) * T::FSZ]; s.v2[m] = q0[(T::F_V + 2) * T::FSZ];
-                    } else {
-                        const double* pm = pin + cf + (m - 2) * sk;
+                    } else if (m == 3) {
+                        const double* pm = pin + cf + sk;
                         s.rho[m] = ldg(pm); s.u[m] = ldg(pm + total);
                         s.v0[m] = ldg(pm + 5 * total); s.v1[m] = ldg(pm + 6 * total); s.v2[m] = ldg(pm + 7 * total);
+                    } else {
+                        const double* r = myring + ((k + m) & 1) * 6 * TY * 32;
+                        s.rho[m] = r[T::F_RHO * TY * 32]; s.u[m] = r[T::F_U * TY * 32];
+                        s.v0[m] = r[(T::F_V + 0) * TY * 32]; s.v1[m] = r[(T::F_V + 1) * TY * 32]; s.v2[m] = r[(T::F_V + 2) * TY * 32];
                     }
                 }
-                s.aL = ldg(pin + 4 * total + cf - sk);
+                s.aL = (myring + ((k + 1) & 1) * 6 * TY * 32)[T::F_A * TY * 32];
             }
             s.aR = q0[T::F_A * T::FSZ];
             Frame fr;
@@ -698,6 +727,13 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             for (int q = 0; q < NCQ; ++q) out[q * qstride] = Fl[q];
         }
 
+        if (DIM == 3 && cell_ok && plane_has_cells) {
+            // this plane's own cell replaces plane k-2 in the ring (same parity); nobody else reads the slot
+            const double* q0 = tl + (wy + 2) * T::COLS + (lane + 2);
+            double* r = myring + (k & 1) * 6 * TY * 32;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) r[f * TY * 32] = q0[f * T::FSZ];
+        }
         if (DIM == 3 && k < kend) wait_plane(k + 1 - k0);
         __syncthreads();
 
@@ -724,7 +760,8 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             }
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) {
-                const double FW = fW[(q * TY + wy) * 33 + lane], FE = fW[(q * TY + wy) * 33 + lane + 1];
+                const double FW = fW[(q * TY + wy) * 32 + lane];
+                const double FE = (lane == 31) ? fX[q * TY + wy] : fW[(q * TY + wy) * 32 + lane + 1];
                 const double FS = fS[(q * (TY + 1) + wy) * 32 + lane], FN = fS[(q * (TY + 1) + wy + 1) * 32 + lane];
                 double si = FW * aW;          // 0 - F*(-A)
                 si = si - FE * aE;
@@ -767,7 +804,8 @@ constexpr size_t v2_smem_bytes()
 {
     typedef Tile<DIM, TY> T;
     constexpr int NCQ = Layout<DIM, 1>::NCQ;
-    return sizeof(double) * (2 * T::SIZE + 2 * NCQ * TY * 33 + 2 * NCQ * (TY + 1) * 32 + 2 * NCQ * TY * 32) + sizeof(EbBlockDesc);
+    return sizeof(double) * (2 * T::SIZE + NCQ * TY * 32 + 2 * NCQ * TY + 2 * NCQ * (TY + 1) * 32 + NCQ * TY * 32 +
+                             ((DIM == 3) ? 2 * 6 * TY * 32 : 0)) + sizeof(EbBlockDesc);
 }
 
 template <int DIM, int FLUX, bool CART, bool CLIP>
