@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _abi
 from .gas import FlowState, IdealGas, set_gas_model
-from .grids import (box_grid_2d, box_grid_3d, quad_patch_grid, split_grid, connect_block_array,
+from .grids import (box_grid_2d, box_grid_3d, quad_patch_grid, split_grid, connect_block_array, roberts_function, hex_volume_grid,
                     uniform_box_geometry)
 from .sim import (Config, FluidBlock, InFlowBC_Supersonic, OutFlowBC_Simple, OutFlowBC_SimpleExtrapolate,
                   WallBC_WithSlip, identify_block_connections)
@@ -51,6 +51,35 @@ def cone20(flux_calculator="ausmdv", nx0=10, nx1=30, ny=40, **cfg_kw):
     identify_block_connections([blk0, blk1], 2)
     blk0.bcList["west"] = InFlowBC_Supersonic(inflow)
     blk1.bcList["east"] = OutFlowBC_Simple()
+    return cfg, gm, [blk0, blk1]
+
+
+def ramp3d(flux_calculator="adaptive_hanel_ausmdv", **cfg_kw):
+    """Mach 1.5 flow over a 10-degree ramp, 3D, two blocks (examples/eilmer/3D/simple-ramp/sg/ramp.lua):
+    10x4x40 cells ahead of the ramp, 30x4x40 over it, k-lines clustered towards the wedge surface with
+    RobertsFunction(end0=true, end1=false, beta=1.2), Euler update, the default flux calculator.  The
+    reference's test expects 862 +- 3 steps to t = 5 ms (ramp-test.rb:33)."""
+    gm = ideal_air()
+    cfg = Config(dimensions=3, flux_calculator=flux_calculator, gasdynamic_update_scheme="euler",
+                 max_time=5.0e-3, max_step=1000, dt_init=1.0e-6, cfl_value=0.5)
+    for k, v in cfg_kw.items():
+        setattr(cfg, k, v)
+    initial = FlowState(gm, p=5955.0, T=304.0, velx=0.0)
+    inflow = FlowState(gm, p=95.84e3, T=1103.0, velx=1000.0)
+
+    def box(x0, xs, ys=0.1, zs=1.0):
+        return [[x0, 0, 0], [x0 + xs, 0, 0], [x0 + xs, ys, 0], [x0, ys, 0],
+                [x0, 0, zs], [x0 + xs, 0, zs], [x0 + xs, ys, zs], [x0, ys, zs]]
+    cluster_k = roberts_function(True, False, 1.2)
+    grid0 = hex_volume_grid(box(0.0, 0.2), 11, 5, 41, cf_t=cluster_k)
+    c1 = box(0.2, 0.8)
+    c1[1][2] = c1[2][2] = 0.8 * math.tan(math.pi * 10.0 / 180.0)
+    grid1 = hex_volume_grid(c1, 31, 5, 41, cf_t=cluster_k)
+    blk0 = FluidBlock(grid0, initial, id=0)
+    blk1 = FluidBlock(grid1, initial, id=1)
+    blk0.bcList["west"] = InFlowBC_Supersonic(inflow)
+    blk1.bcList["east"] = OutFlowBC_Simple()
+    identify_block_connections([blk0, blk1], 3)
     return cfg, gm, [blk0, blk1]
 
 

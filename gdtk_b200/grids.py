@@ -38,6 +38,47 @@ def quad_patch_grid(p00, p10, p11, p01, nic, njc):
     return out[0], out[1]
 
 
+def roberts_function(end0, end1, beta):
+    """RobertsFunction of src/geom/misc/univariatefunctions.d:110-181 as a callable on [0, 1]."""
+    cluster = (end0 or end1) and beta > 1.0
+    alpha = 0.5 if (end0 and end1) else 0.0
+    reverse = bool(end0 and not end1)
+
+    def f(t):
+        t = np.asarray(t, dtype=float)
+        if reverse:
+            t = 1.0 - t
+        if cluster:
+            lam = ((beta + 1.0) / (beta - 1.0)) ** ((t - alpha) / (1.0 - alpha))
+            tbar = ((beta + 2.0 * alpha) * lam - beta + 2.0 * alpha) / ((2.0 * alpha + 1.0) * (1.0 + lam))
+        else:
+            tbar = t
+        return 1.0 - tbar if reverse else tbar
+    return f
+
+
+def hex_volume_grid(corners, niv, njv, nkv, cf_r=None, cf_s=None, cf_t=None):
+    """StructuredGrid:new{pvolume=TFIVolume:new{vertices=p0..p7}, niv=, njv=, nkv=, cfList=} for a
+    hexahedron with straight edges (then the TFI volume is the trilinear map of its corners) and one
+    cluster function per parameter direction (all four edges of a direction alike, so the blended
+    parameter of sgrid.d:690-732 is the edge value).  corners: p0..p7 in Eilmer's order (p0-p3 bottom
+    face counter-clockwise, p4-p7 above them).  Returns X, Y, Z of shape (nkv, njv, niv)."""
+    ident = lambda t: np.asarray(t, dtype=float)
+    r = (cf_r or ident)(np.arange(niv) / (niv - 1))[None, None, :]
+    s = (cf_s or ident)(np.arange(njv) / (njv - 1))[None, :, None]
+    t = (cf_t or ident)(np.arange(nkv) / (nkv - 1))[:, None, None]
+    P = np.asarray(corners, dtype=float)
+    w = [(1 - r) * (1 - s) * (1 - t), r * (1 - s) * (1 - t), r * s * (1 - t), (1 - r) * s * (1 - t),
+         (1 - r) * (1 - s) * t, r * (1 - s) * t, r * s * t, (1 - r) * s * t]
+    out = []
+    for m in range(3):
+        a = 0.0
+        for n in range(8):
+            a = a + w[n] * P[n][m]
+        out.append(np.ascontiguousarray(a))
+    return out[0], out[1], out[2]
+
+
 def uniform_box_geometry(dims, nic, njc, nkc, dx, dy, dz=1.0):
     """BlockGeometry of a uniform Cartesian block without touching every vertex.
 

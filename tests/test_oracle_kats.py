@@ -9,6 +9,8 @@ CPU oracle.  fluxcalc.d / onedinterp.d / fvcell.d have no function-level vectors
    Run here with flux_calculator='ausmdv' and a Coons patch for the second block (see
    gdtk_b200/cases.py), hence the slightly wider step-count window.
 """
+import math
+
 import numpy as np
 
 from gdtk_b200 import Simulation, cases
@@ -77,6 +79,63 @@ def test_cone20_with_the_reference_default_flux_calculator(oracle):
     p_surface = float(sim.interior(1, P[2])[0, 0, 20])
     q_inf = 0.5 * (95.84e3 / (gm.Rgas * 1103.0)) * 1000.0 ** 2
     assert abs(p_surface - (95.84e3 + 0.387 * q_inf)) < 1.0e3
+    sim.close()
+
+
+def ramp_force(sim, blocks):
+    """estimate_ramp_force.lua: minus the pressure force on the bottom (k = 0) faces of block 1."""
+    from gdtk_b200.geometry import NG
+    g = blocks[1].geom
+    p = sim.interior(1, sim.download_flow(1)[2])[0]                  # k = 0 layer, (njc, nic)
+    sl = (g.kg, slice(NG, NG + g.njc), slice(NG, NG + g.nic))
+    f = g.face[2]
+    return [-float(np.sum(f[9][sl] * p * f[m][sl])) for m in range(3)]
+
+
+def ramp_shock_angle(sim, blocks):
+    """estimate_shock_angle.lua: 30 % pressure rise along every i-strip, straight-line fit in (x, z)."""
+    from gdtk_b200.geometry import NG
+    xs, zs, ps = [], [], []
+    for b in blocks:
+        g = b.geom
+        sl = (slice(g.kg, g.kg + g.nkc), slice(NG, NG + g.njc), slice(NG, NG + g.nic))
+        xs.append(g.pos[0][sl]); zs.append(g.pos[2][sl]); ps.append(sim.interior(b.id, sim.download_flow(b.id)[2]))
+    X, Z, P = (np.concatenate(a, axis=2) for a in (xs, zs, ps))
+    xsh, ysh = [], []
+    for k in range(P.shape[0]):
+        for j in range(P.shape[1]):
+            x, y, p = X[k, j], Z[k, j], P[k, j]
+            trig = p[0] + 0.3 * (p.max() - p[0])
+            xo, yo, po = x[0], y[0], p[0]
+            xn, yn, pn = xo, yo, po
+            for i in range(1, len(p)):
+                xn, yn, pn = x[i], y[i], p[i]
+                if pn > trig:
+                    break
+                xo, yo, po = xn, yn, pn
+            fr = (trig - po) / (pn - po)
+            xl, yl = xo * (1 - fr) + xn * fr, yo * (1 - fr) + yn * fr
+            if xl < 0.65:
+                xsh.append(xl); ysh.append(yl)
+    xsh, ysh = np.array(xsh), np.array(ysh)
+    a1 = (np.mean(xsh * ysh) - xsh.mean() * ysh.mean()) / (np.mean(xsh * xsh) - xsh.mean() ** 2)
+    a0 = ysh.mean() - a1 * xsh.mean()
+    return math.degrees(math.atan(a1)), float(np.mean(np.abs(a0 + a1 * xsh - ysh)))
+
+
+def test_simple_ramp_3d(oracle):
+    """examples/eilmer/3D/simple-ramp/sg (ramp-test.rb): 3D general-metric blocks with clustered k-lines,
+    Euler update, the default adaptive flux calculator.  The reference's test expects 862 +- 3 steps, a
+    57 +- 1 degree straight shock, and prints force = Vector3(2214.56, 3.93211e-14, -12559.4) N
+    (ramp-test.rb:33,55-56,64-74); the oracle reproduces the printed digits."""
+    cfg, gm, blocks = cases.ramp3d()
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    steps = sim.run()
+    assert abs(steps - 862) < 3
+    fx, fy, fz = ramp_force(sim, blocks)
+    assert abs(fx - 2214.56) < 0.01 and abs(fy) < 1.0e-9 and abs(fz + 12559.4) < 0.1
+    angle, dev = ramp_shock_angle(sim, blocks)
+    assert abs(angle - 57.0) < 1.0 and dev < 0.002
     sim.close()
 
 

@@ -9,7 +9,7 @@ it is additionally required to be bit-identical.
 import numpy as np
 import pytest
 
-from gdtk_b200 import cases
+from gdtk_b200 import Simulation, cases
 from util import run_case, max_rel_diff, identical
 
 pytestmark = pytest.mark.gpu
@@ -44,6 +44,25 @@ def _compare(factory, oracle, product, nsteps, expect_bitwise=True, **kw):
 def test_sod_ausmdv(oracle, product, dims):
     """Shock tube, uniform Cartesian blocks (fast path), two blocks with a full-face copy."""
     ss, sf = _compare(cases.sod, oracle, product, 60, dims=dims, ncells=100, nblocks=2)
+
+
+def test_simple_ramp_3d_first_steps(oracle, product):
+    """examples/eilmer/3D/simple-ramp/sg: clustered general-metric 3D blocks, Euler update, default adaptive flux."""
+    _compare(cases.ramp3d, oracle, product, 150)
+
+
+def test_simple_ramp_3d_to_the_end(product):
+    """The whole job on the GPU (throughput build) against the reference's own expectations
+    (ramp-test.rb:33,64-74): 862 +- 3 steps, force = Vector3(2214.56, ~0, -12559.4) N on the ramp."""
+    from test_oracle_kats import ramp_force
+    cfg, gm, blocks = cases.ramp3d()
+    cfg.strict_fp = False
+    sim = Simulation(cfg, gm, blocks, lib=product)
+    steps = sim.run()
+    assert abs(steps - 862) < 3
+    fx, fy, fz = ramp_force(sim, blocks)
+    assert abs(fx - 2214.56) < 0.01 and abs(fy) < 1.0e-9 and abs(fz + 12559.4) < 0.1
+    sim.close()
 
 
 @pytest.mark.parametrize("flux", FLUXES)
