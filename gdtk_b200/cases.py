@@ -28,7 +28,7 @@ def ideal_air():
     return IdealGas(mMass=0.02896, gamma=1.4, name="air")
 
 
-def cone20(flux_calculator="ausmdv", nx0=10, nx1=30, ny=40, **cfg_kw):
+def cone20(flux_calculator="ausmdv", nx0=10, nx1=30, ny=40, fbarray=False, **cfg_kw):
     """Mach 1.5 flow over a 20-degree cone, 2D axisymmetric, 2 blocks (C1).
 
     Geometry, states and settings of cone20.lua:26-66.  Differences, both forced by
@@ -46,6 +46,19 @@ def cone20(flux_calculator="ausmdv", nx0=10, nx1=30, ny=40, **cfg_kw):
     d, e, f = (1.0, 1.0), (0.2, 1.0), (0.0, 1.0)
     grid0 = quad_patch_grid(a, b, e, f, nx0, ny)
     grid1 = quad_patch_grid(b, c, d, e, nx1, ny)
+    if fbarray:
+        # sg-mpi/cone20.lua:48-51: FBArray{grid0, njb=2} and FBArray{grid1, nib=3, njb=2}, eight blocks
+        blocks = []
+        for grid, nib, njb, state in ((grid0, 1, 2, inflow), (grid1, 3, 2, initial)):
+            for ib, jb, kb, sub in split_grid(grid, nib, njb):
+                blk = FluidBlock(sub, state, id=len(blocks))
+                if grid is grid0 and ib == 0:
+                    blk.bcList["west"] = InFlowBC_Supersonic(inflow)
+                if grid is grid1 and ib == nib - 1:
+                    blk.bcList["east"] = OutFlowBC_Simple()
+                blocks.append(blk)
+        identify_block_connections(blocks, 2)
+        return cfg, gm, blocks
     blk0 = FluidBlock(grid0, inflow, id=0)
     blk1 = FluidBlock(grid1, initial, id=1)
     identify_block_connections([blk0, blk1], 2)
