@@ -1008,6 +1008,29 @@ int eb200_download_flow(int sim, int blk_id, double* const* prims, int nprims)
     return 0;
 }
 
+int eb200_probe_cells(int sim, int n, const int* blk_ids, const int* ijk, double* out, int nprims)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (!s->committed) { set_err("probe_cells needs a committed simulation"); return -1; }
+    if (nprims != s->P.nprim) { set_err("expected %d primitive variables", s->P.nprim); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    const double* prim = s->A.prim[s->cur];
+    for (int m = 0; m < n; ++m) {
+        Block* b = get_blk(s, blk_ids[m]); if (!b) return -1;
+        const int i = ijk[3 * m], j = ijk[3 * m + 1], k = ijk[3 * m + 2];
+        if (!b->local || i < 0 || i >= b->nic || j < 0 || j >= b->njc || k < 0 || k >= b->nkc) {
+            set_err("probe %d: cell (%d,%d,%d) is not an interior cell of a local block %d", m, i, j, k, blk_ids[m]);
+            return -1;
+        }
+        const long long c = b->cell0 + b->cidx(i, j, k);
+        // one strided copy: nprims rows of one double, row pitch = one field of the arena
+        CUDA_OK(cudaMemcpy2DAsync(out + (size_t)m * nprims, sizeof(double), prim + c, (size_t)s->P.total * sizeof(double),
+                                  sizeof(double), (size_t)nprims, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
 int eb200_download_conserved(int sim, int blk_id, double* const* U, int ncq)
 {
     Sim* s = get_sim(sim); if (!s) return -1;

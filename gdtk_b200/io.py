@@ -196,6 +196,25 @@ class FlowFromFile:
         return out
 
 
+def write_history_file(path, sim, key):
+    """hist/<job>-blk-B-cell-C.dat.0 of history.d:28-95: a header naming the columns, then one line per sample:
+    time and the cell's flow-file line.  `key` is a history point of sim (Simulation.set_history_point)."""
+    ib, i, j, k = key
+    blk = next(b for b in sim.local_blocks if b.id == ib)
+    g = blk.geom
+    c = (g.kg + k, NG + j, NG + i)
+    names = flow_variable_list(sim.gmodel)
+    nsp = len(getattr(sim.gmodel, "species_names", None) or ["air"])
+    with open(path, "w", encoding="ascii") as f:
+        f.write("# 1:t " + "".join(f"{n + 2}:{v} " for n, v in enumerate(names)) + "\n")
+        for row in sim.history[key]:
+            t, P = row[0], row[1:]
+            vals = [g.pos[0][c], g.pos[1][c], g.pos[2][c], g.vol[c], P[0], P[5], P[6], P[7], P[2], P[4], 0.0, 0.0, 0.0, 0.0, 0.0]
+            vals += (list(P[8:8 + nsp]) + [-1.0]) if nsp > 1 else [1.0]
+            vals += [P[1], P[3]]
+            f.write(f"{t:.18e} " + " ".join(f"{v:.18e}" for v in vals) + "\n")
+
+
 def job_file(job_dir, job, kind, blk_id, tindx):
     """<job_dir>/<kind>/tNNNN/<job>.<kind>.bBBBB.tNNNN.gz (kind = 'grid' or 'flow'), simcore_io.d naming."""
     return os.path.join(job_dir, kind, f"t{tindx:04d}", f"{job}.{kind}.b{blk_id:04d}.t{tindx:04d}.gz")

@@ -54,6 +54,7 @@ class Config:
         self.dt_init = 1.0e-3                              # :1281
         self.dt_max = 1.0e-3                               # :1282
         self.max_time = 1.0e-3
+        self.dt_history = 1.0e-3                           # history cells are sampled at this interval of simulated time
         self.max_step = 100
         self.max_attempts_for_step = 3                     # :947
         self.max_invalid_cells = 0                         # :1014
@@ -317,6 +318,11 @@ class Simulation:
         self.dt_allow = None
         self.cfl_max = 0.0
         self.dt_history = []
+        # setHistoryPoint{ib=, i=, j=, k=}: (time, FlowState variables) of every history cell, taken each
+        # config.dt_history of simulated time like write_history_cells_to_files (simcore.d:942,1235-1243)
+        self.history_points = []
+        self.history = {}
+        self.t_history = None
         self._setup(exchange)
 
     # -- set-up ------------------------------------------------------------
@@ -525,14 +531,41 @@ class Simulation:
         self.step += 1
         self.dt_history.append(self.dt_global)
 
+    def set_history_point(self, ib, i, j, k=0):
+        """setHistoryPoint{ib=, i=, j=, k=} for a block owned by this process."""
+        key = (int(ib), int(i), int(j), int(k))
+        self.history_points.append(key)
+        self.history[key] = []
+        return key
+
+    def probe_cells(self, points):
+        """FlowState variables (EB200_PRIM order) of interior cells [(ib, i, j, k), ...]."""
+        n = len(points)
+        ids = (C.c_int * n)(*[p[0] for p in points])
+        ijk = (C.c_int * (3 * n))(*[v for p in points for v in p[1:4]])
+        out = np.zeros((n, self.nprim))
+        self.lib.check(self.lib.probe_cells(self.handle, n, ids, ijk, out.ctypes.data_as(_abi.DP), self.nprim), "probe_cells")
+        return out
+
+    def write_history(self):
+        if self.history_points:
+            for key, row in zip(self.history_points, self.probe_cells(self.history_points)):
+                self.history[key].append((self.time,) + tuple(float(v) for v in row))
+
     def run(self, max_step=None, max_time=None):
-        """integrate_in_time (simcore.d:1014-1331) without IO."""
+        """integrate_in_time (simcore.d:1014-1331) without file IO; history cells are sampled every
+        config.dt_history (simcore.d:942,1235-1243)."""
         max_step = self.config.max_step if max_step is None else max_step
         max_time = self.config.max_time if max_time is None else max_time
+        if self.t_history is None:
+            self.t_history = self.time + self.config.dt_history
         while self.time < max_time and self.step < max_step:
             if not self.config.fixed_time_step:
                 self.determine_time_step_size()
             self.gasdynamic_step()
+            if self.history_points and self.time >= self.t_history:
+                self.write_history()
+                self.t_history += self.config.dt_history
         return self.step
 
     def run_fixed(self, nsteps, dt):

@@ -252,6 +252,12 @@ int eb200_download_flow(int sim, int blk_id, double* const* prims, int nprims);
  * mass, xMom, yMom, [zMom], totEnergy, [species x nsp]). */
 int eb200_download_conserved(int sim, int blk_id, double* const* U, int ncq);
 
+/* FlowStates of single cells of local blocks, e.g. the history points of a job
+ * (setHistoryPoint; history.d:80-95 writes one line per history cell).
+ * Probe m is interior cell (ijk[3m], ijk[3m+1], ijk[3m+2]) of block blk_ids[m];
+ * out[m * nprims + v] is its variable v in the EB200_PRIM_* order. */
+int eb200_probe_cells(int sim, int n, const int* blk_ids, const int* ijk, double* out, int nprims);
+
 /* ---- the hot path ------------------------------------------------------ */
 
 /* Per-block time-step limits, min-reduced over all local blocks

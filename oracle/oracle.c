@@ -1711,6 +1711,23 @@ int orc_download_flow(int sim, int blk_id, double* const* prims, int nprims)
     return 0;
 }
 
+int orc_probe_cells(int sim, int n, const int* blk_ids, const int* ijk, double* out, int nprims)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (nprims != s->nprim) { set_err("expected %d primitive variables", s->nprim); return -1; }
+    for (int m = 0; m < n; ++m) {
+        Blk* b = get_blk(s, blk_ids[m]); if (!b) return -1;
+        const int i = ijk[3 * m], j = ijk[3 * m + 1], k = ijk[3 * m + 2];
+        if (!b->local || i < 0 || i >= b->nic || j < 0 || j >= b->njc || k < 0 || k >= b->nkc) {
+            set_err("probe %d: cell (%d,%d,%d) is not an interior cell of block %d", m, i, j, k, blk_ids[m]);
+            return -1;
+        }
+        const long c = cidx(b, i + NG, j + NG, k + b->kg);
+        for (int v = 0; v < nprims; ++v) out[(long)m * nprims + v] = PR(s, b, v)[c];
+    }
+    return 0;
+}
+
 int orc_download_conserved(int sim, int blk_id, double* const* U, int ncq)
 {
     Sim* s = get_sim(sim); if (!s) return -1;

@@ -92,3 +92,24 @@ def test_cone20_from_the_reference_files(oracle):
     steps = sim.run()
     assert abs(steps - 833) < 3
     sim.close()
+
+
+def test_history_points(tmp_path, oracle):
+    """setHistoryPoint of cone20.lua (ib=1, i=20, j=0 and ib=0, i=5, j=5): samples every dt_history, probe equals the
+    downloaded block, and the history file has one line per sample in the flow-file layout."""
+    cfg, gm, blocks = cases.cone20(dt_history=1.0e-4)
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    k1, k0 = sim.set_history_point(1, 20, 0), sim.set_history_point(0, 5, 5)
+    sim.run(max_step=200, max_time=1.0)
+    n = len(sim.history[k1])
+    assert n == int(sim.time / 1.0e-4) and n == len(sim.history[k0]) and n >= 5
+    times = [r[0] for r in sim.history[k1]]
+    assert all(t2 > t1 for t1, t2 in zip(times, times[1:])) and times[0] >= 1.0e-4
+    P = sim.download_flow(1)
+    probe = sim.probe_cells([k1])[0]
+    assert all(probe[v] == sim.interior(1, P[v])[0, 0, 20] for v in range(8))
+    io.write_history_file(tmp_path / "cone20-blk-1-cell-20.dat.0", sim, k1)
+    lines = open(tmp_path / "cone20-blk-1-cell-20.dat.0").read().splitlines()
+    assert lines[0].startswith("# 1:t 2:pos.x 3:pos.y") and len(lines) == n + 1
+    assert len(lines[1].split()) == 1 + len(io.flow_variable_list(gm))
+    sim.close()

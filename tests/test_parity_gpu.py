@@ -46,6 +46,27 @@ def test_sod_ausmdv(oracle, product, dims):
     ss, sf = _compare(cases.sod, oracle, product, 60, dims=dims, ncells=100, nblocks=2)
 
 
+def test_probe_histories(oracle, product):
+    """History cells (setHistoryPoint) sampled every dt_history: the FMA-free build gives the oracle's numbers,
+    the throughput build is within 1e-9 (north_star: 'dt and probe histories within 1e-9')."""
+    runs = {}
+    for name, lib, strict in (("oracle", oracle, True), ("strict", product, True), ("fast", product, False)):
+        cfg, gm, blocks = cases.cone20(dt_history=5.0e-5)
+        cfg.strict_fp = strict
+        sim = Simulation(cfg, gm, blocks, lib=lib)
+        keys = [sim.set_history_point(1, 20, 0), sim.set_history_point(1, 1, 1), sim.set_history_point(0, 5, 30)]
+        sim.run(max_step=300, max_time=1.0)
+        runs[name] = np.array([[row for row in sim.history[k]] for k in keys])     # (point, sample, 1 + nprim)
+        sim.close()
+    assert runs["oracle"].shape[1] >= 10
+    assert np.array_equal(runs["strict"], runs["oracle"])
+    assert runs["fast"].shape == runs["oracle"].shape
+    scale = np.max(np.abs(runs["oracle"]), axis=(0, 1))
+    scale[6] = scale[7] = scale[8] = max(scale[6], scale[7], scale[8])            # velocity components share a scale
+    scale[scale == 0.0] = 1.0
+    assert np.max(np.abs(runs["fast"] - runs["oracle"]) / scale) < 1.0e-9
+
+
 def test_simple_ramp_3d_first_steps(oracle, product):
     """examples/eilmer/3D/simple-ramp/sg: clustered general-metric 3D blocks, Euler update, default adaptive flux."""
     _compare(cases.ramp3d, oracle, product, 150)
