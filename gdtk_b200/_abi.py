@@ -23,6 +23,7 @@ FACE_NAMES = ["west", "east", "south", "north", "bottom", "top"]
 FLUX_CALCULATORS = {
     "ausmdv": 0, "hanel": 1, "ldfss0": 2, "ldfss2": 3, "ausm_plus_up": 4, "roe": 5,
     "adaptive_hanel_ausmdv": 6, "adaptive_hanel_ausm_plus_up": 7, "adaptive_ldfss0_ldfss2": 8,
+    "efm": 9, "adaptive_efm_ausmdv": 10, "adaptive": 10,
 }
 # config.gasdynamic_update_scheme names (reference src/eilmer/globalconfig.d:126-200)
 UPDATE_SCHEMES = {

@@ -93,9 +93,12 @@ __device__ __forceinline__ void to_local(const Frame& f, double& x, double& y, d
         double b = x * f.t1x + y * f.t1y + z * f.t1z;
         double c = x * f.t2x + y * f.t2y + z * f.t2z;
         x = a; y = b; z = c;
-    } else {                       // z = 0, n.z = t1.z = 0, t2 = (0,0,1): the dropped terms are exact zeros
-        double a = x * f.nx + y * f.ny;
-        double b = x * f.t1x + y * f.t1y;
+    } else {
+        // z = 0, n.z = t1.z = 0, t2 = (0,0,1): the dropped terms are exact +0.0.  They are still added because
+        // (-0) + (+0) = +0: the sign of a zero velocity component must be the reference's -- efm's
+        // erf approximation jumps by 1e-9 between sn = -0 and sn = +0 (copysign, fluxcalc.d:1311)
+        double a = x * f.nx + y * f.ny + 0.0;
+        double b = x * f.t1x + y * f.t1y + 0.0;
         x = a; y = b;
     }
 }
@@ -845,6 +848,118 @@ __device__ __forceinline__ void flux_roe(const Prim<NSP>& L, const Prim<NSP>& R,
                              - (a0 * (w0 * (kehat + tkehat) + rhat * (vhat * dv + what * dw + dtke - theta)))
                              - (a1 * w1 * (Hhat + uhat * ahat))
                              - (a2 * w2 * (Hhat - uhat * ahat)));
+}
+
+
+// fluxcalc.d:1280-1312 exxef: exp(-x^2) and erf(x) by a polynomial approximation
+__device__ __forceinline__ void exxef(double sn, double& exx, double& ef)
+{
+    const double Pc = 0.327591100, A1 = 0.254829592, A2 = -0.284496736, A3 = 1.421413741, A4 = -1.453152027, A5 = 1.061405429;
+    double ef1;
+    if (fabs(sn) > 5.0) { exx = 0.138879e-10; ef1 = 1.0; }
+    else {
+        const double snsq = sn * sn;
+        exx = exp(-snsq);
+        const double y = eb_div(1.0, 1.0 + Pc * fabs(sn));
+        ef1 = 1.0 - y * (A1 + y * (A2 + y * (A3 + y * (A4 + A5 * y)))) * exx;
+    }
+    ef = copysign(ef1, sn);
+}
+
+// gmodel.Cv(Q): ideal_gas.d (a constant), therm_perf_gas.d:417-424
+template <int GASM, int NSP>
+__device__ __forceinline__ double gas_Cv(const EbGas* __restrict__ g, const Prim<NSP>& Q)
+{
+    if (GASM == EB200_GAS_IDEAL) return g->Cv;
+    double cv = 0.0;
+#pragma unroll
+    for (int i = 0; i < NSP; ++i) { double c; cea_Cp(g->curves[i], Q.T, c); cv += Q.massf[i] * (c - g->Rsp[i]); }
+    return cv;
+}
+
+// fluxcalc.d:1131-1277 efmflx, the equilibrium flux method of Macrossan & Pullin (factor = 1).
+// Reads T of both states.  Note rtL = Rgas*tL but rtR = presR/rhoR, as in the reference.
+template <int DIM, int NSP, int GASM>
+__device__ __forceinline__ void flux_efm(const EbGas* __restrict__ g, const Prim<NSP>& L, const Prim<NSP>& R, double* F)
+{
+    typedef Layout<DIM, NSP> Lay;
+    const double dtwspi = 0.282094792;
+    const double rhoL = L.rho, presL = L.p, eL = L.u, tL = L.T, vnL = L.vx, vpL = L.vy, vqL = (DIM == 3) ? L.vz : 0.0;
+    const double rhoR = R.rho, presR = R.p, eR = R.u, tR = R.T, vnR = R.vx, vpR = R.vy, vqR = (DIM == 3) ? R.vz : 0.0;
+    double hL = eL + eb_div(presL, rhoL); hL += 0.0;
+    double hR = eR + eb_div(presR, rhoR); hR += 0.0;
+    const double cvL = gas_Cv<GASM, NSP>(g, L), RgasL = eb_div(presL, (rhoL * tL));
+    const double cvR = gas_Cv<GASM, NSP>(g, R), RgasR = eb_div(presR, (rhoR * tR));
+    const double rLsqrt = eb_sqrt(rhoL), rRsqrt = eb_sqrt(rhoR);
+    const double alpha = eb_div(rLsqrt, (rLsqrt + rRsqrt));
+    const double cv = alpha * cvL + (1.0 - alpha) * cvR;
+    const double Rgas = alpha * RgasL + (1.0 - alpha) * RgasR;
+    const double cp = cv + Rgas;
+    const double gam = eb_div(cp, cv);
+    const double con = eb_div(0.5 * (gam + 1.0), (gam - 1.0));
+    double exL, efL, exR, efR;
+    const double rtL = Rgas * tL;
+    const double cmpL = eb_sqrt(2.0 * rtL);
+    const double hvsqL = 0.5 * (vnL * vnL + vpL * vpL + vqL * vqL);
+    const double snL = eb_div(vnL, (1.0 * cmpL));
+    exxef(snL, exL, efL);
+    const double wL = 0.5 * (1.0 + efL);
+    const double dL = exL * dtwspi;
+    const double rtR = eb_div(presR, rhoR);
+    const double cmpR = eb_sqrt(2.0 * rtR);
+    const double hvsqR = 0.5 * (vnR * vnR + vpR * vpR + vqR * vqR);
+    const double snR = eb_div(vnR, (1.0 * cmpR));
+    exxef(snR, exR, efR);
+    const double wR = 0.5 * (1.0 - efR);
+    const double dR = -exR * dtwspi;
+    const double fmsL = (wL * rhoL * vnL) + (dL * cmpL * rhoL);
+    const double fmsR = (wR * rhoR * vnR) + (dR * cmpR * rhoR);
+    const double mass_flux = 1.0 * (fmsL + fmsR);
+    F[Lay::iMass] = mass_flux;
+    F[Lay::iXMom] = 1.0 * (fmsL * vnL + fmsR * vnR + wL * presL + wR * presR);
+    F[Lay::iYMom] = 1.0 * (fmsL * vpL + fmsR * vpR);
+    if (DIM == 3) F[Lay::iZMom] = 1.0 * (fmsL * vqL + fmsR * vqR);
+    F[Lay::iEnergy] = 1.0 * ((wL * rhoL * vnL) * (hvsqL + hL) + (wR * rhoR * vnR) * (hvsqR + hR) +
+                             (dL * cmpL * rhoL) * (hvsqL + con * rtL) + (dR * cmpR * rhoR) * (hvsqR + con * rtR));
+    if (NSP > 1) {
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) F[Lay::iSpecies + i] = mass_flux * ((mass_flux > 0.0) ? L.massf[i] : R.massf[i]);
+    }
+}
+
+// One place that knows which basic calculators an adaptive one blends (fluxcalc.d:1315-1412): `shock` where the
+// detector marks the face (IFace.fs.S = 1; alpha is 0 or 1 on this path), `smooth` elsewhere.
+template <int FLUX>
+struct FluxPair {
+    static constexpr bool adaptive = (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV || FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP ||
+                                      FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2 || FLUX == EB200_FLUX_ADAPTIVE_EFM_AUSMDV);
+    static constexpr int shock = (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV || FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) ? EB200_FLUX_HANEL
+                               : (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) ? EB200_FLUX_LDFSS0
+                               : (FLUX == EB200_FLUX_ADAPTIVE_EFM_AUSMDV) ? EB200_FLUX_EFM : FLUX;
+    static constexpr int smooth = (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV || FLUX == EB200_FLUX_ADAPTIVE_EFM_AUSMDV) ? EB200_FLUX_AUSMDV
+                                : (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) ? EB200_FLUX_AUSM_PLUS_UP
+                                : (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) ? EB200_FLUX_LDFSS2 : FLUX;
+};
+
+template <int DIM, int NSP, int GASM, int BASE>
+__device__ __forceinline__ void basic_flux(const EbParams& P, const EbGas* __restrict__ gas, const Prim<NSP>& L, const Prim<NSP>& R, double* F)
+{
+    if (BASE == EB200_FLUX_AUSMDV) flux_ausmdv<DIM, NSP>(L, R, P.entropy_fix != 0, F);
+    else if (BASE == EB200_FLUX_HANEL) flux_hanel<DIM, NSP>(L, R, F);
+    else if (BASE == EB200_FLUX_LDFSS0) flux_ldfss<DIM, NSP, 0>(L, R, F);
+    else if (BASE == EB200_FLUX_LDFSS2) flux_ldfss<DIM, NSP, 2>(L, R, F);
+    else if (BASE == EB200_FLUX_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, NSP>(L, R, P.M_inf, F);
+    else if (BASE == EB200_FLUX_ROE) flux_roe<DIM, NSP>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
+    else flux_efm<DIM, NSP, GASM>(gas, L, R, F);
+}
+
+// The flux calculator FLUX for states in the face frame, in the reference's order of operations
+template <int DIM, int NSP, int GASM, int FLUX>
+__device__ __forceinline__ void flux_in_face_frame(const EbParams& P, const EbGas* __restrict__ gas, const Prim<NSP>& L,
+                                                   const Prim<NSP>& R, double alpha, double* F)
+{
+    if (FluxPair<FLUX>::adaptive && alpha > 0.0) basic_flux<DIM, NSP, GASM, FluxPair<FLUX>::shock>(P, gas, L, R, F);
+    else basic_flux<DIM, NSP, GASM, FluxPair<FLUX>::smooth>(P, gas, L, R, F);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -561,10 +561,11 @@ int eb200_init(const eb200_config* cfg)
     if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT && cfg->dimensions != 3) {
         set_err("thermally perfect gas: kernels are built for 3D only"); return -1;
     }
-    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
+    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_ADAPTIVE_EFM_AUSMDV) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
     if (cfg->flux_calculator == EB200_FLUX_ROE && cfg->n_species > 1) { set_err("roe with multiple species is not on this path yet"); return -1; }
     if (!n_stages_for(cfg->update_scheme)) { set_err("unsupported update scheme %d", cfg->update_scheme); return -1; }
-    const bool adaptive = cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV;
+    const bool adaptive = (cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV && cfg->flux_calculator <= EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) ||
+                          cfg->flux_calculator == EB200_FLUX_ADAPTIVE_EFM_AUSMDV;
     if (adaptive && cfg->compression_tolerance > 0.0) { set_err("compression_tolerance should be negative!"); return -1; }
     if (adaptive && cfg->n_species > 1 && cfg->flux_calculator != EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) {
         set_err("thermally perfect gas: of the adaptive flux calculators only adaptive_hanel_ausmdv is built"); return -1;

@@ -1,12 +1,12 @@
 // flux_inst.cu -- instantiates the fused flux+update kernel for ONE flux calculator
-// (-DEB_FLUX=0..5, enum eb200_flux_calculator) in ONE arithmetic mode (-DEB_NS=...).
+// (-DEB_FLUX=0..10, enum eb200_flux_calculator) in ONE arithmetic mode (-DEB_NS=...).
 #ifndef EB_FLUX
 #error "EB_FLUX must be defined"
 #endif
 #ifdef EB_NO_TPG
 #define EB_FLUX_HAS_TPG 0
 #else
-#define EB_FLUX_HAS_TPG (EB_FLUX != 5 && EB_FLUX != 7 && EB_FLUX != 8)   /* roe with several species is not on this path;
+#define EB_FLUX_HAS_TPG (EB_FLUX != 5 && EB_FLUX != 7 && EB_FLUX != 8 && EB_FLUX != 10)   /* roe with several species is not on this path;
                                                                           of the adaptive ones only the default is built for TPG */
 #endif
 #include "flux_kernel.cuh"

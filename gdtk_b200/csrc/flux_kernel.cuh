@@ -168,24 +168,9 @@ __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __rest
         if (CART) { axis_to_local(D.fr[d], L.vx, L.vy, L.vz); axis_to_local(D.fr[d], R.vx, R.vy, R.vz); }
         else { to_local<DIM>(fr, L.vx, L.vy, L.vz); to_local<DIM>(fr, R.vx, R.vy, R.vz); }
     }
-    if (FLUX == EB200_FLUX_AUSMDV) flux_ausmdv<DIM, NSP>(L, R, P.entropy_fix != 0, F);
-    else if (FLUX == EB200_FLUX_HANEL) flux_hanel<DIM, NSP>(L, R, F);
-    else if (FLUX == EB200_FLUX_LDFSS0) flux_ldfss<DIM, NSP, 0>(L, R, F);
-    else if (FLUX == EB200_FLUX_LDFSS2) flux_ldfss<DIM, NSP, 2>(L, R, F);
-    else if (FLUX == EB200_FLUX_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, NSP>(L, R, P.M_inf, F);
-    else if (FLUX == EB200_FLUX_ROE) flux_roe<DIM, NSP>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
-    else {
-        // adaptive calculators (fluxcalc.d:1332-1372): IFace.fs.S is 0 or 1 on this path (PJ detector, no
-        // smoothing), so exactly one of the two schemes runs, with factor 1
-        const double alpha = A.Sf[d] ? A.Sf[d][c] : 0.0;
-        if (alpha > 0.0) {
-            if (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) flux_ldfss<DIM, NSP, 0>(L, R, F);
-            else flux_hanel<DIM, NSP>(L, R, F);
-        } else {
-            if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) flux_ausmdv<DIM, NSP>(L, R, P.entropy_fix != 0, F);
-            else if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, NSP>(L, R, P.M_inf, F);
-            else flux_ldfss<DIM, NSP, 2>(L, R, F);
-        }
+    {
+        const double alpha = (FluxPair<FLUX>::adaptive && A.Sf[d]) ? A.Sf[d][c] : 0.0;
+        flux_in_face_frame<DIM, NSP, GASM, FLUX>(P, gas, L, R, alpha, F);
     }
     // momentum flux back to the global frame (fluxcalc.d:169-175)
     double fx = F[Lay::iXMom], fy = F[Lay::iYMom], fz = (DIM == 3) ? F[Lay::iZMom] : 0.0;

@@ -316,15 +316,15 @@ __device__ __forceinline__ void face_core_uniform(const EbParams& P, const EbGas
             R.p = ldg(prim_fallback + 2 * total + cR0);
         }
     }
-    if (FLUX == EB200_FLUX_ROE) { L.massf[0] = 1.0; R.massf[0] = 1.0; flux_roe<DIM, 1>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F); }
-    else if (FLUX < EB200_FLUX_ROE) flux_components<DIM, FLUX>(L, R, 0, P.entropy_fix != 0, P.M_inf, F);
-    else if (alpha > 0.0) {
-        if (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) flux_components<DIM, EB200_FLUX_LDFSS0>(L, R, 0, false, P.M_inf, F);
-        else flux_components<DIM, EB200_FLUX_HANEL>(L, R, 0, false, P.M_inf, F);
+    constexpr int SHOCK = FluxPair<FLUX>::shock, SMOOTH = FluxPair<FLUX>::smooth;
+    L.massf[0] = 1.0; R.massf[0] = 1.0;
+    if (SHOCK == EB200_FLUX_EFM || SMOOTH == EB200_FLUX_EFM) { L.T = L.u * gas->Cvinv; R.T = R.u * gas->Cvinv; }   // efm reads T
+    if (FluxPair<FLUX>::adaptive && alpha > 0.0) {
+        if constexpr (SHOCK < EB200_FLUX_ROE) flux_components<DIM, SHOCK>(L, R, 0, false, P.M_inf, F);
+        else basic_flux<DIM, 1, EB200_GAS_IDEAL, SHOCK>(P, gas, L, R, F);
     } else {
-        if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) flux_components<DIM, EB200_FLUX_AUSMDV>(L, R, 0, P.entropy_fix != 0, P.M_inf, F);
-        else if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) flux_components<DIM, EB200_FLUX_AUSM_PLUS_UP>(L, R, 0, false, P.M_inf, F);
-        else flux_components<DIM, EB200_FLUX_LDFSS2>(L, R, 0, false, P.M_inf, F);
+        if constexpr (SMOOTH < EB200_FLUX_ROE) flux_components<DIM, SMOOTH>(L, R, 0, P.entropy_fix != 0, P.M_inf, F);
+        else basic_flux<DIM, 1, EB200_GAS_IDEAL, SMOOTH>(P, gas, L, R, F);
     }
 }
 #endif
@@ -378,17 +378,11 @@ __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __rest
 #endif
     }
 #ifdef EB_FAST_MATH
-    if (!ROT && FLUX != EB200_FLUX_ROE) {
+    constexpr bool has_component_form = (FluxPair<FLUX>::shock < EB200_FLUX_ROE) && (FluxPair<FLUX>::smooth < EB200_FLUX_ROE);
+    if constexpr (!ROT && has_component_form) {
         // 2D i-faces have t1 = -y; the component form never looks at the sign of a tangential component
-        if (FLUX <= EB200_FLUX_ROE) flux_components<DIM, FLUX>(L, R, d, P.entropy_fix != 0, P.M_inf, F);
-        else if (alpha > 0.0) {
-            if (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) flux_components<DIM, EB200_FLUX_LDFSS0>(L, R, d, false, P.M_inf, F);
-            else flux_components<DIM, EB200_FLUX_HANEL>(L, R, d, false, P.M_inf, F);
-        } else {
-            if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) flux_components<DIM, EB200_FLUX_AUSMDV>(L, R, d, P.entropy_fix != 0, P.M_inf, F);
-            else if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) flux_components<DIM, EB200_FLUX_AUSM_PLUS_UP>(L, R, d, false, P.M_inf, F);
-            else flux_components<DIM, EB200_FLUX_LDFSS2>(L, R, d, false, P.M_inf, F);
-        }
+        if (FluxPair<FLUX>::adaptive && alpha > 0.0) flux_components<DIM, FluxPair<FLUX>::shock>(L, R, d, false, P.M_inf, F);
+        else flux_components<DIM, FluxPair<FLUX>::smooth>(L, R, d, P.entropy_fix != 0, P.M_inf, F);
         return;
     }
 #endif
@@ -402,20 +396,7 @@ __device__ __forceinline__ void face_core(const EbParams& P, const EbGas* __rest
         L.vx = (d == 0) ? lx : ly; L.vy = (d == 0) ? -ly : lx;
         R.vx = (d == 0) ? rx : ry; R.vy = (d == 0) ? -ry : rx;
     }
-    if (FLUX == EB200_FLUX_AUSMDV) flux_ausmdv<DIM, 1>(L, R, P.entropy_fix != 0, F);
-    else if (FLUX == EB200_FLUX_HANEL) flux_hanel<DIM, 1>(L, R, F);
-    else if (FLUX == EB200_FLUX_LDFSS0) flux_ldfss<DIM, 1, 0>(L, R, F);
-    else if (FLUX == EB200_FLUX_LDFSS2) flux_ldfss<DIM, 1, 2>(L, R, F);
-    else if (FLUX == EB200_FLUX_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, 1>(L, R, P.M_inf, F);
-    else if (FLUX == EB200_FLUX_ROE) flux_roe<DIM, 1>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
-    else if (alpha > 0.0) {   // adaptive calculators, fluxcalc.d:1332-1372 (alpha is 0 or 1 on this path)
-        if (FLUX == EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) flux_ldfss<DIM, 1, 0>(L, R, F);
-        else flux_hanel<DIM, 1>(L, R, F);
-    } else {
-        if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSMDV) flux_ausmdv<DIM, 1>(L, R, P.entropy_fix != 0, F);
-        else if (FLUX == EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, 1>(L, R, P.M_inf, F);
-        else flux_ldfss<DIM, 1, 2>(L, R, F);
-    }
+    flux_in_face_frame<DIM, 1, EB200_GAS_IDEAL, FLUX>(P, gas, L, R, alpha, F);
     if (!ROT) {              // momentum flux back to (x, y, z) order
         if (DIM == 3) {
             const double f0 = F[Lay::iXMom], f1 = F[Lay::iYMom], f2 = F[Lay::iZMom];
@@ -704,7 +685,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
             }
             const EbWeights& w = CART ? D.w[d] : wl;
             double Fl[NCQ];
-            const double alpha = (FLUX > EB200_FLUX_ROE) ? A.Sf[d][cf] : 0.0;
+            const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[d][cf] : 0.0;
 #ifdef EB_FAST_MATH
             if (UNIFORM) {
                 face_core_uniform<DIM, FLUX, CLIP>(P, gas, D.uq[d], s, alpha, S.prim_in, cf - st, cf, Fl);

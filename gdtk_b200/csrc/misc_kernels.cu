@@ -12,12 +12,12 @@ namespace EB_NS {
                                  int nblocks, long long ncta, const EbArena& A, const EbStageArgs& S,          \
                                  int tile_y, int which, cudaStream_t st);
 EB_DECL_FLUX(0) EB_DECL_FLUX(1) EB_DECL_FLUX(2) EB_DECL_FLUX(3) EB_DECL_FLUX(4) EB_DECL_FLUX(5)
-EB_DECL_FLUX(6) EB_DECL_FLUX(7) EB_DECL_FLUX(8)
+EB_DECL_FLUX(6) EB_DECL_FLUX(7) EB_DECL_FLUX(8) EB_DECL_FLUX(9) EB_DECL_FLUX(10)
 #define EB_DECL_DBG(k)                                                                                         \
     void launch_face_debug_k##k(const EbParams& P, int gas_model, const EbGas* gas, const EbArena& A,           \
                                 const double* prim, int nfaces, double* Fout, int* ok_out, cudaStream_t st);
 EB_DECL_DBG(0) EB_DECL_DBG(1) EB_DECL_DBG(2) EB_DECL_DBG(3) EB_DECL_DBG(4) EB_DECL_DBG(5)
-EB_DECL_DBG(6) EB_DECL_DBG(7) EB_DECL_DBG(8)
+EB_DECL_DBG(6) EB_DECL_DBG(7) EB_DECL_DBG(8) EB_DECL_DBG(9) EB_DECL_DBG(10)
 
 void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* gas, const EbArena& A, const double* prim,
                        int nfaces, double* Fout, int* ok_out, cudaStream_t st)
@@ -32,6 +32,8 @@ void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* ga
     case 6: launch_face_debug_k6(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 7: launch_face_debug_k7(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 8: launch_face_debug_k8(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 9: launch_face_debug_k9(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 10: launch_face_debug_k10(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     }
 }
 
@@ -51,6 +53,8 @@ void launch_flux_update(int flux_calc, int gm, const EbParams& P, const EbGas* g
     case 6: launch_flux_update_k6(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 7: launch_flux_update_k7(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 8: launch_flux_update_k8(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 9: launch_flux_update_k9(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 10: launch_flux_update_k10(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     }
 }
 

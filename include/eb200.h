@@ -66,7 +66,9 @@ enum eb200_flux_calculator {
      * PJ_ShockDetector shockdetectors.d:22-93, fluidblock.d:479-605) */
     EB200_FLUX_ADAPTIVE_HANEL_AUSMDV = 6,        /* the reference's default (globalconfig.d:1031) */
     EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP = 7,
-    EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2 = 8
+    EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2 = 8,
+    EB200_FLUX_EFM = 9,                          /* fluxcalc.d:1131-1312 (equilibrium flux method) */
+    EB200_FLUX_ADAPTIVE_EFM_AUSMDV = 10          /* config.flux_calculator = "adaptive" (globalconfig.d:333) */
 };
 
 /* config.gasdynamic_update_scheme (src/eilmer/globalconfig.d:126-200);

@@ -908,6 +908,83 @@ static void roe(const Sim* s, const FS* Lft, const FS* Rght, double* F)
                                     - (fabs(lambda[2]) * ((dp - rhat * ahat * du) / (2.0 * ahat2)) * (Hhat - uhat * ahat)));
 }
 
+/* fluxcalc.d:1280-1312 exxef: exp(-x^2) and erf(x) by a polynomial approximation */
+static void exxef(double sn, double* exx, double* ef)
+{
+    const double P = 0.327591100, A1 = 0.254829592, A2 = -0.284496736, A3 = 1.421413741, A4 = -1.453152027, A5 = 1.061405429;
+    const double LIMIT = 5.0, EXLIM = 0.138879e-10, EFLIM = 1.0;
+    double ef1;
+    if (fabs(sn) > LIMIT) { *exx = EXLIM; ef1 = EFLIM; }
+    else {
+        double snsq = sn * sn;
+        *exx = exp(-snsq);
+        double y = 1.0 / (1.0 + P * fabs(sn));
+        ef1 = 1.0 - y * (A1 + y * (A2 + y * (A3 + y * (A4 + A5 * y)))) * *exx;
+    }
+    *ef = copysign(ef1, sn);
+}
+
+/* gmodel.Cv(Q): ideal_gas.d (constant), therm_perf_gas.d:417-424 */
+static double gas_Cv(const Sim* s, const Gas* Q)
+{
+    if (s->cfg.gas_model == EB200_GAS_IDEAL) return s->Cv;
+    double cv[MAXSP];
+    for (int i = 0; i < s->nsp; ++i) { double c; cea_Cp(&s->curves[i], Q->T, &c); cv[i] = c - s->Rsp[i]; }
+    return mass_average(s, Q, cv);
+}
+
+/* fluxcalc.d:1131-1277 efmflx (Macrossan & Pullin), factor = 1; note rtL = Rgas*tL but rtR = presR/rhoR */
+static void efmflx(const Sim* s, const FS* Lft, const FS* Rght, double* F)
+{
+    const double factor = 1.0;
+    const double PHI = 1.0, dtwspi = 0.282094792;
+    double rhoL = Lft->gas.rho, presL = Lft->gas.p, eL = Lft->gas.u;
+    double hL = eL + presL / rhoL;
+    hL += 0.0;
+    double tL = Lft->gas.T, vnL = Lft->vx, vpL = Lft->vy, vqL = Lft->vz;
+    double rhoR = Rght->gas.rho, presR = Rght->gas.p, eR = Rght->gas.u;
+    double hR = eR + presR / rhoR;
+    hR += 0.0;
+    double tR = Rght->gas.T, vnR = Rght->vx, vpR = Rght->vy, vqR = Rght->vz;
+    double cvL = gas_Cv(s, &Lft->gas), RgasL = presL / (rhoL * tL);
+    double cvR = gas_Cv(s, &Rght->gas), RgasR = presR / (rhoR * tR);
+    double rLsqrt = sqrt(rhoL), rRsqrt = sqrt(rhoR);
+    double alpha = rLsqrt / (rLsqrt + rRsqrt);
+    double cv = alpha * cvL + (1.0 - alpha) * cvR;
+    double Rgas = alpha * RgasL + (1.0 - alpha) * RgasR;
+    double cp = cv + Rgas;
+    double gam = cp / cv;
+    double con = 0.5 * (gam + 1.0) / (gam - 1.0);
+    double exL, efL, exR, efR;
+    double rtL = Rgas * tL;
+    double cmpL = sqrt(2.0 * rtL);
+    double hvsqL = 0.5 * (vnL * vnL + vpL * vpL + vqL * vqL);
+    double snL = vnL / (PHI * cmpL);
+    exxef(snL, &exL, &efL);
+    double wL = 0.5 * (1.0 + efL);
+    double dL = exL * dtwspi;
+    double rtR = presR / rhoR;
+    double cmpR = sqrt(2.0 * rtR);
+    double hvsqR = 0.5 * (vnR * vnR + vpR * vpR + vqR * vqR);
+    double snR = vnR / (PHI * cmpR);
+    exxef(snR, &exR, &efR);
+    double wR = 0.5 * (1.0 - efR);
+    double dR = -exR * dtwspi;
+    double fmsL = (wL * rhoL * vnL) + (dL * cmpL * rhoL);
+    double fmsR = (wR * rhoR * vnR) + (dR * cmpR * rhoR);
+    double mass_flux = factor * (fmsL + fmsR);
+    F[s->iMass] += mass_flux;
+    F[s->iXMom] += factor * (fmsL * vnL + fmsR * vnR + wL * presL + wR * presR);
+    F[s->iYMom] += factor * (fmsL * vpL + fmsR * vpR);
+    if (s->threeD) F[s->iZMom] += factor * (fmsL * vqL + fmsR * vqR);
+    F[s->iEnergy] += factor * ((wL * rhoL * vnL) * (hvsqL + hL) + (wR * rhoR * vnR) * (hvsqR + hR) +
+                               (dL * cmpL * rhoL) * (hvsqL + con * rtL) + (dR * cmpR * rhoR) * (hvsqR + con * rtR));
+    if (s->nsp > 1) {
+        const FS* up = (mass_flux > 0.0) ? Lft : Rght;
+        for (int i = 0; i < s->nsp; ++i) F[s->iSpecies + i] += mass_flux * up->gas.massf[i];
+    }
+}
+
 /* fluxcalc.d:54-184 compute_interface_flux_interior (gvel = 0, omegaz = 0, no MHD).
  * Lft/Rght are tampered with, as in the reference.  F is in the global frame on return. */
 static void compute_interface_flux_interior(const Sim* s, FS* Lft, FS* Rght, const FaceGeo* g, double alpha, double* F)
@@ -938,6 +1015,11 @@ static void compute_interface_flux_interior(const Sim* s, FS* Lft, FS* Rght, con
     case EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2:
         if (alpha > 0.0) ldfss(s, Lft, Rght, F, 0);
         if (alpha < 1.0) ldfss(s, Lft, Rght, F, 2);
+        break;
+    case EB200_FLUX_EFM: efmflx(s, Lft, Rght, F); break;
+    case EB200_FLUX_ADAPTIVE_EFM_AUSMDV:               /* fluxcalc.d:1315-1331 */
+        if (alpha > 0.0) efmflx(s, Lft, Rght, F);
+        if (alpha < 1.0) ausmdv(s, Lft, Rght, F);
         break;
     }
     double v_sqr = gvx * gvx + gvy * gvy + gvz * gvz;
@@ -1551,8 +1633,9 @@ int orc_init(const eb200_config* cfg)
     s->ncq = s->iEnergy + 1;
     if (s->nsp > 1) { s->iSpecies = s->ncq; s->ncq += s->nsp; } else s->iSpecies = -1;
     s->nprim = EB200_NPRIM_BASE + (s->nsp > 1 ? 2 * s->nsp : 0);
-    s->shock_detect = (cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV);
-    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) { set_err("unknown flux calculator"); return -1; }
+    s->shock_detect = ((cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV && cfg->flux_calculator <= EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) ||
+                       cfg->flux_calculator == EB200_FLUX_ADAPTIVE_EFM_AUSMDV);
+    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_ADAPTIVE_EFM_AUSMDV) { set_err("unknown flux calculator"); return -1; }
     if (s->shock_detect && cfg->compression_tolerance > 0.0) { set_err("compression_tolerance should be negative!"); return -1; }
     s->n_stages = n_stages_for(cfg->update_scheme);
     if (!s->n_stages) { set_err("unsupported update scheme"); return -1; }

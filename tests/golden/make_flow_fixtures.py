@@ -25,6 +25,7 @@ CASES = {
     "ffs_hanel": ("ffs", dict(nx=60, ny=20, flux_calculator="hanel"), 20),
     "cone20_adaptive_default": ("cone20", dict(nx0=6, nx1=14, ny=16, flux_calculator="adaptive_hanel_ausmdv"), 60),
     "ramp3d_default_euler": ("ramp3d", dict(), 120),
+    "cone20_adaptive_efm": ("cone20", dict(nx0=6, nx1=14, ny=16, flux_calculator="adaptive"), 60),
     "box3d_ldfss2_rk3": ("box3d", dict(n=8, nb=1, flux_calculator="ldfss2", gasdynamic_update_scheme="tvd-rk3"), 5),
 }
 

@@ -59,8 +59,9 @@ def test_missing_library_fails_loudly(tmp_path):
 def test_config_rejects_options_outside_the_path():
     gm = cases.ideal_air()
     Config().to_struct(gm)              # the reference default (adaptive_hanel_ausmdv) is on the path
+    Config(flux_calculator="adaptive").to_struct(gm)    # = adaptive_efm_ausmdv
     with pytest.raises(ValueError):
-        Config(flux_calculator="adaptive_efm_ausmdv").to_struct(gm)
+        Config(flux_calculator="adaptive_hlle_ausmdv").to_struct(gm)
     with pytest.raises(ValueError):
         Config(shock_detector_smoothing=2).to_struct(gm)
     with pytest.raises(ValueError):

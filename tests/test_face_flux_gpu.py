@@ -16,7 +16,7 @@ from gdtk_b200 import Config, cases
 
 pytestmark = pytest.mark.gpu
 
-FLUXES = ["ausmdv", "hanel", "ldfss0", "ldfss2", "ausm_plus_up", "roe"]
+FLUXES = ["ausmdv", "hanel", "ldfss0", "ldfss2", "ausm_plus_up", "roe", "efm"]
 
 
 def random_faces(gm, dims, n, seed):
@@ -102,12 +102,14 @@ def test_face_flux_matches_oracle(oracle, product, dims, flux, clip):
     cfg.strict_fp = False
     Ff, okf = eval_faces(product, cfg, gm, cells, lens, geo, ncq)
     assert np.array_equal(oko, oks) and np.array_equal(oko, okf)
+    scale = np.abs(Fo).max(axis=1, keepdims=True) + 1e-300
+    scale = np.maximum(scale, np.abs(cells[:, 1:3, 2]).max(axis=1, keepdims=True) * 1e-3)
     bad = np.argwhere(Fs != Fo)
-    if len(bad):
+    if flux == "efm":           # exp() of CUDA and of glibc differ in the last place
+        assert np.max(np.abs(Fs - Fo) / scale) < 1.0e-13
+    elif len(bad):
         i = bad[0][0]
         msg = (f"{len(set(bad[:, 0]))} of {len(Fo)} faces differ; first: face {i}\n cells={cells[i]}\n"
                f" len={lens[i]}\n geo={geo[i]}\n Fo={Fo[i]}\n Fs={Fs[i]}")
         assert False, msg
-    scale = np.abs(Fo).max(axis=1, keepdims=True) + 1e-300
-    scale = np.maximum(scale, np.abs(cells[:, 1:3, 2]).max(axis=1, keepdims=True) * 1e-3)
     assert np.max(np.abs(Ff - Fo) / scale) < 1.0e-11

@@ -39,7 +39,7 @@ def test_cuda_matches_golden(product, name):
             vscale = max(np.abs(ref[f"U_b{bid}_q{q}"]).max() for q in (1, 2))
             for q, a in enumerate(arrs):
                 r = ref[f"U_b{bid}_q{q}"]
-                if strict:
+                if strict and "efm" not in name:       # (efm: exp() of CUDA and glibc differ in the last place)
                     assert np.array_equal(a, r), (name, bid, q)
                 else:
                     scale = vscale if q in (1, 2, 3) and len(arrs) == 5 or q in (1, 2) else np.abs(r).max()

@@ -12,6 +12,7 @@ CPU oracle.  fluxcalc.d / onedinterp.d / fvcell.d have no function-level vectors
 import math
 
 import numpy as np
+import pytest
 
 from gdtk_b200 import Simulation, cases
 
@@ -79,6 +80,18 @@ def test_cone20_with_the_reference_default_flux_calculator(oracle):
     p_surface = float(sim.interior(1, P[2])[0, 0, 20])
     q_inf = 0.5 * (95.84e3 / (gm.Rgas * 1103.0)) * 1000.0 ** 2
     assert abs(p_surface - (95.84e3 + 0.387 * q_inf)) < 1.0e3
+    sim.close()
+
+
+@pytest.mark.parametrize("flux", ["efm", "adaptive"])
+def test_cone20_with_the_equilibrium_flux_method(oracle, flux):
+    """config.flux_calculator = "adaptive" (= adaptive_efm_ausmdv, globalconfig.d:333) is what 37 of the reference's
+    example scripts ask for; cone20 takes the same 833 +- 3 steps with it and with plain efm."""
+    cfg, gm, blocks = cases.cone20(flux_calculator=flux)
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    assert abs(sim.run() - 833) < 3
+    v = probe(sim, blocks, 0.4, 0.5)
+    assert abs(v["a"] - 666.0) < 1.0 and abs(v["p"] - 95.84e3) < 500.0 and abs(v["T"] - 1103.0) < 1.0
     sim.close()
 
 

@@ -17,7 +17,10 @@ pytestmark = pytest.mark.gpu
 REL_TOL_U = 1.0e-10      # north_star: conserved quantities after N steps
 REL_TOL_DT = 1.0e-9      # north_star: dt history
 
-FLUXES = ["ausmdv", "hanel", "ldfss0", "ldfss2", "ausm_plus_up", "roe"]
+# exp() in efm's error-function approximation differs in the last place between CUDA and glibc, so the FMA-free
+# build cannot be bit-identical for the calculators that use it; they are held to the tolerance in both builds
+NOT_BITWISE = ("efm", "adaptive", "adaptive_efm_ausmdv")
+FLUXES = ["ausmdv", "hanel", "ldfss0", "ldfss2", "ausm_plus_up", "roe", "efm"]
 
 
 def _compare(factory, oracle, product, nsteps, expect_bitwise=True, **kw):
@@ -89,13 +92,13 @@ def test_simple_ramp_3d_to_the_end(product):
 @pytest.mark.parametrize("flux", FLUXES)
 def test_flux_calculators_3d_cartesian(oracle, product, flux):
     """C4-style sweep: every flux calculator on a small 3D multi-block box, Cartesian path."""
-    _compare(cases.box3d, oracle, product, 8, n=16, nb=2, flux_calculator=flux)
+    _compare(cases.box3d, oracle, product, 8, n=16, nb=2, flux_calculator=flux, expect_bitwise=flux not in NOT_BITWISE)
 
 
 @pytest.mark.parametrize("flux", FLUXES)
 def test_flux_calculators_3d_general_metric(oracle, product, flux):
     """Same on the sheared (ramp-like) grid: per-face metrics, rotations in the loop."""
-    _compare(cases.box3d, oracle, product, 6, n=12, nb=2, flux_calculator=flux, sheared=True)
+    _compare(cases.box3d, oracle, product, 6, n=12, nb=2, flux_calculator=flux, sheared=True, expect_bitwise=flux not in NOT_BITWISE)
 
 
 @pytest.mark.parametrize("flux", ["ausmdv", "ausm_plus_up", "roe"])
@@ -217,7 +220,7 @@ def test_thermally_perfect_five_species(oracle, product, flux, sheared):
     _compare(cases.tpg_box3d, oracle, product, 5, expect_bitwise=False, n=12, nb=2, flux_calculator=flux, sheared=sheared)
 
 
-ADAPTIVE = ["adaptive_hanel_ausmdv", "adaptive_hanel_ausm_plus_up", "adaptive_ldfss0_ldfss2"]
+ADAPTIVE = ["adaptive_hanel_ausmdv", "adaptive_hanel_ausm_plus_up", "adaptive_ldfss0_ldfss2", "adaptive"]   # "adaptive" = adaptive_efm_ausmdv
 
 
 @pytest.mark.parametrize("flux", ADAPTIVE)
@@ -225,7 +228,7 @@ def test_adaptive_flux_calculators_cone20(oracle, product, flux):
     """The reference's default flux calculator (adaptive_hanel_ausmdv) and its siblings: PJ shock
     detector at stage 1 (detect_shocks), hanel/ldfss0 on marked faces.  cone20 has a real shock,
     reflecting walls, inflow, outflow and a block connection, so ghost-cell S values matter."""
-    _compare(cases.cone20, oracle, product, 120, flux_calculator=flux)
+    _compare(cases.cone20, oracle, product, 120, flux_calculator=flux, expect_bitwise=flux not in NOT_BITWISE)
 
 
 @pytest.mark.parametrize("flux", ADAPTIVE)
@@ -233,9 +236,9 @@ def test_adaptive_flux_calculators_3d(oracle, product, flux):
     if "ausm_plus_up" not in flux:
         # (AUSM+up started from gas at rest is unstable -- the reference says so itself, fluxcalc.d:1421-1424
         #  -- and amplifies round-off differences; the FMA-free build still matches bit for bit)
-        _compare(cases.sod, oracle, product, 40, dims=3, ncells=48, nj=4, nk=3, nblocks=3, flux_calculator=flux)
-    _compare(cases.box3d, oracle, product, 6, n=12, nb=2, sheared=True, flux_calculator=flux)
-    _compare(cases.box3d, oracle, product, 6, n=16, nb=2, flux_calculator=flux)
+        _compare(cases.sod, oracle, product, 40, dims=3, ncells=48, nj=4, nk=3, nblocks=3, flux_calculator=flux, expect_bitwise=flux not in NOT_BITWISE)
+    _compare(cases.box3d, oracle, product, 6, n=12, nb=2, sheared=True, flux_calculator=flux, expect_bitwise=flux not in NOT_BITWISE)
+    _compare(cases.box3d, oracle, product, 6, n=16, nb=2, flux_calculator=flux, expect_bitwise=flux not in NOT_BITWISE)
 
 
 def test_unstable_scheme_still_matches_bitwise_in_strict_build(oracle, product):
