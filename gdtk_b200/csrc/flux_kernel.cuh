@@ -23,6 +23,10 @@
 #ifndef EB_MIN_CTAS
 #define EB_MIN_CTAS 1        // second argument of __launch_bounds__: resident CTAs per SM to aim for
 #endif
+#ifndef EB_MIN_CTAS_TPG
+#define EB_MIN_CTAS_TPG 2    // thermally perfect gas: the Newton solves are latency-bound, two CTAs (128 registers,
+                             // more spills) beat one with 255 registers by 23 %; three (80 registers) lose again
+#endif
 
 namespace EB_NS {
 
@@ -247,7 +251,7 @@ __device__ __forceinline__ void finish_cell(const EbParams& P, const EbGas* __re
 }
 
 template <int DIM, int FLUX, int GASM, int NSP, bool CART, int TY>
-__global__ void __launch_bounds__(32 * TY, EB_MIN_CTAS)
+__global__ void __launch_bounds__(32 * TY, (GASM == EB200_GAS_IDEAL) ? EB_MIN_CTAS : EB_MIN_CTAS_TPG)
 flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc* __restrict__ descs, int nblocks,
                    const EbArena A, const EbStageArgs S)
 {
