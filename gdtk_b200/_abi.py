@@ -39,6 +39,8 @@ BC_INFLOW_SUPERSONIC = 1
 BC_OUTFLOW_SIMPLE_EXTRAPOLATE = 2
 BC_OUTFLOW_SIMPLE_FLUX = 3
 BC_EXCHANGE_FULL_FACE = 4
+BC_OUTFLOW_FIXED_P = 5
+BC_OUTFLOW_FIXED_PT = 6
 
 
 class Species(C.Structure):

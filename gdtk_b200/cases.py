@@ -96,7 +96,7 @@ def ramp3d(flux_calculator="adaptive_hanel_ausmdv", **cfg_kw):
     return cfg, gm, [blk0, blk1]
 
 
-def sod(dims=3, ncells=100, nj=2, nk=2, flux_calculator="ausmdv", nblocks=1, **cfg_kw):
+def sod(dims=3, ncells=100, nj=2, nk=2, flux_calculator="ausmdv", nblocks=1, east_bc=None, west_bc=None, **cfg_kw):
     """Sod's shock tube along x (examples/eilmer/3D/sod-shock-tube/sg/sod.lua: L=1.0,
     high p=1e5,T=348.4 | low p=1e4,T=278.8, ideal air, t=0.6 ms)."""
     gm = ideal_air()
@@ -119,6 +119,10 @@ def sod(dims=3, ncells=100, nj=2, nk=2, flux_calculator="ausmdv", nblocks=1, **c
     for n, (ib, jb, kb, sub) in enumerate(parts):
         blocks[(ib, jb, kb)] = FluidBlock(sub, init, id=n)
     connect_block_array(blocks, dims)
+    if east_bc is not None:            # open the tube at an end (the reference's tube is closed: walls)
+        blocks[(nblocks - 1, 0, 0)].bcList["east"] = east_bc
+    if west_bc is not None:
+        blocks[(0, 0, 0)].bcList["west"] = west_bc
     return cfg, gm, list(blocks.values())
 
 

@@ -439,7 +439,7 @@ int fill_local_ghost_cells(Sim* s, double* prim, bool all_copies)
 {
     const long long ncopy = all_copies ? s->ncopy_full : s->ncopy;
     if (ncopy + s->nrefl + s->nfill > 0)
-        MODE_CALL(s, launch_ghosts, s->P, s->d_desc, s->A, prim, s->d_copy, ncopy, s->d_refl, s->nrefl, s->d_fill, s->nfill, s->d_params, s->stream);
+        MODE_CALL(s, launch_ghosts, s->P, s->d_gas, s->d_desc, s->A, prim, s->d_copy, ncopy, s->d_refl, s->nrefl, s->d_fill, s->nfill, s->d_params, s->stream);
     return 0;
 }
 
@@ -719,12 +719,18 @@ int eb200_block_set_bc(int sim, int blk_id, int face, int kind, const double* pa
     Block* b = get_blk(s, blk_id); if (!b) return -1;
     if (s->committed) { set_err("set_bc after commit"); return -1; }
     if (face < 0 || face >= s->nfaces) { set_err("bad face %d", face); return -1; }
-    if (kind < 0 || kind > EB200_BC_EXCHANGE_FULL_FACE) { set_err("unknown bc kind %d", kind); return -1; }
+    if (kind < 0 || kind > EB200_BC_OUTFLOW_FIXED_PT) { set_err("unknown bc kind %d", kind); return -1; }
     BC& bc = b->bc[face];
     bc.kind = kind; bc.other_blk = other_blk; bc.other_face = other_face; bc.orientation = orientation;
     if (kind == EB200_BC_INFLOW_SUPERSONIC) {
         if (nparams != s->P.nprim || !params) { set_err("inflow FlowState needs %d values", s->P.nprim); return -1; }
         bc.params.assign(params, params + nparams);
+    }
+    if (kind == EB200_BC_OUTFLOW_FIXED_P || kind == EB200_BC_OUTFLOW_FIXED_PT) {
+        const int need = (kind == EB200_BC_OUTFLOW_FIXED_P) ? 1 : 2;
+        if (nparams != need || !params) { set_err("bc kind %d needs %d parameter(s)", kind, need); return -1; }
+        bc.params.assign((size_t)s->P.nprim, 0.0);          // one slot of the parameter table: { p_outside, T_outside | -1 }
+        bc.params[0] = params[0]; bc.params[1] = (need == 2) ? params[1] : -1.0;
     }
     if (kind == EB200_BC_EXCHANGE_FULL_FACE) {
         if (s->threeD && orientation != 0) { set_err("only orientation 0 is supported in 3D"); return -1; }
@@ -905,6 +911,12 @@ int eb200_commit(int sim)
                 params.insert(params.end(), bc.params.begin(), bc.params.end());
                 for_face_ghosts(s, b, f, [&](int, int, int, long long, long long ghost, long long, long long) {
                     fill.push_back({ (int)(b->cell0 + ghost), bc.param_index });
+                });
+            } else if (bc.kind == EB200_BC_OUTFLOW_FIXED_P || bc.kind == EB200_BC_OUTFLOW_FIXED_PT) {
+                bc.param_index = (int)(params.size() / nprim);
+                params.insert(params.end(), bc.params.begin(), bc.params.end());
+                for_face_ghosts(s, b, f, [&](int, int, int, long long, long long ghost, long long mirror, long long) {
+                    refl.push_back({ (int)(b->cell0 + ghost), (int)(b->cell0 + mirror), bc.param_index, b->local_index * 4 + 3 });
                 });
             } else {   // zero-order extrapolation (both outflow kinds)
                 for_face_ghosts(s, b, f, [&](int, int, int, long long, long long ghost, long long, long long first) {

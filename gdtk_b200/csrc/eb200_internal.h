@@ -140,7 +140,7 @@ struct EbFillItem { int dst, param; };
     void launch_signal(const EbParams& P, const EbBlockDesc* descs, int nblocks, long long max_cells,   \
                        const EbArena& A, const double* prim, double dt_current, double cfl_value,        \
                        unsigned long long* red, double* last_signal, cudaStream_t st);                   \
-    void launch_ghosts(const EbParams& P, const EbBlockDesc* desc, const EbArena& A, double* prim,       \
+    void launch_ghosts(const EbParams& P, const EbGas* gas, const EbBlockDesc* desc, const EbArena& A, double* prim, \
                        const EbCopyItem* copy, long long ncopy, const EbReflectItem* refl,               \
                        long long nrefl, const EbFillItem* fill, long long nfill, const double* params,   \
                        cudaStream_t st);                                                                 \

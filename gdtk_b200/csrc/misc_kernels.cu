@@ -216,7 +216,7 @@ void launch_signal(const EbParams& P, const EbBlockDesc* descs, int nblocks, lon
 // extrapolation (extrapolate_copy.d:129-145); reflect: internal_copy_then_reflect.d:111-134
 // with ghost_cell.d:33-43; fill: flow_state_copy.d:92-107.
 
-__global__ void ghost_kernel(const EbParams P, const EbBlockDesc* __restrict__ descs, const EbArena A, double* __restrict__ prim,
+__global__ void ghost_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc* __restrict__ descs, const EbArena A, double* __restrict__ prim,
                              const EbCopyItem* __restrict__ copy, long long ncopy,
                              const EbReflectItem* __restrict__ refl, long long nrefl,
                              const EbFillItem* __restrict__ fill, long long nfill, const double* __restrict__ params)
@@ -240,6 +240,33 @@ __global__ void ghost_kernel(const EbParams P, const EbBlockDesc* __restrict__ d
     } else if (t < ncopy + nrefl) {
         const EbReflectItem it = refl[t - ncopy];
         const double* __restrict__ src = prim + it.src;
+        if ((it.meta & 3) == 3) {
+            // OutFlowBC_FixedP / FixedPT (fixed_p.d, fixed_pt.d): ghost layer n = interior layer n, then p (and T)
+            // from the boundary condition and update_thermo_from_pT; fidx = index of { p_outside, T_outside | -1 }
+            for (int v = 0; v < nprim; ++v) prim[(long long)v * total + it.dst] = __ldg(src + (long long)v * total);
+            const double p_out = params[(long long)it.fidx * nprim], T_out = params[(long long)it.fidx * nprim + 1];
+            const double T = (T_out > 0.0) ? T_out : __ldg(src + 3 * total);
+            double rho, u;
+            if (gas->model == EB200_GAS_IDEAL) {              // ideal_gas.d:89-97
+                rho = p_out / (T * gas->Rgas);
+                u = gas->Cv * T;
+            } else {                                          // perf_gas_mix_eos.d:55-62, therm_perf_gas_mix_eos.d:61-66
+                double Rmix = 0.0;
+                for (int i = 0; i < gas->nsp; ++i) Rmix += __ldg(src + (long long)(8 + i) * total) * gas->Rsp[i];
+                const double denom = Rmix * T;
+                rho = p_out / denom;
+                const double logT = log(T);
+                u = 0.0;
+                for (int i = 0; i < gas->nsp; ++i) {
+                    double h;
+                    cea_h(gas->curves[i], T, logT, h);
+                    u += __ldg(src + (long long)(8 + i) * total) * (h - gas->Rsp[i] * T);
+                }
+            }
+            prim[it.dst] = rho; prim[total + it.dst] = u; prim[2 * total + it.dst] = p_out; prim[3 * total + it.dst] = T;
+            if (P.shock_detect) A.S[it.dst] = A.S[it.src];
+            return;
+        }
         double x = __ldg(src + 5 * total), y = __ldg(src + 6 * total), z = __ldg(src + 7 * total);
         {
             double tmp[5];
@@ -268,14 +295,14 @@ __global__ void ghost_kernel(const EbParams P, const EbBlockDesc* __restrict__ d
     }
 }
 
-void launch_ghosts(const EbParams& P, const EbBlockDesc* desc, const EbArena& A, double* prim,
+void launch_ghosts(const EbParams& P, const EbGas* gas, const EbBlockDesc* desc, const EbArena& A, double* prim,
                    const EbCopyItem* copy, long long ncopy, const EbReflectItem* refl, long long nrefl,
                    const EbFillItem* fill, long long nfill, const double* params, cudaStream_t st)
 {
     const long long n = ncopy + nrefl + nfill;
     if (n == 0) return;
     const int threads = 256;
-    ghost_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(P, desc, A, prim, copy, ncopy, refl, nrefl, fill, nfill, params);
+    ghost_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(P, gas, desc, A, prim, copy, ncopy, refl, nrefl, fill, nfill, params);
 }
 
 // halo pack / unpack for blocks owned by other processes: buf[v*n + t]; with the shock detector on,

@@ -169,6 +169,28 @@ class OutFlowBC_SimpleFlux(BoundaryCondition):
 OutFlowBC_Simple = OutFlowBC_SimpleFlux   # bc.lua:1625
 
 
+class OutFlowBC_FixedP(BoundaryCondition):
+    """bc.lua:1627-1647: extrapolate, then fix the ghost-cell pressure."""
+    kind = _abi.BC_OUTFLOW_FIXED_P
+
+    def __init__(self, p_outside):
+        self.p_outside = float(p_outside)
+
+    def params(self):
+        return [self.p_outside]
+
+
+class OutFlowBC_FixedPT(BoundaryCondition):
+    """bc.lua:1649-1670: extrapolate, then fix the ghost-cell pressure and temperature."""
+    kind = _abi.BC_OUTFLOW_FIXED_PT
+
+    def __init__(self, p_outside, T_outside):
+        self.p_outside, self.T_outside = float(p_outside), float(T_outside)
+
+    def params(self):
+        return [self.p_outside, self.T_outside]
+
+
 class ExchangeBC_FullFace(BoundaryCondition):
     kind = _abi.BC_EXCHANGE_FULL_FACE
 

@@ -103,7 +103,14 @@ enum eb200_bc_kind {
     EB200_BC_OUTFLOW_SIMPLE_FLUX = 3,
     /* ExchangeBC_FullFace (bc.lua:1672): GhostCellFullFaceCopy
      * bc/ghost_cell_effect/full_face_copy.d:1657-1903 */
-    EB200_BC_EXCHANGE_FULL_FACE = 4
+    EB200_BC_EXCHANGE_FULL_FACE = 4,
+    /* OutFlowBC_FixedP (bc.lua:1627-1647): ExtrapolateCopy, then GhostCellFixedP
+     * (bc/ghost_cell_effect/fixed_p.d): ghost cell n = interior cell n with p = p_outside and
+     * update_thermo_from_pT; params = { p_outside } */
+    EB200_BC_OUTFLOW_FIXED_P = 5,
+    /* OutFlowBC_FixedPT (bc.lua:1649-1670), GhostCellFixedPT (fixed_pt.d): also T = T_outside;
+     * params = { p_outside, T_outside } */
+    EB200_BC_OUTFLOW_FIXED_PT = 6
 };
 
 /* Order of the primitive (FlowState) variables in upload/download and in the
@@ -225,6 +232,7 @@ int eb200_block_set_geometry(int sim, int blk_id,
 
 /* Boundary condition of one block face.
  *   kind = EB200_BC_INFLOW_SUPERSONIC: params = FlowState, nparams = 8 (+ 2*nsp if nsp > 1)
+ *   kind = EB200_BC_OUTFLOW_FIXED_P: params = { p_outside }; EB200_BC_OUTFLOW_FIXED_PT: { p_outside, T_outside }
  *   kind = EB200_BC_EXCHANGE_FULL_FACE: other_blk/other_face/orientation as in
  *          full_face_copy.d:141-1380 (orientation 0 only in 3D; 2D all face pairs). */
 int eb200_block_set_bc(int sim, int blk_id, int face, int kind,

@@ -64,6 +64,7 @@ typedef struct {
 typedef struct {
     int kind, other_blk, other_face, orientation;
     FS fstate;               /* for FlowStateCopy */
+    double p_outside, T_outside;   /* FixedP / FixedPT */
 } BC;
 
 typedef struct {
@@ -1149,6 +1150,15 @@ static void apply_pre_recon_bcs(const Sim* s, Blk* b)
                 case EB200_BC_OUTFLOW_SIMPLE_EXTRAPOLATE:
                 case EB200_BC_OUTFLOW_SIMPLE_FLUX:
                     load_fs(s, b, hi ? cf - st : cf, &fs); Sval = b->S[hi ? cf - st : cf]; break;
+                case EB200_BC_OUTFLOW_FIXED_P:
+                case EB200_BC_OUTFLOW_FIXED_PT:
+                    /* ExtrapolateCopy is overwritten by FixedP/FixedPT (fixed_p.d, fixed_pt.d: apply_structured_grid):
+                     * ghost layer n takes interior layer n, then p (and T), then update_thermo_from_pT */
+                    load_fs(s, b, src, &fs); Sval = b->S[src];
+                    fs.gas.p = bc->p_outside;
+                    if (bc->kind == EB200_BC_OUTFLOW_FIXED_PT) fs.gas.T = bc->T_outside;
+                    gas_update_thermo_from_pT(s, &fs.gas);    /* rho_s keeps the copied values, as in the reference */
+                    break;
                 default: continue;
                 }
                 store_fs(s, b, dst, &fs);
@@ -1749,6 +1759,11 @@ int orc_block_set_bc(int sim, int blk_id, int face, int kind, const double* para
     if (kind == EB200_BC_INFLOW_SUPERSONIC) {
         if (nparams != s->nprim) { set_err("inflow FlowState needs %d values", s->nprim); return -1; }
         fs_from_params(s, params, &bc->fstate);
+    }
+    if (kind == EB200_BC_OUTFLOW_FIXED_P || kind == EB200_BC_OUTFLOW_FIXED_PT) {
+        const int need = (kind == EB200_BC_OUTFLOW_FIXED_P) ? 1 : 2;
+        if (nparams != need || !params) { set_err("bc kind %d needs %d parameter(s)", kind, need); return -1; }
+        bc->p_outside = params[0]; bc->T_outside = (need == 2) ? params[1] : 0.0;
     }
     if (kind == EB200_BC_EXCHANGE_FULL_FACE && s->threeD && orientation != 0) { set_err("only orientation 0 supported in 3D"); return -1; }
     return 0;

@@ -210,3 +210,30 @@ def test_mutating_cell_velocities_like_the_reference_changes_nothing_visible(ora
     for a, b in zip(*res):
         scale = np.abs(a).max()
         assert np.max(np.abs(a - b)) <= 1.0e-12 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("with_T", [False, True])
+def test_fixed_pressure_outflow(oracle, with_T):
+    """OutFlowBC_FixedP / OutFlowBC_FixedPT (fixed_p.d, fixed_pt.d): after a step the ghost cells behind the face hold
+    the interior cells of the same layer with p = p_outside (and T = T_outside), rho and u from update_thermo_from_pT."""
+    from gdtk_b200 import OutFlowBC_FixedP, OutFlowBC_FixedPT
+    from gdtk_b200.geometry import NG
+    bc = OutFlowBC_FixedPT(2.0e4, 300.0) if with_T else OutFlowBC_FixedP(2.0e4)
+    cfg, gm, blocks = cases.sod(dims=2, ncells=40, nj=3, nblocks=2, east_bc=bc)
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    sim.run(max_step=30, max_time=1.0)
+    P = sim.download_flow(1)                       # padded arrays, ghost cells as the last stage filled them
+    nic = blocks[1].geom.nic
+    rows = slice(NG, NG + 3)
+    for layer in range(2):
+        ghost = (0, rows, NG + nic + layer)
+        inner = (0, rows, NG + nic - 1 - layer)
+        assert np.all(P[2][ghost] == 2.0e4)
+        T = P[3][ghost]
+        # (the ghost cells were filled from the input of the last stage, the interior is one stage newer)
+        if with_T:
+            assert np.all(T == 300.0)
+        else:
+            assert np.all(np.abs(T - P[3][inner]) < 0.05 * P[3][inner])
+        assert np.array_equal(P[0][ghost], 2.0e4 / (T * gm.Rgas)) and np.array_equal(P[1][ghost], gm.Cv * T)
+    sim.close()

@@ -49,6 +49,29 @@ def test_sod_ausmdv(oracle, product, dims):
     ss, sf = _compare(cases.sod, oracle, product, 60, dims=dims, ncells=100, nblocks=2)
 
 
+@pytest.mark.parametrize("dims", [2, 3])
+def test_fixed_pressure_outflow_boundaries(oracle, product, dims):
+    from gdtk_b200 import OutFlowBC_FixedP, OutFlowBC_FixedPT
+    _compare(cases.sod, oracle, product, 60, dims=dims, ncells=60, nblocks=2, east_bc=OutFlowBC_FixedP(2.0e4),
+             west_bc=OutFlowBC_FixedPT(9.0e4, 340.0))
+
+
+def test_fixed_pressure_outflow_thermally_perfect(oracle, product):
+    from gdtk_b200 import OutFlowBC_FixedPT
+    cfg, gm, blocks = cases.tpg_box3d(n=12, nb=2)
+    for b in blocks:
+        if isinstance(b.bcList.get("east"), type(cases.OutFlowBC_Simple())):
+            b.bcList["east"] = OutFlowBC_FixedPT(9.0e4, 2900.0)
+    runs = []
+    for lib, strict in ((oracle, True), (product, True), (product, False)):
+        cfg.strict_fp = strict
+        sim = Simulation(cfg, gm, blocks, lib=lib)
+        sim.run(max_step=4, max_time=1.0)
+        runs.append({b.id: [sim.interior(b.id, a).copy() for a in sim.download_conserved(b.id)] for b in blocks})
+        sim.close()
+    assert max_rel_diff(runs[1], runs[0]) < REL_TOL_U and max_rel_diff(runs[2], runs[0]) < REL_TOL_U
+
+
 def test_probe_histories(oracle, product):
     """History cells (setHistoryPoint) sampled every dt_history: the FMA-free build gives the oracle's numbers,
     the throughput build is within 1e-9 (north_star: 'dt and probe histories within 1e-9')."""
