@@ -218,3 +218,28 @@ def write_history_file(path, sim, key):
 def job_file(job_dir, job, kind, blk_id, tindx):
     """<job_dir>/<kind>/tNNNN/<job>.<kind>.bBBBB.tNNNN.gz (kind = 'grid' or 'flow'), simcore_io.d naming."""
     return os.path.join(job_dir, kind, f"t{tindx:04d}", f"{job}.{kind}.b{blk_id:04d}.t{tindx:04d}.gz")
+
+
+def write_solution_files(job_dir, job, sim, tindx):
+    """write_solution_files (simcore_io.d:78-132) for the blocks of this process: flow/tNNNN/<job>.flow.bBBBB.tNNNN.gz
+    for every local block and one line "tindx time dt" appended to config/<job>.times.  With the grid files and the
+    .config the reference's preparation wrote, ``e4shared --post`` reads the result."""
+    d = os.path.join(job_dir, "flow", f"t{tindx:04d}")
+    os.makedirs(d, exist_ok=True)
+    for b in sim.local_blocks:
+        write_flow(job_file(job_dir, job, "flow", b.id, tindx), sim, b.id, sim.time, label=getattr(b, "label", "") or "")
+    if getattr(sim, "rank", 0) == 0:
+        os.makedirs(os.path.join(job_dir, "config"), exist_ok=True)
+        with open(os.path.join(job_dir, "config", f"{job}.times"), "a", encoding="ascii") as f:
+            f.write(f"{tindx:04d} {sim.time:.18e} {sim.dt_global:.18e}\n")
+
+
+def read_times(job_dir, job):
+    """config/<job>.times -> {tindx: (time, dt)}; lines starting with # are comments."""
+    out = {}
+    with open(os.path.join(job_dir, "config", f"{job}.times"), encoding="ascii") as f:
+        for line in f:
+            if line.strip() and not line.startswith("#"):
+                t = line.split()
+                out[int(t[0])] = (float(t[1]), float(t[2]))
+    return out

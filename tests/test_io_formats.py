@@ -113,3 +113,21 @@ def test_history_points(tmp_path, oracle):
     assert lines[0].startswith("# 1:t 2:pos.x 3:pos.y") and len(lines) == n + 1
     assert len(lines[1].split()) == 1 + len(io.flow_variable_list(gm))
     sim.close()
+
+
+def test_solution_directory_layout(tmp_path, oracle):
+    """flow/tNNNN/<job>.flow.bBBBB.tNNNN.gz + config/<job>.times, the layout e4shared --post reads."""
+    cfg, gm, blocks = cases.cone20(nx0=6, nx1=14, ny=16)
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    io.write_solution_files(tmp_path, "cone20", sim, 0)
+    sim.run(max_step=20, max_time=1.0)
+    io.write_solution_files(tmp_path, "cone20", sim, 1)
+    times = io.read_times(tmp_path, "cone20")
+    assert times[0] == (0.0, sim.config.dt_init) and times[1] == (sim.time, sim.dt_global)
+    for tindx in (0, 1):
+        for b in (0, 1):
+            f = io.read_flow(io.job_file(tmp_path, "cone20", "flow", b, tindx))
+            assert f["sim_time"] == times[tindx][0] and f["data"]["rho"].shape == (1, 16, 6 if b == 0 else 14)
+    rho = sim.interior(1, sim.download_flow(1)[0])
+    assert np.array_equal(io.read_flow(io.job_file(tmp_path, "cone20", "flow", 1, 1))["data"]["rho"], rho)
+    sim.close()
