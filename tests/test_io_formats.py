@@ -131,3 +131,46 @@ def test_solution_directory_layout(tmp_path, oracle):
     rho = sim.interior(1, sim.download_flow(1)[0])
     assert np.array_equal(io.read_flow(io.job_file(tmp_path, "cone20", "flow", 1, 1))["data"]["rho"], rho)
     sim.close()
+
+
+def test_prepared_job_round_trip(tmp_path, oracle):
+    """write_job (what the preparation stage leaves: config JSON in the layout of output.lua / fluidblock.lua / bc.lua,
+    grid and flow files, .times) and load_job / run_job: the job read back from disk runs exactly like the one
+    built in Python, and writes its solutions and history files."""
+    import shutil
+    from gdtk_b200 import job as jobmod
+    from gdtk_b200 import OutFlowBC_FixedP
+    cfg, gm, blocks = cases.cone20(flux_calculator="adaptive", nx0=6, nx1=14, ny=16, max_step=40, dt_history=2.0e-5)
+    blocks[1].bcList["north"] = OutFlowBC_FixedP(5955.0)
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    shutil.copy(os.path.join(DATA, "ideal-air-gas-model.lua"), tmp_path / "ideal-air-gas-model.lua")
+    jobmod.write_job(tmp_path, "cone20", cfg, gm, "ideal-air-gas-model.lua", blocks, sim, history_points=[(1, 7, 0, 0)])
+    key = sim.set_history_point(1, 7, 0, 0)
+    sim.run()
+    U = sim.interior(1, sim.download_conserved(1)[0]).copy()
+
+    cfg2, gm2, blocks2, hist, t0 = jobmod.load_job(tmp_path, "cone20")
+    assert t0 == 0.0 and hist == [(1, 7, 0, 0)] and cfg2.flux_calculator == "adaptive" and cfg2.axisymmetric is True
+    assert [type(blocks2[1].bcList[f]).__name__ for f in ("west", "east", "south", "north")] == \
+        ["ExchangeBC_FullFace", "OutFlowBC_SimpleFlux", "WallBC_WithSlip", "OutFlowBC_FixedP"]
+    assert type(blocks2[0].bcList["west"]).__name__ == "InFlowBC_Supersonic"
+    s2 = jobmod.run_job(tmp_path, "cone20", lib=oracle)
+    assert s2.step == sim.step == 40 and s2.dt_history == sim.dt_history
+    assert np.array_equal(s2.interior(1, s2.download_conserved(1)[0]), U)
+    assert np.array_equal(np.array(s2.history[key]), np.array(sim.history[key]))
+    times = io.read_times(tmp_path, "cone20")
+    assert sorted(times) == [0, 1] and times[1][0] == s2.time
+    assert os.path.exists(tmp_path / "hist" / "cone20-blk-1-cell-7.dat.0")
+    f = io.read_flow(io.job_file(tmp_path, "cone20", "flow", 1, 1))
+    assert np.array_equal(f["data"]["rho"], s2.interior(1, s2.download_flow(1)[0]))
+    sim.close(); s2.close()
+
+    # a viscous job is refused
+    import json
+    path = tmp_path / "config" / "cone20.config"
+    J = json.load(open(path)); J["viscous"] = True; json.dump(J, open(path, "w"))
+    try:
+        jobmod.load_job(tmp_path, "cone20")
+        assert False, "viscous job was accepted"
+    except ValueError:
+        pass
