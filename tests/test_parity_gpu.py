@@ -306,3 +306,28 @@ def test_step_failure_and_retry(product):
     sim.gasdynamic_step()
     assert sim.dt_global < 1.0e-2
     sim.close()
+
+
+def test_run_stage_command_line(tmp_path, product):
+    """python -m gdtk_b200 --run --job=cone20: a prepared job directory in, solutions out, and the 'Step= N final-t= T'
+    line the reference's test scripts parse (cone20-test.rb:27-31)."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    from gdtk_b200 import io, job as jobmod
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg, gm, blocks = cases.cone20(flux_calculator="adaptive", max_step=80)
+    sim = Simulation(cfg, gm, blocks, lib=product)
+    shutil.copy(os.path.join(root, "tests", "golden", "ref_sample_data", "ideal-air-gas-model.lua"), tmp_path / "ideal-air-gas-model.lua")
+    jobmod.write_job(tmp_path, "cone20", cfg, gm, "ideal-air-gas-model.lua", blocks, sim, history_points=[(1, 20, 0, 0)])
+    sim.run()
+    rho = sim.interior(1, sim.download_flow(1)[0]).copy()
+    sim.close()
+    out = subprocess.run([sys.executable, "-m", "gdtk_b200", "--run", "--job=cone20", f"--dir={tmp_path}"], cwd=root,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = next(t for t in out.stdout.splitlines() if "final-t=" in t)
+    assert int(line.split()[1]) == 80
+    f = io.read_flow(io.job_file(tmp_path, "cone20", "flow", 1, 1))
+    assert np.array_equal(f["data"]["rho"], rho)
