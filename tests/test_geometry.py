@@ -59,3 +59,25 @@ def test_axisymmetric_volume_and_ghost_lengths():
     assert np.array_equal(g.len[0][0, NG:NG + 40, 1], g.len[0][0, NG:NG + 40, NG])
     assert np.array_equal(g.len[0][0, NG:NG + 40, 0], g.len[0][0, NG:NG + 40, NG + 1])
     assert np.array_equal(g.len[1][0, NG + 40 + 1, NG:NG + 30], g.len[1][0, NG + 40 - 2, NG:NG + 30])
+
+
+def test_roberts_cluster_function_matches_the_reference_unit_test():
+    """src/geom/misc/univariatefunctions.d:814-816: RobertsFunction(false, true, 1.1)."""
+    from gdtk_b200.grids import roberts_function
+    cf = roberts_function(False, True, 1.1)
+    assert abs(float(cf(0.1)) - 0.166167) < 1.0e-4 * 0.166167 + 1e-9
+    assert abs(float(cf(0.9)) - 0.96657) < 1.0e-4 * 0.96657 + 1e-9
+    assert float(cf(0.0)) == 0.0 and abs(float(cf(1.0)) - 1.0) < 1e-15
+    # clustering towards the other end is the mirror image
+    rev = roberts_function(True, False, 1.1)
+    assert abs(float(rev(0.9)) - (1.0 - float(cf(0.1)))) < 1e-15
+
+
+def test_hexahedron_grid_is_the_trilinear_map_of_its_corners():
+    from gdtk_b200.grids import hex_volume_grid
+    c = [[0, 0, 0], [2, 0, 0.5], [2, 1, 0.5], [0, 1, 0], [0, 0, 1], [2, 0, 1], [2, 1, 1], [0, 1, 1]]
+    X, Y, Z = hex_volume_grid(c, 5, 3, 4)
+    assert X.shape == (4, 3, 5)
+    assert (X[0, 0, 0], Y[0, 0, 0], Z[0, 0, 0]) == (0.0, 0.0, 0.0) and (X[-1, -1, -1], Y[-1, -1, -1], Z[-1, -1, -1]) == (2.0, 1.0, 1.0)
+    assert abs(Z[0, 0, -1] - 0.5) < 1e-15 and abs(Z[0, 1, 2] - 0.25) < 1e-15      # bottom face rises linearly along x
+    assert np.allclose(X[:, :, 2], 1.0)
