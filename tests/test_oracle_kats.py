@@ -64,6 +64,8 @@ def test_cone20(oracle):
     rho_inf = 95.84e3 / (gm.Rgas * 1103.0)
     q_inf = 0.5 * rho_inf * 1000.0 ** 2
     assert abs(p_surface - (95.84e3 + 0.387 * q_inf)) < 1.0e3
+    angle, dev = ramp_shock_angle(sim, blocks, other=1, x_limit=0.9)     # cone20-test.rb:108-109
+    assert abs(angle - 49.547) < 1.0 and dev < 0.002
     sim.close()
 
 
@@ -133,14 +135,15 @@ def ramp_force(sim, blocks):
     return [-float(np.sum(f[9][sl] * p * f[m][sl])) for m in range(3)]
 
 
-def ramp_shock_angle(sim, blocks):
-    """estimate_shock_angle.lua: 30 % pressure rise along every i-strip, straight-line fit in (x, z)."""
+def ramp_shock_angle(sim, blocks, other=2, x_limit=0.65):
+    """estimate_shock_angle.lua: 30 % pressure rise along every i-strip, straight-line fit in (x, z) for the ramp,
+    in (x, y) with x < 0.9 for the cone."""
     from gdtk_b200.geometry import NG
     xs, zs, ps = [], [], []
     for b in blocks:
         g = b.geom
         sl = (slice(g.kg, g.kg + g.nkc), slice(NG, NG + g.njc), slice(NG, NG + g.nic))
-        xs.append(g.pos[0][sl]); zs.append(g.pos[2][sl]); ps.append(sim.interior(b.id, sim.download_flow(b.id)[2]))
+        xs.append(g.pos[0][sl]); zs.append(g.pos[other][sl]); ps.append(sim.interior(b.id, sim.download_flow(b.id)[2]))
     X, Z, P = (np.concatenate(a, axis=2) for a in (xs, zs, ps))
     xsh, ysh = [], []
     for k in range(P.shape[0]):
@@ -156,7 +159,7 @@ def ramp_shock_angle(sim, blocks):
                 xo, yo, po = xn, yn, pn
             fr = (trig - po) / (pn - po)
             xl, yl = xo * (1 - fr) + xn * fr, yo * (1 - fr) + yn * fr
-            if xl < 0.65:
+            if xl < x_limit:
                 xsh.append(xl); ysh.append(yl)
     xsh, ysh = np.array(xsh), np.array(ysh)
     a1 = (np.mean(xsh * ysh) - xsh.mean() * ysh.mean()) / (np.mean(xsh * xsh) - xsh.mean() ** 2)
