@@ -9,7 +9,7 @@ the accelerated path on disk.
   ``build_flow_variable_list`` (:107-152)
 * the files of src/eilmer/sample-data (an earlier layout of the same two formats without keywords in
   the header) are read as well; they are the reference's own sample output and serve as golden data
-  (tests/golden/ref_sample_data, tests/test_io_formats.py).
+  (tests/golden/ref_sample_cone20.npz made by tests/golden/make_ref_sample_fixtures.py; tests/test_io_formats.py).
 
 Host-side plumbing only (numpy + gzip); nothing here touches the GPU.
 """

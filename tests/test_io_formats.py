@@ -1,29 +1,48 @@
-"""Eilmer's grid and flow file formats (gdtk_b200/io.py) against the reference's own sample output
-(tests/golden/ref_sample_data = src/eilmer/sample-data of the reference): the files pin the readers,
-the cell geometry and the ideal-gas state; the job they describe (cone20 as the reference prepared
-it, block 1 on its area-orthogonality grid) is then run through the oracle."""
+"""Eilmer's grid and flow file formats (gdtk_b200/io.py, job.py) and the reference's own sample output
+(src/eilmer/sample-data of the reference: the cone20 grids and initial flow files its preparation stage wrote).
+tests/golden/ref_sample_cone20.npz holds the arrays of those files (tests/golden/make_ref_sample_fixtures.py);
+they pin the cell geometry and the relations of the ideal-gas state, and the job they describe (block 1 on its
+area-orthogonality grid) is run through the oracle.  Where the reference tree itself is present (the build
+container) the readers are also run on the original files."""
 import os
 
 import numpy as np
+import pytest
 
 from gdtk_b200 import Simulation, cases, io
-from gdtk_b200.gas import set_gas_model
+from gdtk_b200.gas import FlowState, set_gas_model
 from gdtk_b200.geometry import NG, geometry_2d
 from gdtk_b200.sim import FluidBlock, InFlowBC_Supersonic, OutFlowBC_Simple, identify_block_connections
 
-DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_sample_data")
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+GAS = os.path.join(GOLD, "gas", "ideal-air-gas-model.json")
+REF_SAMPLES = "/root/reference/src/eilmer/sample-data"
+SAMPLE = dict(np.load(os.path.join(GOLD, "ref_sample_cone20.npz")))
 
 
-def sample(kind, blk):
-    return os.path.join(DATA, f"cone20.{kind}.b{blk:04d}.t0000.gz")
+def sample_flow(b):
+    names = [str(n) for n in SAMPLE[f"b{b}_names"]]
+    return {"sim_time": float(SAMPLE[f"b{b}_sim_time"]), "names": names, "label": "", "dimensions": 2,
+            "data": {n: SAMPLE[f"b{b}_{n}"] for n in names}}
 
 
-def test_sample_grids_are_read():
-    g0, g1 = io.read_grid(sample("grid", 0)), io.read_grid(sample("grid", 1))
-    assert g0["X"].shape == (1, 41, 11) and g1["X"].shape == (1, 41, 31) and g0["dimensions"] == 2
-    assert g0["X"][0, 0, -1] == 0.2 and g1["X"][0, 0, 0] == 0.2          # the blocks meet at x = 0.2
-    assert abs(g1["Y"][0, 0, -1] - 0.29118) < 1e-12 and g1["X"][0, 0, -1] == 1.0    # end of the cone surface
-    assert np.all(g1["Y"][0, -1, :] == 1.0)
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="the reference tree is not on this machine")
+def test_readers_on_the_reference_files():
+    for b in (0, 1):
+        g = io.read_grid(os.path.join(REF_SAMPLES, f"cone20.grid.b{b:04d}.t0000.gz"))
+        assert g["dimensions"] == 2 and np.array_equal(g["X"][0], SAMPLE[f"b{b}_X"]) and np.array_equal(g["Y"][0], SAMPLE[f"b{b}_Y"])
+        f = io.read_flow(os.path.join(REF_SAMPLES, f"cone20.flow.b{b:04d}.t0000.gz"))
+        assert f["names"][:5] == ["pos.x", "pos.y", "pos.z", "volume", "rho"] and f["sim_time"] == 0.0
+        assert all(np.array_equal(f["data"][n], SAMPLE[f"b{b}_{n}"]) for n in f["names"])
+
+
+def test_sample_grids():
+    X0, X1, Y1 = SAMPLE["b0_X"], SAMPLE["b1_X"], SAMPLE["b1_Y"]
+    assert X0.shape == (41, 11) and X1.shape == (41, 31)
+    assert X0[0, -1] == 0.2 and X1[0, 0] == 0.2                         # the blocks meet at x = 0.2
+    assert abs(Y1[0, -1] - 0.29118) < 1e-12 and X1[0, -1] == 1.0         # end of the cone surface
+    assert np.all(Y1[-1, :] == 1.0)
 
 
 def test_cell_centres_and_axisymmetric_volumes_match_the_reference_output():
@@ -32,24 +51,22 @@ def test_cell_centres_and_axisymmetric_volumes_match_the_reference_output():
     the unrounded vertices: differences of coordinates rounded at 5e-13 over cell sizes of 0.02 leave
     about 1e-10 of the cell volume."""
     for blk in (0, 1):
-        X, Y = io.grid_arrays(io.read_grid(sample("grid", blk)))
-        geom = geometry_2d(X, Y, True)
-        f = io.read_flow(sample("flow", blk))["data"]
+        geom = geometry_2d(SAMPLE[f"b{blk}_X"], SAMPLE[f"b{blk}_Y"], True)
         sl = (0, slice(NG, NG + geom.njc), slice(NG, NG + geom.nic))
-        for mine, ref in ((geom.pos[0][sl], f["pos.x"][0]), (geom.pos[1][sl], f["pos.y"][0]), (geom.vol[sl], f["volume"][0])):
+        for mine, ref in ((geom.pos[0][sl], SAMPLE[f"b{blk}_pos.x"][0]), (geom.pos[1][sl], SAMPLE[f"b{blk}_pos.y"][0]),
+                          (geom.vol[sl], SAMPLE[f"b{blk}_volume"][0])):
             assert np.max(np.abs(mine - ref) / np.abs(ref)) < 1.0e-10
 
 
 def test_ideal_gas_relations_hold_in_the_reference_output():
     """The sample flow files were written with an earlier ideal-air file (R = 8.31451/0.028964, not the
-    0.02896 of the lua file next to them), so only the relations between the columns are checked:
+    0.02896 of today's file), so only the relations between the columns are checked:
     a^2 = gamma p / rho, e = p / (rho (gamma - 1)), R = p / (rho T) constant."""
-    gm = set_gas_model(os.path.join(DATA, "ideal-air-gas-model.lua"))
+    gm = set_gas_model(GAS)
     for blk in (0, 1):
-        f = io.read_flow(sample("flow", blk))["data"]
-        p, T, rho = f["p"], f["T[0]"], f["rho"]
-        assert np.max(np.abs(np.sqrt(gm.gamma * p / rho) - f["a"]) / f["a"]) < 2e-12
-        assert np.max(np.abs(p / (rho * (gm.gamma - 1.0)) - f["e[0]"]) / f["e[0]"]) < 2e-12
+        p, T, rho = SAMPLE[f"b{blk}_p"], SAMPLE[f"b{blk}_T[0]"], SAMPLE[f"b{blk}_rho"]
+        assert np.max(np.abs(np.sqrt(gm.gamma * p / rho) - SAMPLE[f"b{blk}_a"]) / SAMPLE[f"b{blk}_a"]) < 2e-12
+        assert np.max(np.abs(p / (rho * (gm.gamma - 1.0)) - SAMPLE[f"b{blk}_e[0]"]) / SAMPLE[f"b{blk}_e[0]"]) < 2e-12
         R = p / (rho * T)
         assert abs(R.max() - R.min()) / R.max() < 2e-12 and abs(R.mean() - 8.31451 / 0.028964) < 1e-6
 
@@ -76,15 +93,13 @@ def test_grid_and_flow_round_trip(tmp_path, oracle):
     sim.close(); s2.close()
 
 
-def test_cone20_from_the_reference_files(oracle):
+def test_cone20_on_the_reference_grid(oracle):
     """The job as the reference prepared it: its grids (block 1 is the area-orthogonality grid that
-    cases.cone20 replaces by a Coons patch) and its initial flow files, the default flux calculator.
+    cases.cone20 replaces by a Coons patch) and its initial flow, the default flux calculator.
     cone20-test.rb expects 833 +- 3 steps."""
-    gm = set_gas_model(os.path.join(DATA, "ideal-air-gas-model.lua"))
+    gm = set_gas_model(GAS)
     cfg, _, _ = cases.cone20(flux_calculator="adaptive_hanel_ausmdv")
-    blocks = [FluidBlock(io.grid_arrays(io.read_grid(sample("grid", b))), io.FlowFromFile(io.read_flow(sample("flow", b))), id=b)
-              for b in (0, 1)]
-    from gdtk_b200.gas import FlowState
+    blocks = [FluidBlock((SAMPLE[f"b{b}_X"], SAMPLE[f"b{b}_Y"]), io.FlowFromFile(sample_flow(b)), id=b) for b in (0, 1)]
     blocks[0].bcList["west"] = InFlowBC_Supersonic(FlowState(gm, p=95.84e3, T=1103.0, velx=1000.0))
     blocks[1].bcList["east"] = OutFlowBC_Simple()
     identify_block_connections(blocks, 2)
@@ -143,8 +158,8 @@ def test_prepared_job_round_trip(tmp_path, oracle):
     cfg, gm, blocks = cases.cone20(flux_calculator="adaptive", nx0=6, nx1=14, ny=16, max_step=40, dt_history=2.0e-5)
     blocks[1].bcList["north"] = OutFlowBC_FixedP(5955.0)
     sim = Simulation(cfg, gm, blocks, lib=oracle)
-    shutil.copy(os.path.join(DATA, "ideal-air-gas-model.lua"), tmp_path / "ideal-air-gas-model.lua")
-    jobmod.write_job(tmp_path, "cone20", cfg, gm, "ideal-air-gas-model.lua", blocks, sim, history_points=[(1, 7, 0, 0)])
+    shutil.copy(GAS, tmp_path / "ideal-air-gas-model.json")
+    jobmod.write_job(tmp_path, "cone20", cfg, gm, "ideal-air-gas-model.json", blocks, sim, history_points=[(1, 7, 0, 0)])
     key = sim.set_history_point(1, 7, 0, 0)
     sim.run()
     U = sim.interior(1, sim.download_conserved(1)[0]).copy()

@@ -319,8 +319,8 @@ def test_run_stage_command_line(tmp_path, product):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cfg, gm, blocks = cases.cone20(flux_calculator="adaptive", max_step=80)
     sim = Simulation(cfg, gm, blocks, lib=product)
-    shutil.copy(os.path.join(root, "tests", "golden", "ref_sample_data", "ideal-air-gas-model.lua"), tmp_path / "ideal-air-gas-model.lua")
-    jobmod.write_job(tmp_path, "cone20", cfg, gm, "ideal-air-gas-model.lua", blocks, sim, history_points=[(1, 20, 0, 0)])
+    shutil.copy(os.path.join(root, "tests", "golden", "gas", "ideal-air-gas-model.json"), tmp_path / "ideal-air-gas-model.json")
+    jobmod.write_job(tmp_path, "cone20", cfg, gm, "ideal-air-gas-model.json", blocks, sim, history_points=[(1, 20, 0, 0)])
     sim.run()
     rho = sim.interior(1, sim.download_flow(1)[0]).copy()
     sim.close()
