@@ -30,6 +30,7 @@ UPDATE_SCHEMES = {
     "euler": 0, "pc": 1, "predictor-corrector": 1, "predictor_corrector": 1,
     "midpoint": 2, "classic-rk3": 3, "classic_rk3": 3, "tvd-rk3": 4, "tvd_rk3": 4,
 }
+THERMO_INTERPOLATORS = {"rhou": 0, "pt": 1, "rhop": 2, "rhot": 3}
 N_STAGES = {0: 1, 1: 2, 2: 2, 3: 3, 4: 3}
 
 GAS_IDEAL, GAS_THERMALLY_PERFECT = 0, 1
@@ -70,7 +71,7 @@ class Config(C.Structure):
         ("strict_fp", C.c_int),
         ("rank", C.c_int),
         ("device", C.c_int),
-        ("reserved_i", C.c_int * 5),
+        ("reserved_i", C.c_int * 4), ("thermo_interpolator", C.c_int),
         ("epsilon_van_albada", C.c_double),
         ("M_inf", C.c_double),
         ("max_velocity", C.c_double),

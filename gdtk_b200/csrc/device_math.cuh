@@ -434,6 +434,43 @@ __device__ __forceinline__ bool thermo_from_rhoT(const EbGas* __restrict__ g, Pr
     }
 }
 
+// ideal_gas.d:89-97 / therm_perf_gas.d:230-234 update_thermo_from_pT
+template <int GASM, int NSP>
+__device__ __forceinline__ bool thermo_from_pT(const EbGas* __restrict__ g, Prim<NSP>& Q)
+{
+    if (GASM == EB200_GAS_IDEAL) {
+        if (Q.T <= 0.0 || Q.p <= 0.0) return false;
+        Q.rho = eb_div(Q.p, (Q.T * g->Rgas));
+        Q.u = g->Cv * Q.T;
+        return true;
+    } else {
+        double Rmix = 0.0;
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) Rmix += Q.massf[i] * g->Rsp[i];
+        const double denom = Rmix * Q.T;
+        Q.rho = eb_div(Q.p, denom);
+        return tpg_energy<NSP>(g, Q.massf, Q.T, Q.u);
+    }
+}
+
+// ideal_gas.d:116-124 / therm_perf_gas.d:245-249 update_thermo_from_rhop
+template <int GASM, int NSP>
+__device__ __forceinline__ bool thermo_from_rhop(const EbGas* __restrict__ g, Prim<NSP>& Q)
+{
+    if (GASM == EB200_GAS_IDEAL) {
+        if (Q.p <= 0.0 || Q.rho <= 0.0) return false;
+        Q.T = eb_div(Q.p, (Q.rho * g->Rgas));
+        Q.u = g->Cv * Q.T;
+        return true;
+    } else {
+        double Rmix = 0.0;
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) Rmix += Q.massf[i] * g->Rsp[i];
+        Q.T = eb_div(Q.p, (Rmix * Q.rho));
+        return tpg_energy<NSP>(g, Q.massf, Q.T, Q.u);
+    }
+}
+
 template <int GASM, int NSP>
 __device__ __forceinline__ bool sound_speed(const EbGas* __restrict__ g, Prim<NSP>& Q)
 {

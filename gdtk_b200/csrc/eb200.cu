@@ -593,6 +593,10 @@ int eb200_init(const eb200_config* cfg)
     P.eps_va = cfg->epsilon_van_albada; P.M_inf = cfg->M_inf; P.max_velocity = cfg->max_velocity;
     P.max_temp = cfg->max_temp; P.min_temp = cfg->min_temp; P.low_T = cfg->suggested_low_T_value;
     P.shock_detect = adaptive ? 1 : 0; P.strict_shock = cfg->strict_shock_detector;
+    if (cfg->thermo_interpolator < EB200_INTERP_RHOU || cfg->thermo_interpolator > EB200_INTERP_RHOT) {
+        set_err("unknown thermo_interpolator %d", cfg->thermo_interpolator); return -1;
+    }
+    P.thermo_interp = cfg->thermo_interpolator; P.pad_ti = 0;
     P.comp_tol = cfg->compression_tolerance; P.shear_tol = cfg->shear_tolerance;
     EbGas& g = s->hgas; memset(&g, 0, sizeof g);
     g.model = cfg->gas_model; g.nsp = cfg->n_species;

@@ -22,7 +22,8 @@ void EB_CAT(launch_flux_update_k, EB_FLUX)(const EbParams& P, int gas_model, con
 {
     // tile_y < 0: force the generic kernel (A/B testing); otherwise the tuned kernel handles the reference's
     // default configuration (ideal gas, second-order reconstruction, limiter on)
-    const bool tuned = (tile_y >= 0) && gas_model == EB200_GAS_IDEAL && P.interpolation_order == 2 && P.apply_limiter != 0;
+    const bool tuned = (tile_y >= 0) && gas_model == EB200_GAS_IDEAL && P.interpolation_order == 2 && P.apply_limiter != 0 &&
+                       P.thermo_interp == EB200_INTERP_RHOU;
     if (tuned) launch_flux_update_v2_impl<EB_FLUX>(P, gas, desc, nblocks, ncta, A, S, which, st);
     else launch_flux_update_impl<EB_FLUX>(P, gas_model, gas, desc, nblocks, ncta, A, S, tile_y, which, st);
 }

@@ -124,32 +124,70 @@ __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __rest
         interp_scalar(w, lim, clip, eps, vL1y, vL0y, vR0y, vR1y, L.vy, R.vy);
         if (DIM == 3) interp_scalar(w, lim, clip, eps, vL1z, vL0z, vR0z, vR1z, L.vz, R.vz);
         else { L.vz = 0.0; R.vz = 0.0; }
+        const int ti = P.thermo_interp;
+        bool okL, okR;
         if (NSP > 1) {
-            double rho_L = 0.0, rho_R = 0.0;
 #pragma unroll
             for (int i = 0; i < NSP; ++i) {
                 const double* ps = prim + (8 + NSP + i) * total;
                 interp_scalar(w, lim, clip, eps, ldg(ps + cL1), ldg(ps + cL0), ldg(ps + cR0), ldg(ps + cR1), L.rho_s[i], R.rho_s[i]);
-                rho_L += L.rho_s[i]; rho_R += R.rho_s[i];
             }
-            L.rho = rho_L; R.rho = rho_R;
+        }
+        if (ti == EB200_INTERP_PT) {            // onedinterp.d:820-850: p and T, then the mass fractions
+            const double* pp = prim + 2 * total;
+            const double* pT = prim + 3 * total;
+            interp_scalar(w, lim, clip, eps, ldg(pp + cL1), ldg(pp + cL0), ldg(pp + cR0), ldg(pp + cR1), L.p, R.p);
+            interp_scalar(w, lim, clip, eps, ldg(pT + cL1), ldg(pT + cL0), ldg(pT + cR0), ldg(pT + cR1), L.T, R.T);
+            if (NSP > 1) {                      // Lft/Rght start as copies of the cells: their mass fractions
+#pragma unroll
+                for (int i = 0; i < NSP; ++i) { L.massf[i] = ldg(prim + (8 + i) * total + cL0); R.massf[i] = ldg(prim + (8 + i) * total + cR0); }
+            } else { L.massf[0] = 1.0; R.massf[0] = 1.0; }
+            okL = thermo_from_pT<GASM, NSP>(gas, L);
+            okR = thermo_from_pT<GASM, NSP>(gas, R);
+        } else {
+            if (NSP > 1) {
+                double rho_L = 0.0, rho_R = 0.0;
+#pragma unroll
+                for (int i = 0; i < NSP; ++i) { rho_L += L.rho_s[i]; rho_R += R.rho_s[i]; }
+                L.rho = rho_L; R.rho = rho_R;
+#pragma unroll
+                for (int i = 0; i < NSP; ++i) { L.massf[i] = L.rho_s[i] / L.rho; R.massf[i] = R.rho_s[i] / R.rho; }
+                ok &= scale_mass_fractions<NSP>(L.massf);
+                ok &= scale_mass_fractions<NSP>(R.massf);
+            } else {
+                interp_scalar(w, lim, clip, eps, ldg(prim + cL1), rhoL0, rhoR0, ldg(prim + cR1), L.rho, R.rho);
+                L.massf[0] = 1.0; R.massf[0] = 1.0;
+            }
+            if (ti == EB200_INTERP_RHOP) {
+                const double* pp = prim + 2 * total;
+                interp_scalar(w, lim, clip, eps, ldg(pp + cL1), ldg(pp + cL0), ldg(pp + cR0), ldg(pp + cR1), L.p, R.p);
+                okL = thermo_from_rhop<GASM, NSP>(gas, L);
+                okR = thermo_from_rhop<GASM, NSP>(gas, R);
+            } else if (ti == EB200_INTERP_RHOT) {
+                const double* pT = prim + 3 * total;
+                interp_scalar(w, lim, clip, eps, ldg(pT + cL1), ldg(pT + cL0), ldg(pT + cR0), ldg(pT + cR1), L.T, R.T);
+                okL = thermo_from_rhoT<GASM, NSP>(gas, L);
+                okR = thermo_from_rhoT<GASM, NSP>(gas, R);
+            } else {
+                interp_scalar(w, lim, clip, eps, ldg(prim + total + cL1), uL0, uR0, ldg(prim + total + cR1), L.u, R.u);
+                okL = thermo_from_rhou<GASM, NSP>(gas, L);
+                okR = thermo_from_rhou<GASM, NSP>(gas, R);
+            }
+        }
+        // on a failed thermo update: fall back to the cell-centre state (onedinterp.d:45-74)
+        if (!okL) {
+            load_prim<NSP>(L, prim, total, cL0);
+            L.vx = vL0x; L.vy = vL0y; L.vz = vL0z;        // the cell's velocity, currently in the local frame
+        }
+        if (!okR) {
+            load_prim<NSP>(R, prim, total, cR0);
+            R.vx = vR0x; R.vy = vR0y; R.vz = vR0z;
+        }
+        if (ti == EB200_INTERP_PT && NSP > 1) {
 #pragma unroll
             for (int i = 0; i < NSP; ++i) { L.massf[i] = L.rho_s[i] / L.rho; R.massf[i] = R.rho_s[i] / R.rho; }
             ok &= scale_mass_fractions<NSP>(L.massf);
             ok &= scale_mass_fractions<NSP>(R.massf);
-        } else {
-            interp_scalar(w, lim, clip, eps, ldg(prim + cL1), rhoL0, rhoR0, ldg(prim + cR1), L.rho, R.rho);
-            L.massf[0] = 1.0; R.massf[0] = 1.0;
-        }
-        interp_scalar(w, lim, clip, eps, ldg(prim + total + cL1), uL0, uR0, ldg(prim + total + cR1), L.u, R.u);
-        // thermo update with fall-back to the cell-centre state (onedinterp.d:45-74)
-        if (!thermo_from_rhou<GASM, NSP>(gas, L)) {
-            load_prim<NSP>(L, prim, total, cL0);
-            L.vx = vL0x; L.vy = vL0y; L.vz = vL0z;        // the cell's velocity, currently in the local frame
-        }
-        if (!thermo_from_rhou<GASM, NSP>(gas, R)) {
-            load_prim<NSP>(R, prim, total, cR0);
-            R.vx = vR0x; R.vy = vR0y; R.vz = vR0z;
         }
         if (!CART && local_frame) {
             // back to the global frame (onedinterp.d:979-987); the flux calculation rotates again

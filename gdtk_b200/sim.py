@@ -93,8 +93,8 @@ class Config:
             raise ValueError(f"gasdynamic_update_scheme {self.gasdynamic_update_scheme!r} not supported")
         if self.interpolation_order not in (1, 2):
             raise ValueError("interpolation_order must be 1 or 2 on this path")
-        if self.thermo_interpolator != "rhou":
-            raise ValueError("only thermo_interpolator='rhou' (the default) is on this path")
+        if self.thermo_interpolator not in _abi.THERMO_INTERPOLATORS:
+            raise ValueError(f"unknown thermo_interpolator {self.thermo_interpolator!r}")
         if self.viscous or self.reacting:
             raise ValueError("viscous / reacting flow is outside the accelerated path")
         if self.axisymmetric and self.dimensions != 2:
@@ -114,6 +114,7 @@ class Config:
         c.update_scheme = _abi.UPDATE_SCHEMES[self.gasdynamic_update_scheme]
         c.max_invalid_cells = self.max_invalid_cells
         c.strict_fp = int(self.strict_fp)
+        c.thermo_interpolator = _abi.THERMO_INTERPOLATORS[self.thermo_interpolator]
         c.reserved_i[0] = int(self.force_general_path)
         c.reserved_i[1] = int(self.force_generic_kernel)
         c.reserved_i[2] = int(self.no_tma)

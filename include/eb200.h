@@ -71,6 +71,11 @@ enum eb200_flux_calculator {
     EB200_FLUX_ADAPTIVE_EFM_AUSMDV = 10          /* config.flux_calculator = "adaptive" (globalconfig.d:333) */
 };
 
+/* config.thermo_interpolator (globalconfig.d:1073, onedinterp.d:771-978) */
+enum eb200_thermo_interpolator {
+    EB200_INTERP_RHOU = 0, EB200_INTERP_PT = 1, EB200_INTERP_RHOP = 2, EB200_INTERP_RHOT = 3
+};
+
 /* config.gasdynamic_update_scheme (src/eilmer/globalconfig.d:126-200);
  * gamma tables at simcore_gasdynamic_step.d:1235-1395. */
 enum eb200_update_scheme {
@@ -159,11 +164,13 @@ typedef struct eb200_config {
                                        0: fused multiply-add allowed (throughput build) */
     int rank;                       /* this process's rank (0 when single process) */
     int device;                     /* CUDA device ordinal used by this process */
-    int reserved_i[5];              /* testing knobs: [0] != 0 never use the uniform-Cartesian fast path;
+    int reserved_i[4];              /* testing knobs: [0] != 0 never use the uniform-Cartesian fast path;
                                        [1] != 0 always use the generic flux kernel;
                                        [2] != 0 stage tiles with cp.async even where TMA could be used;
                                        [3] != 0 fill every ghost cell with the ghost-cell kernel (no stores into
                                        neighbouring blocks from the flux kernel) */
+    int thermo_interpolator;        /* eb200_thermo_interpolator: which pair of thermodynamic variables is
+                                       reconstructed (config.thermo_interpolator, onedinterp.d:771-978); 0 = rhou */
     double epsilon_van_albada;      /* 1e-12 */
     double M_inf;                   /* 0.01 (ausm_plus_up) */
     double max_velocity;            /* flowstate_limits: 30000 */

@@ -564,7 +564,23 @@ static int interp_l2r2(const Sim* s, FS cells[4], const double len[4], const Fac
             interp_l2r2_scalar(s, &w, cL1->gas.rho_s[i], cL0->gas.rho_s[i], cR0->gas.rho_s[i], cR1->gas.rho_s[i],
                                &Lft->gas.rho_s[i], &Rght->gas.rho_s[i], beta);
     }
-    /* case InterpolateOption.rhou :854-896 */
+    const int ti = s->cfg.thermo_interpolator;
+    if (ti == EB200_INTERP_PT) {                      /* case InterpolateOption.pt :820-850 */
+        interp_l2r2_scalar(s, &w, cL1->gas.p, cL0->gas.p, cR0->gas.p, cR1->gas.p, &Lft->gas.p, &Rght->gas.p, beta);
+        interp_l2r2_scalar(s, &w, cL1->gas.T, cL0->gas.T, cR0->gas.T, cR1->gas.T, &Lft->gas.T, &Rght->gas.T, beta);
+        if (gas_update_thermo_from_pT(s, &Lft->gas)) *Lft = *cL0;
+        if (gas_update_thermo_from_pT(s, &Rght->gas)) *Rght = *cR0;
+        if (nsp > 1) {
+            for (int i = 0; i < nsp; ++i) {
+                Lft->gas.massf[i] = Lft->gas.rho_s[i] / Lft->gas.rho;
+                Rght->gas.massf[i] = Rght->gas.rho_s[i] / Rght->gas.rho;
+            }
+            if (scale_mass_fractions(nsp, Lft->gas.massf)) return -1;
+            if (scale_mass_fractions(nsp, Rght->gas.massf)) return -1;
+        } else { Lft->gas.massf[0] = 1.0; Rght->gas.massf[0] = 1.0; }
+        goto back_to_global;
+    }
+    /* cases rhou :854-896, rhop :896-940, rhot :940-978 share the density part */
     if (nsp > 1) {
         double rho_L = 0.0, rho_R = 0.0;
         for (int i = 0; i < nsp; ++i) { rho_L += Lft->gas.rho_s[i]; rho_R += Rght->gas.rho_s[i]; }
@@ -579,10 +595,21 @@ static int interp_l2r2(const Sim* s, FS cells[4], const double len[4], const Fac
     } else {
         interp_l2r2_scalar(s, &w, cL1->gas.rho, cL0->gas.rho, cR0->gas.rho, cR1->gas.rho, &Lft->gas.rho, &Rght->gas.rho, beta);
     }
-    interp_l2r2_scalar(s, &w, cL1->gas.u, cL0->gas.u, cR0->gas.u, cR1->gas.u, &Lft->gas.u, &Rght->gas.u, beta);
-    /* mixin(codeForThermoUpdateBoth("rhou")) :45-74: on exception copy the whole cell state */
-    if (gas_update_thermo_from_rhou(s, &Lft->gas)) *Lft = *cL0;
-    if (gas_update_thermo_from_rhou(s, &Rght->gas)) *Rght = *cR0;
+    if (ti == EB200_INTERP_RHOP) {
+        interp_l2r2_scalar(s, &w, cL1->gas.p, cL0->gas.p, cR0->gas.p, cR1->gas.p, &Lft->gas.p, &Rght->gas.p, beta);
+        if (gas_update_thermo_from_rhop(s, &Lft->gas)) *Lft = *cL0;
+        if (gas_update_thermo_from_rhop(s, &Rght->gas)) *Rght = *cR0;
+    } else if (ti == EB200_INTERP_RHOT) {
+        interp_l2r2_scalar(s, &w, cL1->gas.T, cL0->gas.T, cR0->gas.T, cR1->gas.T, &Lft->gas.T, &Rght->gas.T, beta);
+        if (gas_update_thermo_from_rhoT(s, &Lft->gas)) *Lft = *cL0;
+        if (gas_update_thermo_from_rhoT(s, &Rght->gas)) *Rght = *cR0;
+    } else {
+        interp_l2r2_scalar(s, &w, cL1->gas.u, cL0->gas.u, cR0->gas.u, cR1->gas.u, &Lft->gas.u, &Rght->gas.u, beta);
+        /* mixin(codeForThermoUpdateBoth("rhou")) :45-74: on exception copy the whole cell state */
+        if (gas_update_thermo_from_rhou(s, &Lft->gas)) *Lft = *cL0;
+        if (gas_update_thermo_from_rhou(s, &Rght->gas)) *Rght = *cR0;
+    }
+back_to_global:
     if (s->cfg.interpolate_in_local_frame) {          /* :979-987 */
         to_global(&Lft->vx, &Lft->vy, &Lft->vz, g); to_global(&Rght->vx, &Rght->vy, &Rght->vz, g);
         to_global(&cL1->vx, &cL1->vy, &cL1->vz, g); to_global(&cL0->vx, &cL0->vy, &cL0->vz, g);

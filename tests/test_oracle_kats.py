@@ -240,3 +240,15 @@ def test_fixed_pressure_outflow(oracle, with_T):
             assert np.all(np.abs(T - P[3][inner]) < 0.05 * P[3][inner])
         assert np.array_equal(P[0][ghost], 2.0e4 / (T * gm.Rgas)) and np.array_equal(P[1][ghost], gm.Cv * T)
     sim.close()
+
+
+@pytest.mark.parametrize("ti", ["pt", "rhop", "rhot"])
+def test_cone20_with_other_thermo_interpolators(oracle, ti):
+    """The choice of reconstructed thermodynamic pair changes the face states only within the scheme's accuracy:
+    the same step count (+-3) and free-stream values as with rhou."""
+    cfg, gm, blocks = cases.cone20(thermo_interpolator=ti)
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    assert abs(sim.run() - 833) < 12
+    v = probe(sim, blocks, 0.4, 0.5)
+    assert abs(v["a"] - 666.0) < 1.0 and abs(v["p"] - 95.84e3) < 500.0 and abs(v["T"] - 1103.0) < 1.0
+    sim.close()

@@ -72,6 +72,20 @@ def test_fixed_pressure_outflow_thermally_perfect(oracle, product):
     assert max_rel_diff(runs[1], runs[0]) < REL_TOL_U and max_rel_diff(runs[2], runs[0]) < REL_TOL_U
 
 
+@pytest.mark.parametrize("ti", ["pt", "rhop", "rhot"])
+def test_thermo_interpolators(oracle, product, ti):
+    """config.thermo_interpolator other than the default rhou (onedinterp.d:771-978): another pair of thermodynamic
+    variables is reconstructed and another update_thermo_from_* closes the state (generic kernel)."""
+    _compare(cases.cone20, oracle, product, 80, flux_calculator="ausmdv", thermo_interpolator=ti)
+    _compare(cases.box3d, oracle, product, 6, n=12, nb=2, sheared=True, thermo_interpolator=ti)
+    _compare(cases.sod, oracle, product, 40, dims=3, ncells=48, nj=4, nk=3, nblocks=2, thermo_interpolator=ti)
+
+
+def test_thermo_interpolators_thermally_perfect(oracle, product):
+    for ti in ("pt", "rhop", "rhot"):
+        _compare(cases.tpg_box3d, oracle, product, 3, expect_bitwise=False, n=12, nb=2, thermo_interpolator=ti)
+
+
 def test_probe_histories(oracle, product):
     """History cells (setHistoryPoint) sampled every dt_history: the FMA-free build gives the oracle's numbers,
     the throughput build is within 1e-9 (north_star: 'dt and probe histories within 1e-9')."""
