@@ -105,6 +105,7 @@ SIGNATURES = {
     "block_create": (C.c_int, [C.c_int] * 6),
     "block_set_geometry": (C.c_int, [C.c_int, C.c_int, DP, DP, DP, DP, DP, DPP]),
     "block_set_bc": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, DP, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "block_set_face_map": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_longlong]),
     "commit": (C.c_int, [C.c_int]),
     "set_exchange": (C.c_int, [C.c_int, EXCHANGE_FN, C.c_void_p]),
     "upload_flow": (C.c_int, [C.c_int, C.c_int, DPP, C.c_int]),

@@ -42,6 +42,7 @@ void set_err(const char* fmt, ...)
 
 struct BC {
     int kind = EB200_BC_WALL_WITH_SLIP, other_blk = -1, other_face = -1, orientation = 0;
+    std::vector<int> map;          // eb200_block_set_face_map: (i, j, k) of the source cell of every ghost cell
     std::vector<double> params;
     int param_index = -1;
 };
@@ -454,8 +455,9 @@ bool face_pushes(const Sim* s, const Block* b, int f, const Block** other)
     const Block* ot = nullptr;
     for (auto& q : s->blocks) if (q->id == bc.other_blk) ot = q.get();
     if (!ot || !ot->local || !b->local || ot == b) return false;
-    if (bc.other_face != (f ^ 1)) return false;
+    if (bc.other_face != (f ^ 1) || !bc.map.empty()) return false;
     const BC& back = ot->bc[f ^ 1];
+    if (!back.map.empty()) return false;
     if (back.kind != EB200_BC_EXCHANGE_FULL_FACE || back.other_blk != b->id || back.other_face != f) return false;
     if (ot->nic != b->nic || ot->njc != b->njc || ot->nkc != b->nkc) return false;
     if (b->nic < 4 || b->njc < 4 || (s->threeD && b->nkc < 4)) return false;
@@ -743,6 +745,29 @@ int eb200_block_set_bc(int sim, int blk_id, int face, int kind, const double* pa
     return 0;
 }
 
+int eb200_block_set_face_map(int sim, int blk_id, int face, const int* src_ijk, long long n)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Block* b = get_blk(s, blk_id); if (!b) return -1;
+    if (s->committed) { set_err("set_face_map after commit"); return -1; }
+    if (face < 0 || face >= s->nfaces) { set_err("bad face %d", face); return -1; }
+    BC& bc = b->bc[face];
+    if (bc.kind != EB200_BC_EXCHANGE_FULL_FACE) { set_err("block %d face %d: a cell map needs a full-face exchange", blk_id, face); return -1; }
+    Block* ot = get_blk(s, bc.other_blk); if (!ot) return -1;
+    const int d = face / 2;
+    const int nn[3] = { b->nic, b->njc, b->nkc };
+    const long long want = (long long)EB_NG * nn[(d + 1) % 3] * nn[(d + 2) % 3];
+    if (n != want || !src_ijk) { set_err("block %d face %d: the cell map needs %lld entries", blk_id, face, want); return -1; }
+    for (long long m = 0; m < n; ++m) {
+        const int i = src_ijk[3 * m], j = src_ijk[3 * m + 1], k = src_ijk[3 * m + 2];
+        if (i < 0 || i >= ot->nic || j < 0 || j >= ot->njc || k < 0 || k >= ot->nkc) {
+            set_err("block %d face %d: map entry %lld (%d,%d,%d) is outside block %d", blk_id, face, m, i, j, k, ot->id); return -1;
+        }
+    }
+    bc.map.assign(src_ijk, src_ijk + 3 * n);
+    return 0;
+}
+
 int eb200_set_exchange(int sim, eb200_exchange_fn fn, void* user)
 {
     Sim* s = get_sim(sim); if (!s) return -1;
@@ -883,18 +908,31 @@ int eb200_commit(int sim)
                 int err = 0;
                 // the neighbour's flux kernel writes these ghost cells itself when it pushes through its face
                 std::vector<EbCopyItem>& copies = (ot->local && face_pushes(s, ot, bc.other_face, nullptr)) ? copy_pushed : copy;
+                long long m = 0;
                 for_face_ghosts(s, b, f, [&](int t1, int t2, int layer, long long, long long ghost, long long, long long) {
                     int ijk[3];
-                    if (full_face_source(s, f, ot, bc.other_face, t1, t2, layer, ijk)) { err = 1; return; }
+                    if (!bc.map.empty()) { ijk[0] = bc.map[3 * m]; ijk[1] = bc.map[3 * m + 1]; ijk[2] = bc.map[3 * m + 2]; }
+                    else if (full_face_source(s, f, ot, bc.other_face, t1, t2, layer, ijk)) { err = 1; return; }
+                    ++m;
                     if (ot->local) copies.push_back({ (int)(b->cell0 + ghost), (int)(ot->cell0 + ot->cidx(ijk[0], ijk[1], ijk[2])) });
                     else recv_keyed.push_back({ ghost, (int)(b->cell0 + ghost) });
                 });
                 if (err) return -1;
                 if (!ot->local) {
                     // what the neighbour needs from me: its ghost cells behind (ot, other_face), in ITS order
+                    // (the neighbour's own boundary condition is only declared here when it carries a cell map)
+                    const BC& obc = ot->bc[bc.other_face];
+                    const bool omap = obc.kind == EB200_BC_EXCHANGE_FULL_FACE && obc.other_blk == b->id && !obc.map.empty();
+                    if (!bc.map.empty() && !omap) {
+                        set_err("block %d face %d has a cell map but its neighbour, block %d face %d, was declared without one", b->id, f, ot->id, bc.other_face);
+                        return -1;
+                    }
+                    long long mo = 0;
                     for_face_ghosts(s, ot, bc.other_face, [&](int t1, int t2, int layer, long long, long long ghost, long long, long long) {
                         int ijk[3];
-                        if (full_face_source(s, bc.other_face, b, f, t1, t2, layer, ijk)) { err = 1; return; }
+                        if (omap) { ijk[0] = obc.map[3 * mo]; ijk[1] = obc.map[3 * mo + 1]; ijk[2] = obc.map[3 * mo + 2]; }
+                        else if (full_face_source(s, bc.other_face, b, f, t1, t2, layer, ijk)) { err = 1; return; }
+                        ++mo;
                         send_keyed.push_back({ ghost, (int)(b->cell0 + b->cidx(ijk[0], ijk[1], ijk[2])) });
                     });
                     if (err) return -1;

@@ -195,10 +195,13 @@ class OutFlowBC_FixedPT(BoundaryCondition):
 class ExchangeBC_FullFace(BoundaryCondition):
     kind = _abi.BC_EXCHANGE_FULL_FACE
 
-    def __init__(self, otherBlock, otherFace, orientation=0):
+    def __init__(self, otherBlock, otherFace, orientation=0, cell_map=None):
         self.otherBlock = otherBlock          # block id
         self.otherFace = otherFace if isinstance(otherFace, int) else _abi.FACE_NAMES.index(otherFace)
         self.orientation = orientation
+        # int array (n2, n1, 2 layers, 3): source cell (i, j, k) in the other block of every ghost cell behind this
+        # face, for connections other than opposite faces of aligned blocks (face_cell_map below); None: aligned
+        self.cell_map = cell_map
 
 
 # ---------------------------------------------------------------------------
@@ -244,6 +247,75 @@ class FluidBlock:
         return sig
 
 
+def _face_corners(grid, face):
+    """Corner vertices of a 3D block face as P[alpha][beta], alpha/beta = low/high end of the in-face
+    directions d1 = (d+1)%3 and d2 = (d+2)%3 (d = face // 2), and the cell counts (n1, n2) along them."""
+    X, Y, Z = (np.asarray(a) for a in grid)
+    nv = (X.shape[2], X.shape[1], X.shape[0])           # vertices along i, j, k
+    d, hi = face // 2, face & 1
+    d1, d2 = (d + 1) % 3, (d + 2) % 3
+    P = [[None, None], [None, None]]
+    for al in (0, 1):
+        for be in (0, 1):
+            idx = [0, 0, 0]
+            idx[d] = nv[d] - 1 if hi else 0
+            idx[d1] = al * (nv[d1] - 1)
+            idx[d2] = be * (nv[d2] - 1)
+            i, j, k = idx
+            P[al][be] = (float(X[k, j, i]), float(Y[k, j, i]), float(Z[k, j, i]))
+    return P, (nv[d1] - 1, nv[d2] - 1)
+
+
+def face_cell_map(grid_a, face_a, grid_b, face_b, tol=1.0e-6):
+    """If face_a of block A and face_b of block B coincide (their four corners match in some order), the
+    source cell in B of every ghost cell behind face_a of A: int array of shape (n2, n1, NG, 3) with (i, j, k),
+    indexed by the cell indices along A's in-face directions and the ghost layer.  None if they do not coincide.
+    Replaces the case tables of full_face_copy.d:141-1380 by matching corners, which covers every pair of
+    faces and all four rotations."""
+    PA, (na1, na2) = _face_corners(grid_a, face_a)
+    PB, (nb1, nb2) = _face_corners(grid_b, face_b)
+
+    def find(p):
+        for ga in (0, 1):
+            for de in (0, 1):
+                if _close(p, PB[ga][de], tol):
+                    return ga, de
+        return None
+    c00, c10, c01, c11 = find(PA[0][0]), find(PA[1][0]), find(PA[0][1]), find(PA[1][1])
+    if None in (c00, c10, c01, c11) or len({c00, c10, c01, c11}) != 4:
+        return None
+    a_runs_along_first = c10[0] != c00[0]           # does A's first in-face direction run along B's first?
+    if a_runs_along_first:
+        if c10[1] != c00[1] or c01[0] != c00[0]:
+            return None
+        if (na1, na2) != (nb1, nb2):
+            return None
+    else:
+        if c10[0] != c00[0] or c01[1] != c00[1]:
+            return None
+        if (na1, na2) != (nb2, nb1):
+            return None
+    XB = np.asarray(grid_b[0])
+    nB = (XB.shape[2] - 1, XB.shape[1] - 1, XB.shape[0] - 1)
+    e, ehi = face_b // 2, face_b & 1
+    e1, e2 = (e + 1) % 3, (e + 2) % 3
+    out = np.zeros((na2, na1, NG, 3), dtype=np.int32)
+    a1 = np.arange(na1)[None, :]
+    a2 = np.arange(na2)[:, None]
+    if a_runs_along_first:
+        c = (nb1 - 1 - a1) if c00[0] else a1
+        dd = (nb2 - 1 - a2) if c00[1] else a2
+    else:
+        dd = (nb2 - 1 - a1) if c00[1] else a1
+        c = (nb1 - 1 - a2) if c00[0] else a2
+    c, dd = np.broadcast_to(c, (na2, na1)), np.broadcast_to(dd, (na2, na1))
+    for layer in range(NG):
+        out[:, :, layer, e] = (nB[e] - 1 - layer) if ehi else layer
+        out[:, :, layer, e1] = c
+        out[:, :, layer, e2] = dd
+    return out
+
+
 def _close(p, q, tol):
     return all(abs(a - b) <= tol for a, b in zip(p, q))
 
@@ -273,6 +345,14 @@ def identify_block_connections(blocks, dims, tol=1.0e-6):
                         ok = rev if is_rev else same
                     else:
                         ok = (fa ^ 1) == fb and all(_close(p, q, tol) for p, q in zip(pa, pb))
+                        if not ok and all(any(_close(p, q, tol) for q in pb) for p in pa):
+                            # the faces coincide some other way round: connect them through explicit cell maps
+                            mab = face_cell_map(A.grid, fa, B.grid, fb, tol)
+                            mba = face_cell_map(B.grid, fb, A.grid, fa, tol)
+                            if mab is not None and mba is not None:
+                                A.bcList[na] = ExchangeBC_FullFace(B.id, fb, 0, cell_map=mab)
+                                B.bcList[nb] = ExchangeBC_FullFace(A.id, fa, 0, cell_map=mba)
+                            continue
                     if ok:
                         A.bcList[na] = ExchangeBC_FullFace(B.id, fb, 0)
                         B.bcList[nb] = ExchangeBC_FullFace(A.id, fa, 0)
@@ -407,6 +487,24 @@ class Simulation:
                                                bc.orientation), "block_set_bc")
                 else:
                     lib.check(lib.block_set_bc(h, b.id, f, bc.kind, pa, len(p), -1, -1, 0), "block_set_bc")
+        # explicit cell maps of connections that are not between opposite faces of aligned blocks: every process
+        # declares them for its own blocks and for the faces of other processes' blocks that meet its own
+        def declare_map(blk, f, bc):
+            m = np.ascontiguousarray(bc.cell_map, dtype=np.int32)
+            lib.check(lib.block_set_face_map(h, blk.id, f, m.ctypes.data_as(C.POINTER(C.c_int)), m.size // 3), "block_set_face_map")
+        local_ids = {b.id for b in local}
+        for b in self.blocks:
+            if b.id not in needed:
+                continue
+            for f in range(nfaces):
+                bc = b.bcList.get(_abi.FACE_NAMES[f])
+                if not isinstance(bc, ExchangeBC_FullFace) or bc.cell_map is None:
+                    continue
+                if b.id in local_ids:
+                    declare_map(b, f, bc)
+                elif bc.otherBlock in local_ids:
+                    lib.check(lib.block_set_bc(h, b.id, f, bc.kind, (C.c_double * 1)(), 0, bc.otherBlock, bc.otherFace, 0), "block_set_bc")
+                    declare_map(b, f, bc)
         if exchange is not None:
             self._exchange_cb = _abi.EXCHANGE_FN(exchange)
             lib.check(lib.set_exchange(h, self._exchange_cb, None), "set_exchange")
@@ -434,6 +532,22 @@ class Simulation:
         d, hi = face // 2, face & 1
         n = (g.nic, g.njc, g.nkc)
         on = (og.nic, og.njc, og.nkc)
+        bc = b.bcList.get(_abi.FACE_NAMES[face])
+        if getattr(bc, "cell_map", None) is not None:
+            # only the length along the face normal of a ghost cell is ever used (stencils are one-dimensional):
+            # it is the neighbour's cell length along ITS face normal
+            e = other_face // 2
+            m = bc.cell_map
+            d1, d2 = (d + 1) % 3, (d + 2) % 3
+            off = (NG, NG, g.kg)
+            a1, a2 = np.meshgrid(np.arange(n[d1]), np.arange(n[d2]))
+            for layer in range(NG):
+                idx = [None, None, None]
+                idx[d] = np.full(a1.shape, (n[d] + layer if hi else -1 - layer) + off[d])
+                idx[d1], idx[d2] = a1 + off[d1], a2 + off[d2]
+                src = (m[:, :, layer, 2] + og.kg, m[:, :, layer, 1] + NG, m[:, :, layer, 0] + NG)
+                g.len[d][idx[2], idx[1], idx[0]] = og.len[e][src]
+            return
         for layer in range(NG):
             if self.dims == 3:
                 # aligned, orientation 0: in-face indices carry over unchanged

@@ -246,6 +246,16 @@ int eb200_block_set_bc(int sim, int blk_id, int face, int kind,
                        const double* params, int nparams,
                        int other_blk, int other_face, int orientation);
 
+/* Explicit cell mapping for an EB200_BC_EXCHANGE_FULL_FACE face (call after eb200_block_set_bc): the
+ * faces of two 3D blocks can meet in any of 6 x 6 x 4 ways (full_face_copy.d:141-1380 spells out every
+ * case; ExchangeBC_MappedCell locates source cells by position, mapped_cell_copy.d).  Here the caller
+ * names the source cell of every ghost cell: ghost cell m behind `face`, m = (a2 * n1 + a1) * 2 + layer
+ * with a1, a2 the cell indices along block directions (d+1)%3 and (d+2)%3 (d = face / 2, n1 cells along
+ * the first) and layer 0 next to the face, takes the FlowState of interior cell
+ * (src_ijk[3m], src_ijk[3m+1], src_ijk[3m+2]) of block other_blk.  n = number of ghost cells.
+ * Every process declares the maps of all blocks, its own and the others'. */
+int eb200_block_set_face_map(int sim, int blk_id, int face, const int* src_ijk, long long n);
+
 /* Finish set-up: builds device tables (ghost maps, exchange lists).  Must be
  * called once after all blocks, geometry and BCs are in. */
 int eb200_commit(int sim);

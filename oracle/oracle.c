@@ -63,6 +63,7 @@ typedef struct {
 
 typedef struct {
     int kind, other_blk, other_face, orientation;
+    int* map;                /* orc_block_set_face_map: (i,j,k) of the source cell of every ghost cell, or NULL */
     FS fstate;               /* for FlowStateCopy */
     double p_outside, T_outside;   /* FixedP / FixedPT */
 } BC;
@@ -1200,6 +1201,15 @@ static void apply_pre_recon_bcs(const Sim* s, Blk* b)
  * (east<->west, north<->south, top<->bottom). */
 static int map_full_face_source(const Sim* s, const Blk* me, int face, const Blk* ot, int oface, int a1, int a2, int layer, long* src)
 {
+    if (me->bc[face].map) {        /* explicit map: entry (a2 * n1 + a1) * NG + layer, a1/a2 along directions (d+1)%3, (d+2)%3 */
+        int n[3] = { me->nic, me->njc, me->nkc };
+        int d = face / 2, d1 = (d + 1) % 3;
+        int e1 = s->threeD ? a1 : ((d == 0) ? a1 : 0);      /* 2D: south/north faces have a1 = 0 (the k direction) and a2 = i */
+        long m = ((long)a2 * n[d1] + e1) * NG + layer;
+        const int* q = me->bc[face].map + 3 * m;
+        *src = cidx(ot, q[0] + NG, q[1] + NG, q[2] + ot->kg);
+        return 0;
+    }
     int oi = 0, oj = 0, ok = 0;
     if (!s->threeD) {
         /* index along this boundary: east/west -> j, north/south -> i (full_face_copy.d:704-870) */
@@ -1793,6 +1803,20 @@ int orc_block_set_bc(int sim, int blk_id, int face, int kind, const double* para
         bc->p_outside = params[0]; bc->T_outside = (need == 2) ? params[1] : 0.0;
     }
     if (kind == EB200_BC_EXCHANGE_FULL_FACE && s->threeD && orientation != 0) { set_err("only orientation 0 supported in 3D"); return -1; }
+    return 0;
+}
+
+int orc_block_set_face_map(int sim, int blk_id, int face, const int* src_ijk, long long n)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Blk* b = get_blk(s, blk_id); if (!b) return -1;
+    if (face < 0 || face >= (s->threeD ? 6 : 4)) { set_err("bad face %d", face); return -1; }
+    BC* bc = &b->bc[face];
+    if (bc->kind != EB200_BC_EXCHANGE_FULL_FACE) { set_err("a cell map needs a full-face exchange"); return -1; }
+    if (n != face_ghost_count(s, b, face) || !src_ijk) { set_err("the cell map needs %ld entries", face_ghost_count(s, b, face)); return -1; }
+    free(bc->map);
+    bc->map = (int*)malloc(sizeof(int) * 3 * (size_t)n);
+    memcpy(bc->map, src_ijk, sizeof(int) * 3 * (size_t)n);
     return 0;
 }
 

@@ -24,7 +24,16 @@ def _worker():
     rank, world = dist.get_rank(), dist.get_world_size()
     lib = _abi.load_library(build_oracle(), "orc_")
     ok = True
+    def rotated_pair(**kw):
+        # two 3D blocks whose common face is east of the one and bottom of the other, rotated: explicit cell maps
+        from test_connections3d import make_case, rotations
+        cfg, blocks = make_case(cases.ideal_air(), ((0, 1, 2), (1, 1, 1)), rotations()[17])
+        assert blocks[0].bcList["east"].cell_map is not None
+        cfg.max_step = 100
+        return cfg, cases.ideal_air(), blocks
+
     for name, factory, kw, nsteps in (("box3d", cases.box3d, dict(n=16, nb=2), 12),
+                                      ("rotated-pair", rotated_pair, dict(), 6),
                                       ("ffs", cases.ffs, dict(nx=60, ny=20), 25),
                                       ("cone20", cases.cone20, dict(), 30),
                                       ("cone20-adaptive", cases.cone20, dict(flux_calculator="adaptive_hanel_ausmdv"), 60)):
@@ -72,6 +81,7 @@ def test_two_ranks_match_one_rank_gloo():
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
     assert "box3d: 2 ranks == 1 rank: True" in r.stdout
+    assert "rotated-pair: 2 ranks == 1 rank: True" in r.stdout
     assert "cone20: 2 ranks == 1 rank: True" in r.stdout
     assert "cone20-adaptive: 2 ranks == 1 rank: True" in r.stdout
 

@@ -345,3 +345,22 @@ def test_run_stage_command_line(tmp_path, product):
     assert int(line.split()[1]) == 80
     f = io.read_flow(io.job_file(tmp_path, "cone20", "flow", 1, 1))
     assert np.array_equal(f["data"]["rho"], rho)
+
+
+@pytest.mark.parametrize("n", [1, 6, 11, 17, 22])
+def test_rotated_block_connections_3d(oracle, product, n):
+    """3D blocks that meet through other faces than opposite ones of aligned blocks (explicit cell maps, the
+    reference's 3D/connection-test): same bits as the oracle, which itself reproduces the aligned pair."""
+    from test_connections3d import make_case, rotations
+    rot = rotations()
+    gm = cases.ideal_air()
+    sols = []
+    for lib, strict in ((oracle, True), (product, True), (product, False)):
+        cfg, blocks = make_case(gm, rot[(7 * n) % 24], rot[n])
+        cfg.strict_fp = strict
+        sim = Simulation(cfg, gm, blocks, lib=lib)
+        sim.run()
+        sols.append({b.id: [sim.interior(b.id, a).copy() for a in sim.download_conserved(b.id)] for b in blocks})
+        sim.close()
+    assert identical(sols[1], sols[0])
+    assert max_rel_diff(sols[2], sols[0]) < REL_TOL_U
