@@ -181,6 +181,8 @@ def write_job(job_dir, job, cfg, gm, gas_model_file, blocks, sim, history_points
     os.makedirs(os.path.join(job_dir, "grid", "t0000"), exist_ok=True)
     for b in blocks:
         grid = b.grid
+        if not isinstance(grid, (tuple, list)):
+            raise ValueError(f"block {b.id} was built from metrics only (no vertex grid): it cannot be written as a job")
         io.write_grid(io.job_file(job_dir, job, "grid", b.id, 0), *grid, label=getattr(b, "label", "") or "", dimensions=dims)
     io.write_solution_files(job_dir, job, sim, 0)
 
