@@ -283,7 +283,7 @@ def oracle_library():
     return _abi.load_library(so, "orc_")
 
 
-def run_cpu_sample(args, target_seconds, steps=None):
+def run_cpu_sample(args, target_seconds, steps=None, warmup=1):
     """The CPU oracle (restated reference, one block per OpenMP thread like the reference's
     parallel foreach / one block per MPI rank) on a bounded sample of the 3D workload."""
     from gdtk_b200 import Simulation, cases
@@ -296,8 +296,8 @@ def run_cpu_sample(args, target_seconds, steps=None):
     dt = cfl_dt(sim)
     ncells = n ** 3
     t0 = time.perf_counter()
-    sim.run_fixed(1, dt)
-    t1 = time.perf_counter() - t0
+    sim.run_fixed(max(1, warmup), dt)
+    t1 = (time.perf_counter() - t0) / max(1, warmup)
     if steps is None:
         steps = int(max(1, min(50, target_seconds / max(t1, 1e-3))))
     t0 = time.perf_counter()
@@ -344,10 +344,10 @@ def main():
         # oracle port (restated reference) on all host cores.  Rank 0 only.
         if rank != 0:
             return
-        cb = run_cpu_sample(args, 0.0, steps=max(1, args.steps))
+        cb = run_cpu_sample(args, 0.0, steps=max(1, args.steps), warmup=max(1, args.warmup))
         line = {
             "impl": "reference", "metric": "cell-updates/s (FP64)", "value": cb["value"], "unit": "cell-updates/s",
-            "n_gpus": args.gpus, "steps": cb["steps"], "warmup": 1, "ms_per_step": cb["ms_per_step"],
+            "n_gpus": args.gpus, "steps": cb["steps"], "warmup": max(1, args.warmup), "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "synthetic 3D ideal-air box (bounded sample of the 512^3 job): " + cb["sample"]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
