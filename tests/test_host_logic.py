@@ -146,3 +146,22 @@ def test_retry_gives_up_after_max_attempts():
     with pytest.raises(RuntimeError, match="after 3 attempts"):
         sim.gasdynamic_step()
     assert len(stub.calls) == 3
+
+
+def test_config_options_added_for_the_wider_path():
+    """Names and values are Eilmer's: flux calculators incl. "adaptive" (= adaptive_efm_ausmdv), the four
+    thermo interpolators, and the boundary conditions with parameters."""
+    from gdtk_b200 import _abi, cases
+    from gdtk_b200.sim import Config, OutFlowBC_FixedP, OutFlowBC_FixedPT
+    gm = cases.ideal_air()
+    assert Config(flux_calculator="adaptive").to_struct(gm).flux_calculator == _abi.FLUX_CALCULATORS["adaptive_efm_ausmdv"] == 10
+    assert Config(flux_calculator="efm").to_struct(gm).flux_calculator == 9
+    for name, code in (("rhou", 0), ("pt", 1), ("rhop", 2), ("rhot", 3)):
+        assert Config(flux_calculator="ausmdv", thermo_interpolator=name).to_struct(gm).thermo_interpolator == code
+    try:
+        Config(flux_calculator="ausmdv", thermo_interpolator="rhoe").to_struct(gm)
+        assert False
+    except ValueError:
+        pass
+    assert OutFlowBC_FixedP(2.0e4).params() == [2.0e4] and OutFlowBC_FixedP.kind == 5
+    assert OutFlowBC_FixedPT(2.0e4, 300).params() == [2.0e4, 300.0] and OutFlowBC_FixedPT.kind == 6
