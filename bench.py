@@ -121,6 +121,7 @@ def build_case(args, workload):
                 f"{'k-lines sheared by 10 degrees (general-metric path)' if args.sheared else 'uniform Cartesian'}, "
                 f"l2r2+van Albada, {args.flux}, pc")
         balg = 280.0
+    cfg.force_generic_kernel = {"auto": 0, "generic": 1, "v2": 2}[args.kernel]
     return cfg, gm, blocks, name, balg
 
 
@@ -326,6 +327,9 @@ def main():
     ap.add_argument("--sheared", action="store_true", help="box3d on a sheared grid: every block takes the general-metric path")
     ap.add_argument("--dt-scale", type=float, default=1.0,
                     help="fraction of the CFL time step to run at (ausm_plus_up is not stable at the full CFL step on the noisy box)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "v2"],
+                    help="A/B testing: force the generic fused kernel, or the face-centred tuned kernel (v2) where the "
+                         "cell-centred one (v3) would run")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-n", type=int, default=128)
     ap.add_argument("--cpu-nb", type=int, default=4)

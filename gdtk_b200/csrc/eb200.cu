@@ -822,7 +822,7 @@ int eb200_commit(int sim)
         (b->cartesian ? any_cart : any_general) = true;
         cells_total += (long long)b->nic * b->njc * b->nkc;
     }
-    s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (s->cfg.reserved_i[1] ? 4 : 0);
+    s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (s->cfg.reserved_i[1] == 1 ? 4 : 0) | (s->cfg.reserved_i[1] == 2 ? 8 : 0);
     {
         // k-chunking (3D): a CTA marches over `chunk` planes of its tile.  Aim at >= 20 waves of CTAs
         // (148 SMs x 2 resident CTAs) so that the last, partly filled wave costs little; every chunk

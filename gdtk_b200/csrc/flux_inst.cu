@@ -11,6 +11,7 @@
 #endif
 #include "flux_kernel.cuh"
 #include "flux_kernel_v2.cuh"
+#include "flux_kernel_v3.cuh"
 
 #define EB_CAT2(a, b) a##b
 #define EB_CAT(a, b) EB_CAT2(a, b)
@@ -24,8 +25,14 @@ void EB_CAT(launch_flux_update_k, EB_FLUX)(const EbParams& P, int gas_model, con
     // default configuration (ideal gas, second-order reconstruction, limiter on)
     const bool tuned = (tile_y >= 0) && gas_model == EB200_GAS_IDEAL && P.interpolation_order == 2 && P.apply_limiter != 0 &&
                        P.thermo_interp == EB200_INTERP_RHOU;
-    if (tuned) launch_flux_update_v2_impl<EB_FLUX>(P, gas, desc, nblocks, ncta, A, S, which, st);
-    else launch_flux_update_impl<EB_FLUX>(P, gas_model, gas, desc, nblocks, ncta, A, S, tile_y, which, st);
+    if (tuned) {
+        // uniform-Cartesian blocks whose tiles can be staged by TMA: the cell-centred kernel (tile_y == 1 keeps v2, A/B testing)
+        if ((which & 1) && tile_y == 0 && S.tmaps != nullptr) {
+            launch_flux_update_v3_impl<EB_FLUX>(P, gas, desc, nblocks, ncta, A, S, st);
+            which &= ~1;
+        }
+        if (which) launch_flux_update_v2_impl<EB_FLUX>(P, gas, desc, nblocks, ncta, A, S, which, st);
+    } else launch_flux_update_impl<EB_FLUX>(P, gas_model, gas, desc, nblocks, ncta, A, S, tile_y, which, st);
 }
 void EB_CAT(launch_face_debug_k, EB_FLUX)(const EbParams& P, int gas_model, const EbGas* gas, const EbArena& A,
                                          const double* prim, int nfaces, double* Fout, int* ok_out, cudaStream_t st)

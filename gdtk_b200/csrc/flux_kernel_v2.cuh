@@ -117,15 +117,15 @@ __device__ __forceinline__ void set_normal(int d, double fn, double* F)
     if (DIM == 3) F[Lay::iZMom] = (d == 2) ? fn : F[Lay::iZMom];
 }
 
+// pLrL, pRrR: p/rho of the two states, supplied by the caller (pL * rcp(rL), or (gamma-1) * u for the ideal gas)
 template <int DIM, int FLUX>
-__device__ __forceinline__ void flux_components(const Prim<1>& L, const Prim<1>& R, int d, bool entropy_fix, double M_inf, double* F)
+__device__ __forceinline__ void flux_components_pr(const Prim<1>& L, const Prim<1>& R, int d, bool entropy_fix, double M_inf,
+                                                   double pLrL, double pRrR, double* F)
 {
     typedef Layout<DIM, 1> Lay;
     const double rL = L.rho, pL = L.p, rR = R.rho, pR = R.p, aL = L.a, aR = R.a;
     const double uL = (DIM == 3) ? pick3(d, L.vx, L.vy, L.vz) : ((d == 0) ? L.vx : L.vy);
     const double uR = (DIM == 3) ? pick3(d, R.vx, R.vy, R.vz) : ((d == 0) ? R.vx : R.vy);
-    const double rrL = eb_rcp(rL), rrR = eb_rcp(rR);
-    const double pLrL = pL * rrL, pRrR = pR * rrR;
     const double keL = 0.5 * (L.vx * L.vx + L.vy * L.vy + ((DIM == 3) ? L.vz * L.vz : 0.0));
     const double keR = 0.5 * (R.vx * R.vx + R.vy * R.vy + ((DIM == 3) ? R.vz * R.vz : 0.0));
     const double HL = L.u + pLrL + keL, HR = R.u + pRrR + keR;
@@ -249,6 +249,12 @@ __device__ __forceinline__ void flux_components(const Prim<1>& L, const Prim<1>&
         set_normal<DIM>(d, ru_half * (fromL ? uL : uR) + p_half, F);
         F[Lay::iEnergy] = ru_half * (fromL ? HL : HR);
     }
+}
+
+template <int DIM, int FLUX>
+__device__ __forceinline__ void flux_components(const Prim<1>& L, const Prim<1>& R, int d, bool entropy_fix, double M_inf, double* F)
+{
+    flux_components_pr<DIM, FLUX>(L, R, d, entropy_fix, M_inf, L.p * eb_rcp(L.rho), R.p * eb_rcp(R.rho), F);
 }
 #endif
 

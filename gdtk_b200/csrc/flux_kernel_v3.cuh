@@ -1,0 +1,574 @@
+// flux_kernel_v3.cuh -- fused per-stage kernel for uniform-Cartesian blocks (ideal gas, l2r2 + van Albada):
+// the configuration BASELINE.json's metric is quoted on.
+//
+// What is new against flux_kernel_v2.cuh:
+//   * CELL-CENTRED reconstruction.  The van Albada limiter of a cell in a direction is ONE number
+//     (onedinterp.d:357-384: sL of the face on the plus side and sR of the face on the minus side are built from
+//     the same two slopes), so a thread evaluates it once per cell, direction and variable and produces both the
+//     state at its minus face (the face's R side) and at its plus face (the L side of the next face).  The plus
+//     state travels to the neighbour: by warp shuffle along i, through shared memory along j, in registers
+//     along k.  A face needs 10 limiter evaluations less than in the face-centred form, and one reciprocal serves
+//     two reconstructed values.
+//   * the three directions are compile-time copies: no address selects, no job loop.
+//   * a HELPER WARP (warp TY of the CTA) owns everything that belongs to the tile's halo: the plus states of the
+//     cells west / south of the tile, the faces on the tile's east and north edge, and the TMA issue.  The TY
+//     main warps therefore run divergence-free, identical work.
+//   * planes are staged by TMA two planes ahead into a ring of four tile buffers; the k-stencil of a thread is
+//     its own column in three of them (no per-thread ring, no global loads in the loop except U0 / dUdt).
+//   * throughput build: p/rho = (gamma-1) u (no reciprocal of rho per face side), extrema clipping applied to the
+//     increment (one integer sign test and one FP64 compare per reconstructed value).
+// The FMA-free build uses the reference's expressions in the reference's order and is bit-identical to the oracle.
+#pragma once
+#include "flux_kernel_v2.cuh"
+
+#ifndef EB_V3_MIN_CTAS
+#define EB_V3_MIN_CTAS 2
+#endif
+
+namespace EB_NS {
+
+// One cell, one direction, one variable: states at the minus face (qM, the R side of that face) and at the plus
+// face (qP, the L side of that face).  qm, q0, qp: the cell below, the cell, the cell above along the direction.
+template <bool CLIP>
+__device__ __forceinline__ void recon_cell_scalar(const EbBlockDesc& D, int d, double eps, double qm, double q0, double qp,
+                                                  double& qM, double& qP)
+{
+#ifdef EB_FAST_MATH
+    // raw differences, constants of EbBlockDesc::uq (eps = epsilon_van_albada * uq[4])
+    const double* __restrict__ K = D.uq[d];
+    const double a = q0 - qm, b = qp - q0;
+    const double ab = a * b;
+    const double n = (ab + fabs(ab)) + eps;
+    const double dn = fma(a, a, fma(b, b, eps));
+    const double s = n * eb_rcp(dn);
+    double iP = s * fma(a, K[1], b * K[0]);
+    double iM = s * fma(a, K[3], b * K[2]);
+    if (CLIP) {
+        // limiters.d:43-51 on the increment: between 0 and the difference to the neighbour.  An increment that
+        // points away from the neighbour (sign bits differ: integer test) becomes 0, one that overshoots becomes
+        // the difference (only possible where epsilon dominates the limiter: |a| > 5 |b|, slopes ~ sqrt(eps))
+        iP = ((__double2hiint(iP) ^ __double2hiint(b)) < 0) ? 0.0 : ((fabs(iP) > fabs(b)) ? b : iP);
+        iM = ((__double2hiint(iM) ^ __double2hiint(a)) < 0) ? 0.0 : ((fabs(iM) > fabs(a)) ? a : iM);
+    }
+    qP = q0 + iP;
+    qM = q0 - iM;
+#else
+    const EbWeights& w = D.w[d];
+    const double delm = (q0 - qm) * w.two_over_L0L1;
+    const double delp = (qp - q0) * w.two_over_R0L0;
+    const double s = (delm * delp + fabs(delm * delp) + eps) / (delm * delm + delp * delp + eps);
+    qP = q0 + s * w.aL0 * (delp * w.two_L0_plus_L1 + delm * w.lenR0);
+    qM = q0 - s * w.aR0 * (delp * w.lenL0 + delm * w.two_R0_plus_R1);
+    if (CLIP) {
+        qP = clip_to_limits(qP, q0, qp);
+        qM = clip_to_limits(qM, qm, q0);
+    }
+#endif
+}
+
+// variables: 0 rho, 1 u, 2..4 velocity components (x, y, z)
+template <int DIM, int TY>
+__device__ __forceinline__ void load_cell5(const double* __restrict__ t, int o, double* q)
+{
+    typedef Tile<DIM, TY> T;
+    q[0] = t[T::F_RHO * T::FSZ + o]; q[1] = t[T::F_U * T::FSZ + o];
+    q[2] = t[(T::F_V + 0) * T::FSZ + o]; q[3] = t[(T::F_V + 1) * T::FSZ + o];
+    q[4] = (DIM == 3) ? t[(T::F_V + 2) * T::FSZ + o] : 0.0;
+}
+
+// positive?  (sign bit clear and not zero; the integer compare keeps the FP64 pipe out of it in the throughput build)
+__device__ __forceinline__ bool not_positive(double x)
+{
+#ifdef EB_FAST_MATH
+    return __double2hiint(x) <= 0;
+#else
+    return x <= 0.0;
+#endif
+}
+
+// Reconstruction of one cell along direction d (all variables) with the first-order fall-back of a side whose
+// reconstructed state is not physical (onedinterp.d:45-74: update_thermo_from_rhou throws -> cell values).
+// WANT: bit 0 = minus side, bit 1 = plus side (a side that is not wanted is still computed, the compiler drops it).
+template <int DIM, bool CLIP>
+__device__ __forceinline__ void recon_cell(const EbBlockDesc& D, int d, double eps, const double* qm, const double* q0,
+                                           const double* qp, double* qM, double* qP, bool& fbM, bool& fbP)
+{
+    constexpr int NV = (DIM == 3) ? 5 : 4;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) recon_cell_scalar<CLIP>(D, d, eps, qm[v], q0[v], qp[v], qM[v], qP[v]);
+    if (DIM == 2) { qM[4] = 0.0; qP[4] = 0.0; }
+    fbM = not_positive(qM[1]) || not_positive(qM[0]);
+    fbP = not_positive(qP[1]) || not_positive(qP[0]);
+    if (fbM) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) qM[v] = q0[v];
+    }
+    if (fbP) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) qP[v] = q0[v];
+    }
+}
+
+// Flux of one face along direction DIR from its two reconstructed sides; F in conserved-quantity order with the
+// momentum components in (x, y, z).  fb*: the side fell back to its cell (cL / cR = arena index of that cell).
+template <int DIM, int FLUX, int DIR>
+__device__ __forceinline__ void face_flux_v3(const EbParams& P, const EbGas* __restrict__ gas, const double* Ls, double aL, bool fbL,
+                                             long long cL, const double* Rs, double aR, bool fbR, long long cR, double alpha,
+                                             const double* __restrict__ prim, double* F)
+{
+    typedef Layout<DIM, 1> Lay;
+    Prim<1> L, R;
+    L.rho = Ls[0]; L.u = Ls[1]; L.vx = Ls[2]; L.vy = Ls[3]; L.vz = (DIM == 3) ? Ls[4] : 0.0; L.a = aL; L.massf[0] = 1.0;
+    R.rho = Rs[0]; R.u = Rs[1]; R.vx = Rs[2]; R.vy = Rs[3]; R.vz = (DIM == 3) ? Rs[4] : 0.0; R.a = aR; R.massf[0] = 1.0;
+    constexpr int SHOCK = FluxPair<FLUX>::shock, SMOOTH = FluxPair<FLUX>::smooth;
+#ifdef EB_FAST_MATH
+    (void)fbL; (void)fbR; (void)cL; (void)cR; (void)prim;
+    const double gm1 = gas->Rgas * gas->Cvinv;
+    const double pLrL = gm1 * L.u, pRrR = gm1 * R.u;
+    L.p = L.rho * pLrL; R.p = R.rho * pRrR;
+    constexpr bool has_component_form = (SHOCK < EB200_FLUX_ROE) && (SMOOTH < EB200_FLUX_ROE);
+    if constexpr (has_component_form) {
+        if (FluxPair<FLUX>::adaptive && alpha > 0.0) flux_components_pr<DIM, SHOCK>(L, R, DIR, false, P.M_inf, pLrL, pRrR, F);
+        else flux_components_pr<DIM, SMOOTH>(L, R, DIR, P.entropy_fix != 0, P.M_inf, pLrL, pRrR, F);
+        return;
+    }
+    L.T = L.u * gas->Cvinv; R.T = R.u * gas->Cvinv;
+#else
+    const long long total = P.total;
+    if (fbL) { L.p = ldg(prim + 2 * total + cL); L.T = ldg(prim + 3 * total + cL); }
+    else { L.T = L.u * gas->Cvinv; L.p = L.rho * gas->Rgas * L.T; }
+    if (fbR) { R.p = ldg(prim + 2 * total + cR); R.T = ldg(prim + 3 * total + cR); }
+    else { R.T = R.u * gas->Cvinv; R.p = R.rho * gas->Rgas * R.T; }
+#endif
+    // into the face frame: a renaming of the components (CartFrame conventions of flux_kernel_v2.cuh)
+    if (DIM == 3) {
+        const double lv[3] = { L.vx, L.vy, L.vz }, rv[3] = { R.vx, R.vy, R.vz };
+        L.vx = lv[DIR]; L.vy = lv[(DIR + 1) % 3]; L.vz = lv[(DIR + 2) % 3];
+        R.vx = rv[DIR]; R.vy = rv[(DIR + 1) % 3]; R.vz = rv[(DIR + 2) % 3];
+    } else {
+        const double lx = L.vx, ly = L.vy, rx = R.vx, ry = R.vy;
+        L.vx = (DIR == 0) ? lx : ly; L.vy = (DIR == 0) ? -ly : lx;
+        R.vx = (DIR == 0) ? rx : ry; R.vy = (DIR == 0) ? -ry : rx;
+    }
+    double Ff[Lay::NCQ];
+    flux_in_face_frame<DIM, 1, EB200_GAS_IDEAL, FLUX>(P, gas, L, R, alpha, Ff);
+    F[Lay::iMass] = Ff[Lay::iMass]; F[Lay::iEnergy] = Ff[Lay::iEnergy];
+    if (DIM == 3) {
+        F[Lay::iXMom + DIR] = Ff[Lay::iXMom];
+        F[Lay::iXMom + (DIR + 1) % 3] = Ff[Lay::iYMom];
+        F[Lay::iXMom + (DIR + 2) % 3] = Ff[Lay::iZMom];
+    } else {
+        F[Lay::iXMom] = (DIR == 0) ? Ff[Lay::iXMom] : Ff[Lay::iYMom];
+        F[Lay::iYMom] = (DIR == 0) ? -Ff[Lay::iYMom] : Ff[Lay::iXMom];
+    }
+}
+
+// BFE_SimpleOutflowFlux on a block-boundary face (bc/boundary_flux_effect.d:573-643): returns true and fills F when
+// the face with plus-side cell cf (stride st along DIR) lies on a boundary that carries this boundary condition.
+template <int DIM, int DIR>
+__device__ __forceinline__ bool outflow_override(const EbParams& P, const EbBlockDesc& D, const double* __restrict__ prim,
+                                                 int idx, int n, long long cf, long long st, double* F)
+{
+    if (!D.outflow_flux_faces) return false;
+    int bcf = -1;
+    if (idx == 0) bcf = 2 * DIR; else if (idx == n) bcf = 2 * DIR + 1;
+    if (bcf < 0 || D.bc_kind[bcf] != EB200_BC_OUTFLOW_SIMPLE_FLUX) return false;
+    const int hi = bcf & 1;
+    Prim<1> fs;
+    load_prim<1>(fs, prim, P.total, hi ? cf - st : cf);
+    if (DIM == 2) fs.vz = 0.0;
+    outflow_flux<DIM, 1>(fs, hi ? 1 : -1, D.nvec[DIR][0], D.nvec[DIR][1], D.nvec[DIR][2], F);
+    return true;
+}
+
+// a plus state leaves its thread with the fall-back flag folded into the sign of u (u > 0 for every valid state);
+// only the FMA-free build needs the flag (it reads p and T of the cell instead of recomputing them)
+__device__ __forceinline__ double fold_flag(double u, bool fb)
+{
+#ifdef EB_FAST_MATH
+    (void)fb; return u;
+#else
+    return fb ? -u : u;
+#endif
+}
+__device__ __forceinline__ bool unfold_flag(double& u)
+{
+#ifdef EB_FAST_MATH
+    (void)u; return false;
+#else
+    const bool fb = u < 0.0; u = fabs(u); return fb;
+#endif
+}
+
+template <int DIM, int TY>
+struct V3Smem {
+    typedef Tile<DIM, TY> T;
+    static constexpr int NCQ = Layout<DIM, 1>::NCQ;
+    static constexpr int NBUF = (DIM == 3) ? 4 : 1;
+    static constexpr int O_TILE = 0;
+    static constexpr int O_QPJ = O_TILE + NBUF * T::SIZE;        // [TY+1][5][32]: slot r = plus state (along j) of row r-1
+    static constexpr int O_QPIH = O_QPJ + (TY + 1) * 5 * 32;     // [5][TY]: plus state (along i) of the cell west of the tile
+    static constexpr int O_QPIX = O_QPIH + 5 * TY;               // [5][TY]: plus state of lane 31, for the east-edge face
+    static constexpr int O_FS = O_QPIX + 5 * TY;                 // [NCQ][TY+1][32]: south-face fluxes; row TY = north edge
+    static constexpr int O_FX = O_FS + NCQ * (TY + 1) * 32;      // [NCQ][TY]: east-edge fluxes
+    static constexpr int O_DESC = O_FX + NCQ * TY;
+    static constexpr size_t BYTES = sizeof(double) * O_DESC + sizeof(EbBlockDesc);
+};
+
+template <int DIM, int FLUX, bool CLIP, int TY>
+__global__ void __launch_bounds__(32 * (TY + 1), EB_V3_MIN_CTAS)
+flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc* __restrict__ descs, int nblocks,
+                      const EbArena A, const EbStageArgs S)
+{
+    typedef Layout<DIM, 1> Lay;
+    typedef Tile<DIM, TY> T;
+    typedef V3Smem<DIM, TY> SM;
+    constexpr int NCQ = Lay::NCQ;
+    constexpr int NBUF = SM::NBUF;
+    constexpr int NT = 32 * (TY + 1);
+    extern __shared__ __align__(128) double smem[];
+    double* const tile = smem + SM::O_TILE;
+    double* const qPj = smem + SM::O_QPJ;
+    double* const qPiH = smem + SM::O_QPIH;
+    double* const qPiX = smem + SM::O_QPIX;
+    double* const fS = smem + SM::O_FS;
+    double* const fX = smem + SM::O_FX;
+    EbBlockDesc& D = *reinterpret_cast<EbBlockDesc*>(smem + SM::O_DESC);
+    __shared__ int s_blk;
+    __shared__ __align__(8) unsigned long long s_bar[4];
+
+    const int lane = threadIdx.x, wy = threadIdx.y;
+    const int tid = wy * 32 + lane;
+    const bool helper = (wy == TY);
+    const long long cta = S.tile_list ? (long long)S.tile_list[blockIdx.x] : (long long)blockIdx.x;
+    if (tid == 0) {
+        int lo = 0, hi = nblocks - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (descs[mid].tile0 <= cta) lo = mid; else hi = mid - 1; }
+        s_blk = lo;
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) mbar_init(&s_bar[b], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    {
+        const int* src = reinterpret_cast<const int*>(&descs[s_blk]);
+        int* dst = reinterpret_cast<int*>(&D);
+        for (int n = tid; n < (int)(sizeof(EbBlockDesc) / sizeof(int)); n += NT) dst[n] = src[n];
+    }
+    __syncthreads();
+    if (!D.cartesian) return;
+
+    const long long t = cta - D.tile0;
+    const int ti = (int)(t % D.tiles_i);
+    const int tj = (int)((t / D.tiles_i) % D.tiles_j);
+    const int tm = (int)(t / ((long long)D.tiles_i * D.tiles_j));
+    const int i0 = ti * 32, j0 = tj * TY;
+    const int nic = D.nic, njc = D.njc, nkc = D.nkc;
+    const int NI = D.NI, NJ = D.NJ;
+    const long long sj = D.stride[1], sk = D.stride[2];
+    const long long total = P.total;
+    const int k0 = (DIM == 3) ? tm * D.chunk_m : 0;
+    const int k1 = (DIM == 3) ? min(nkc, k0 + D.chunk_m) : 1;
+    const double eps = P.eps_va;
+#ifdef EB_FAST_MATH
+    const double eps_i = eps * D.uq[0][4], eps_j = eps * D.uq[1][4], eps_k = eps * D.uq[2][4];
+#else
+    const double eps_i = eps, eps_j = eps, eps_k = eps;
+#endif
+
+    // planes are numbered m = k - (k0 - 2) (3D; the first plane a chunk touches is k0 - 2): plane m lives in
+    // tile[m & 3], its barrier completes phase (m >> 2) & 1.  2D: one plane, one buffer.
+    auto issue_plane = [&](int m) {        // one thread
+        const int b = m & (NBUF - 1);
+        double* dst = tile + b * T::SIZE;
+        const void* tmap = reinterpret_cast<const char*>(S.tmaps) + (size_t)s_blk * 128;
+        const int kp = (DIM == 3) ? (k0 - 2 + m) + D.kg : 0;
+        mbar_expect_tx(&s_bar[b], (unsigned)(T::SIZE * sizeof(double)));
+        tma_load_4d(dst, tmap, &s_bar[b], i0, j0, kp, 0);
+        tma_load_4d(dst + 2 * T::FSZ, tmap, &s_bar[b], i0, j0, kp, 4);
+        tma_load_4d(dst + 4 * T::FSZ, tmap, &s_bar[b], i0, j0, kp, 6);
+    };
+    auto wait_plane = [&](int m) { mbar_wait(&s_bar[m & (NBUF - 1)], (unsigned)((m >> 2) & 1)); };
+    auto tile_of = [&](int m) -> const double* { return tile + (m & (NBUF - 1)) * T::SIZE; };
+    const int m_last = (DIM == 3) ? (k1 + 1) - (k0 - 2) : 0;           // last plane this chunk touches
+
+    if (helper && lane == 0) {
+        if (DIM == 3) { issue_plane(0); issue_plane(1); issue_plane(2); issue_plane(3); }
+        else issue_plane(0);
+    }
+
+    // =============================== helper warp ===============================================================
+    if (helper) {
+        const int hr = lane & (TY - 1);                 // row served in the i-halo pass (lanes 0 .. 2 TY - 1)
+        const int hg = lane / TY;                       // 0: cell west of the tile (col 1), 1: cell east of it (col 34)
+        const int oX = (hr + 2) * T::COLS + ((hg == 0) ? 1 : 34);
+        const int oS = 1 * T::COLS + (lane + 2);        // south halo row
+        const int oN = (TY + 2) * T::COLS + (lane + 2); // north halo row
+        const int i = i0 + lane;
+        const bool eastE = (lane >= TY) && (lane < 2 * TY) && (i0 + 32 <= nic) && (j0 + hr < njc);
+        const bool northE = (j0 + TY <= njc) && (i < nic);
+        if (DIM == 3) { wait_plane(0); wait_plane(1); wait_plane(2); __syncthreads(); }
+        for (int k = k0; k < k1; ++k) {
+            const int m = (DIM == 3) ? k - k0 + 2 : 0;
+            if (DIM == 3 && lane == 0 && m + 2 <= m_last) issue_plane(m + 2);      // plane k + 2 -> the buffer plane k - 2 has left
+            wait_plane(m);
+            const double* t0 = tile_of(m);
+            double xM[5], nM[5];
+            bool xfb = false, nfb = false;
+            if (lane < 2 * TY) {
+                double qm[5], q0[5], qp[5], qP[5];
+                bool fbP;
+                load_cell5<DIM, TY>(t0, oX - 1, qm); load_cell5<DIM, TY>(t0, oX, q0); load_cell5<DIM, TY>(t0, oX + 1, qp);
+                recon_cell<DIM, CLIP>(D, 0, eps_i, qm, q0, qp, xM, qP, xfb, fbP);
+                if (hg == 0) {
+                    qP[1] = fold_flag(qP[1], fbP);
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) qPiH[v * TY + hr] = qP[v];
+                }
+            }
+            {
+                double qm[5], q0[5], qp[5], qM[5], qP[5];
+                bool fbM, fbP;
+                load_cell5<DIM, TY>(t0, oS - T::COLS, qm); load_cell5<DIM, TY>(t0, oS, q0); load_cell5<DIM, TY>(t0, oS + T::COLS, qp);
+                recon_cell<DIM, CLIP>(D, 1, eps_j, qm, q0, qp, qM, qP, fbM, fbP);
+                qP[1] = fold_flag(qP[1], fbP);
+#pragma unroll
+                for (int v = 0; v < 5; ++v) qPj[v * 32 + lane] = qP[v];
+            }
+            {
+                double qm[5], q0[5], qp[5], qP[5];
+                bool fbP;
+                load_cell5<DIM, TY>(t0, oN - T::COLS, qm); load_cell5<DIM, TY>(t0, oN, q0); load_cell5<DIM, TY>(t0, oN + T::COLS, qp);
+                recon_cell<DIM, CLIP>(D, 1, eps_j, qm, q0, qp, nM, qP, nfb, fbP);
+            }
+            __syncthreads();                              // barrier R: plus states are published
+            const long long crow = D.cell0 + ((long long)(k + D.kg) * NJ) * NI;
+            if (eastE) {
+                const long long cf = crow + (long long)(j0 + hr + EB_NG) * NI + (i0 + 32 + EB_NG);
+                double F[NCQ];
+                if (!outflow_override<DIM, 0>(P, D, S.prim_in, i0 + 32, nic, cf, 1, F)) {
+                    double Ls[5];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) Ls[v] = qPiX[v * TY + hr];
+                    const bool fbL = unfold_flag(Ls[1]);
+                    const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[0][cf] : 0.0;
+                    face_flux_v3<DIM, FLUX, 0>(P, gas, Ls, t0[T::F_A * T::FSZ + oX - 1], fbL, cf - 1, xM, t0[T::F_A * T::FSZ + oX], xfb, cf,
+                                               alpha, S.prim_in, F);
+                }
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) fX[q * TY + hr] = F[q];
+            }
+            if (northE) {
+                const long long cf = crow + (long long)(j0 + TY + EB_NG) * NI + (i + EB_NG);
+                double F[NCQ];
+                if (!outflow_override<DIM, 1>(P, D, S.prim_in, j0 + TY, njc, cf, sj, F)) {
+                    double Ls[5];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) Ls[v] = qPj[(TY * 5 + v) * 32 + lane];
+                    const bool fbL = unfold_flag(Ls[1]);
+                    const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[1][cf] : 0.0;
+                    face_flux_v3<DIM, FLUX, 1>(P, gas, Ls, t0[T::F_A * T::FSZ + oN - T::COLS], fbL, cf - sj, nM, t0[T::F_A * T::FSZ + oN], nfb, cf,
+                                               alpha, S.prim_in, F);
+                }
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) fS[(q * (TY + 1) + TY) * 32 + lane] = F[q];
+            }
+            __syncthreads();                              // barrier F: fluxes are published
+        }
+        return;
+    }
+
+    // =============================== main warps: one thread per cell of the tile ================================
+    const int i = i0 + lane, j = j0 + wy;
+    const bool cell_ok = (i < nic) && (j < njc);
+    const bool faceW_ok = (i <= nic) && (j < njc);
+    const bool faceS_ok = (i < nic) && (j <= njc);
+    const int o = (wy + 2) * T::COLS + (lane + 2);          // own position in a tile field
+    double acc[NCQ], FB[NCQ];
+    double kP[5];                                           // plus state along k of the cell one plane below
+    bool kPfb = false;
+#pragma unroll
+    for (int q = 0; q < NCQ; ++q) { acc[q] = 0.0; FB[q] = 0.0; }
+#pragma unroll
+    for (int v = 0; v < 5; ++v) kP[v] = 0.0;
+    bool fail = false;
+    int n_invalid = 0;
+
+    if (DIM == 3) {
+        wait_plane(0); wait_plane(1); wait_plane(2);
+        double qm[5], q0[5], qp[5], qM[5];
+        bool fbM;
+        load_cell5<DIM, TY>(tile_of(0), o, qm); load_cell5<DIM, TY>(tile_of(1), o, q0); load_cell5<DIM, TY>(tile_of(2), o, qp);
+        recon_cell<DIM, CLIP>(D, 2, eps_k, qm, q0, qp, qM, kP, fbM, kPfb);
+        __syncthreads();            // plane k0 - 2 has been read: its buffer may be refilled
+    }
+
+    const int kend = (DIM == 3) ? k1 : 0;
+    for (int k = k0; k <= kend; ++k) {
+        const int m = (DIM == 3) ? k - k0 + 2 : 0;
+        const bool has_cells = (DIM == 3) ? (k < k1) : true;
+        const double* t0 = tile_of(m);
+        const long long c = D.cell0 + ((long long)(k + D.kg) * NJ + (j + EB_NG)) * NI + (i + EB_NG);
+        double q0[5];
+        if (DIM == 3) {
+            wait_plane(m + 1);
+            const double* tb = tile_of(m - 1);
+            const double* ta = tile_of(m + 1);
+            double qm[5], qp[5], kM[5], kPn[5];
+            bool fbM, fbP;
+            load_cell5<DIM, TY>(tb, o, qm); load_cell5<DIM, TY>(t0, o, q0); load_cell5<DIM, TY>(ta, o, qp);
+            recon_cell<DIM, CLIP>(D, 2, eps_k, qm, q0, qp, kM, kPn, fbM, fbP);
+            if (cell_ok) {
+                if (!outflow_override<DIM, 2>(P, D, S.prim_in, k, nkc, c, sk, FB)) {
+                    const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[2][c] : 0.0;
+                    face_flux_v3<DIM, FLUX, 2>(P, gas, kP, tb[T::F_A * T::FSZ + o], kPfb, c - sk, kM, t0[T::F_A * T::FSZ + o], fbM, c,
+                                               alpha, S.prim_in, FB);
+                }
+                // finish the cell of the plane below: its top face is this plane's bottom face
+                if (k > k0) {
+                    const long long cp = c - sk;
+                    double dUdt[NCQ];
+#pragma unroll
+                    for (int q = 0; q < NCQ; ++q) { double si = acc[q] - FB[q] * D.area[2]; dUdt[q] = D.vol_inv * si + 0.0; }
+                    long long p0, p1, p2;
+                    push_targets<DIM>(D, i, j, k - 1, cp, p0, p1, p2);
+                    finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, cp, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < 5; ++v) kP[v] = kPn[v];
+            kPfb = fbP;
+            if (!has_cells) break;                  // top face of the chunk: nothing else on this plane (uniform over the CTA)
+        } else {
+            wait_plane(0);
+            load_cell5<DIM, TY>(t0, o, q0);
+        }
+
+        // ---- along i: own minus state, the west neighbour's plus state by shuffle
+        double iM[5], Lw[5];
+        bool ifbM;
+        {
+            double qm[5], qp[5], iP[5];
+            bool fbP;
+            load_cell5<DIM, TY>(t0, o - 1, qm); load_cell5<DIM, TY>(t0, o + 1, qp);
+            recon_cell<DIM, CLIP>(D, 0, eps_i, qm, q0, qp, iM, iP, ifbM, fbP);
+            iP[1] = fold_flag(iP[1], fbP);
+#pragma unroll
+            for (int v = 0; v < 5; ++v) Lw[v] = __shfl_up_sync(0xffffffffu, iP[v], 1);
+            if (lane == 31) {
+#pragma unroll
+                for (int v = 0; v < 5; ++v) qPiX[v * TY + wy] = iP[v];
+            }
+        }
+        // ---- along j: own minus state, own plus state to the row above through shared memory
+        double jM[5];
+        bool jfbM;
+        {
+            double qm[5], qp[5], jP[5];
+            bool fbP;
+            load_cell5<DIM, TY>(t0, o - T::COLS, qm); load_cell5<DIM, TY>(t0, o + T::COLS, qp);
+            recon_cell<DIM, CLIP>(D, 1, eps_j, qm, q0, qp, jM, jP, jfbM, fbP);
+            jP[1] = fold_flag(jP[1], fbP);
+#pragma unroll
+            for (int v = 0; v < 5; ++v) qPj[((wy + 1) * 5 + v) * 32 + lane] = jP[v];
+        }
+        __syncthreads();                                  // barrier R: plus states are published
+
+        double FW[NCQ], FS_[NCQ];
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) { FW[q] = 0.0; FS_[q] = 0.0; }
+        if (lane == 0) {
+#pragma unroll
+            for (int v = 0; v < 5; ++v) Lw[v] = qPiH[v * TY + wy];
+        }
+        if (faceW_ok) {
+            if (!outflow_override<DIM, 0>(P, D, S.prim_in, i, nic, c, 1, FW)) {
+                const bool fbL = unfold_flag(Lw[1]);
+                const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[0][c] : 0.0;
+                face_flux_v3<DIM, FLUX, 0>(P, gas, Lw, t0[T::F_A * T::FSZ + o - 1], fbL, c - 1, iM, t0[T::F_A * T::FSZ + o], ifbM, c,
+                                           alpha, S.prim_in, FW);
+            }
+        }
+        if (faceS_ok) {
+            if (!outflow_override<DIM, 1>(P, D, S.prim_in, j, njc, c, sj, FS_)) {
+                double Ls[5];
+#pragma unroll
+                for (int v = 0; v < 5; ++v) Ls[v] = qPj[(wy * 5 + v) * 32 + lane];
+                const bool fbL = unfold_flag(Ls[1]);
+                const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[1][c] : 0.0;
+                face_flux_v3<DIM, FLUX, 1>(P, gas, Ls, t0[T::F_A * T::FSZ + o - T::COLS], fbL, c - sj, jM, t0[T::F_A * T::FSZ + o], jfbM, c,
+                                           alpha, S.prim_in, FS_);
+            }
+        }
+        double FE[NCQ];
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) {
+            FE[q] = __shfl_down_sync(0xffffffffu, FW[q], 1);
+            fS[(q * (TY + 1) + wy) * 32 + lane] = FS_[q];
+        }
+        __syncthreads();                                  // barrier F: fluxes are published
+
+        if (cell_ok) {
+#pragma unroll
+            for (int q = 0; q < NCQ; ++q) {
+                const double fe = (lane == 31) ? fX[q * TY + wy] : FE[q];
+                const double fn = fS[(q * (TY + 1) + wy + 1) * 32 + lane];
+                double si = FW[q] * D.area[0];          // 0 - F*(-A), summation order W, E, S, N, B, T (fvcell.d:824-854)
+                si = si - fe * D.area[0];
+                si = si + FS_[q] * D.area[1];
+                si = si - fn * D.area[1];
+                if (DIM == 3) si = si + FB[q] * D.area[2];
+                acc[q] = si;
+            }
+            if (DIM == 2) {
+                double dUdt[NCQ];
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) dUdt[q] = D.vol_inv * acc[q] + 0.0;
+                long long p0, p1, p2;
+                push_targets<DIM>(D, i, j, 0, c, p0, p1, p2);
+                finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, c, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
+            }
+        }
+    }
+
+    unsigned any_fail = __ballot_sync(0xffffffffu, fail);
+    int inv = n_invalid;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) inv += __shfl_down_sync(0xffffffffu, inv, o2);
+    if (lane == 0) {
+        if (any_fail) atomicOr(&S.status[0], 1);
+        if (inv) atomicAdd(&S.status[S.stage], inv);
+    }
+}
+
+template <int DIM, int FLUX, bool CLIP>
+void launch_one_v3(const EbParams& P, const EbGas* gas, const EbBlockDesc* desc, int nblocks, long long ncta,
+                   const EbArena& A, const EbStageArgs& S, cudaStream_t st)
+{
+    constexpr int TY = EB_V2_TY;
+    const size_t smem = V3Smem<DIM, TY>::BYTES;
+    auto kern = flux_update_kernel_v3<DIM, FLUX, CLIP, TY>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    kern<<<(unsigned)ncta, dim3(32, TY + 1), smem, st>>>(P, gas, desc, nblocks, A, S);
+}
+
+// uniform-Cartesian blocks, ideal gas, interpolation_order = 2, apply_limiter = true, TMA staging available
+template <int FLUX>
+void launch_flux_update_v3_impl(const EbParams& P, const EbGas* gas, const EbBlockDesc* desc, int nblocks,
+                                long long ncta, const EbArena& A, const EbStageArgs& S, cudaStream_t st)
+{
+    if (P.dims == 3) {
+        if (P.extrema_clipping) launch_one_v3<3, FLUX, true>(P, gas, desc, nblocks, ncta, A, S, st);
+        else launch_one_v3<3, FLUX, false>(P, gas, desc, nblocks, ncta, A, S, st);
+    } else {
+        if (P.extrema_clipping) launch_one_v3<2, FLUX, true>(P, gas, desc, nblocks, ncta, A, S, st);
+        else launch_one_v3<2, FLUX, false>(P, gas, desc, nblocks, ncta, A, S, st);
+    }
+}
+
+}  // namespace EB_NS

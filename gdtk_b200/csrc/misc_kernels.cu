@@ -11,19 +11,26 @@ namespace EB_NS {
     void launch_flux_update_k##k(const EbParams& P, int gas_model, const EbGas* gas, const EbBlockDesc* desc,  \
                                  int nblocks, long long ncta, const EbArena& A, const EbStageArgs& S,          \
                                  int tile_y, int which, cudaStream_t st);
-EB_DECL_FLUX(0) EB_DECL_FLUX(1) EB_DECL_FLUX(2) EB_DECL_FLUX(3) EB_DECL_FLUX(4) EB_DECL_FLUX(5)
+EB_DECL_FLUX(0)
+#ifndef EB_DEV_FLUX0_ONLY
+EB_DECL_FLUX(1) EB_DECL_FLUX(2) EB_DECL_FLUX(3) EB_DECL_FLUX(4) EB_DECL_FLUX(5)
 EB_DECL_FLUX(6) EB_DECL_FLUX(7) EB_DECL_FLUX(8) EB_DECL_FLUX(9) EB_DECL_FLUX(10)
+#endif
 #define EB_DECL_DBG(k)                                                                                         \
     void launch_face_debug_k##k(const EbParams& P, int gas_model, const EbGas* gas, const EbArena& A,           \
                                 const double* prim, int nfaces, double* Fout, int* ok_out, cudaStream_t st);
-EB_DECL_DBG(0) EB_DECL_DBG(1) EB_DECL_DBG(2) EB_DECL_DBG(3) EB_DECL_DBG(4) EB_DECL_DBG(5)
+EB_DECL_DBG(0)
+#ifndef EB_DEV_FLUX0_ONLY
+EB_DECL_DBG(1) EB_DECL_DBG(2) EB_DECL_DBG(3) EB_DECL_DBG(4) EB_DECL_DBG(5)
 EB_DECL_DBG(6) EB_DECL_DBG(7) EB_DECL_DBG(8) EB_DECL_DBG(9) EB_DECL_DBG(10)
+#endif
 
 void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* gas, const EbArena& A, const double* prim,
                        int nfaces, double* Fout, int* ok_out, cudaStream_t st)
 {
     switch (flux_calc) {
     case 0: launch_face_debug_k0(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+#ifndef EB_DEV_FLUX0_ONLY
     case 1: launch_face_debug_k1(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 2: launch_face_debug_k2(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 3: launch_face_debug_k3(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
@@ -34,6 +41,7 @@ void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* ga
     case 8: launch_face_debug_k8(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 9: launch_face_debug_k9(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 10: launch_face_debug_k10(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+#endif
     }
 }
 
@@ -41,10 +49,11 @@ void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* ga
 void launch_flux_update(int flux_calc, int gm, const EbParams& P, const EbGas* gas, const EbBlockDesc* desc, int nblocks,
                         long long ncta, const EbArena& A, const EbStageArgs& S, int which, cudaStream_t st)
 {
-    const int ty = (which & 4) ? -1 : 0;
+    const int ty = (which & 4) ? -1 : ((which & 8) ? 1 : 0);      // -1: generic kernel, 1: v2 instead of v3
     which &= 3;
     switch (flux_calc) {
     case 0: launch_flux_update_k0(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+#ifndef EB_DEV_FLUX0_ONLY
     case 1: launch_flux_update_k1(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 2: launch_flux_update_k2(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 3: launch_flux_update_k3(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
@@ -55,6 +64,7 @@ void launch_flux_update(int flux_calc, int gm, const EbParams& P, const EbGas* g
     case 8: launch_flux_update_k8(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 9: launch_flux_update_k9(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 10: launch_flux_update_k10(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+#endif
     }
 }
 
