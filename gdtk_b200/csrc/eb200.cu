@@ -399,24 +399,38 @@ int exchange_remote(Sim* s, double* prim)
 }
 
 // TMA descriptors for the tile staging of the tuned flux kernel: per prim buffer and local block a
-// 4D tensor (i, j, k, field) in the padded block layout; one box = (36, TY+4, 1, 2 fields).
-// TMA wants 16-byte multiples for the strides, i.e. an even NI; otherwise the kernel stages with cp.async.
-int build_tensor_maps(Sim* s)
+// 4D tensor (i, j, k, field) in the padded block layout; one box = (36, TY+4, 1, 2 fields) with the TY of the
+// kernel that runs the block.  TMA wants 16-byte multiples for the strides, i.e. an even NI; otherwise the
+// face-centred kernel stages with cp.async.
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiled tensor_map_encoder()
 {
-    s->d_tmaps = nullptr;
-    if (s->cfg.reserved_i[2]) return 0;                 // testing knob: never use TMA
-    for (Block* b : s->local) if (b->NI % 2) return 0;
-    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
         qres != cudaDriverEntryPointSuccess) {
         (void)cudaGetLastError();
-        return 0;
+        return nullptr;
     }
-    EncodeTiled encode = (EncodeTiled)fn;
+    return (EncodeTiled)fn;
+}
+
+// Can the tiles be staged by TMA?  (16-byte strides: even padded widths; the driver entry point exists)
+bool tma_available(const Sim* s)
+{
+    if (s->cfg.reserved_i[2]) return false;             // testing knob: never use TMA
+    for (const Block* b : s->local) if (b->NI % 2) return false;
+    return tensor_map_encoder() != nullptr;
+}
+
+int build_tensor_maps(Sim* s)
+{
+    s->d_tmaps = nullptr;
+    if (!tma_available(s)) return 0;
+    EncodeTiled encode = tensor_map_encoder();
     const size_t nl = s->local.size();
     std::vector<CUtensorMap> maps(3 * nl);
     for (int p = 0; p < 3; ++p) {
@@ -424,12 +438,12 @@ int build_tensor_maps(Sim* s)
             const Block* b = s->local[n];
             cuuint64_t gdim[4] = { (cuuint64_t)b->NI, (cuuint64_t)b->NJ, (cuuint64_t)b->NK, (cuuint64_t)s->P.nprim };
             cuuint64_t gstride[3] = { (cuuint64_t)b->NI * 8, (cuuint64_t)b->NI * b->NJ * 8, (cuuint64_t)s->P.total * 8 };
-            cuuint32_t box[4] = { EB_V2_COLS, EB_V2_TY + 4, 1, 2 };
+            cuuint32_t box[4] = { EB_V2_COLS, (cuuint32_t)((s->hdesc[n].v3 ? EB_V3_TY : EB_V2_TY) + 4), 1, 2 };
             cuuint32_t estr[4] = { 1, 1, 1, 1 };
             CUresult r = encode(&maps[p * nl + n], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, s->A.prim[p] + b->cell0, gdim, gstride, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return 0;            // fall back to cp.async staging
+            if (r != CUDA_SUCCESS) { set_err("cuTensorMapEncodeTiled failed (%d)", (int)r); return -7; }
         }
     }
     return dev_upload(s, &s->d_tmaps, maps);
@@ -823,24 +837,36 @@ int eb200_commit(int sim)
         cells_total += (long long)b->nic * b->njc * b->nkc;
     }
     s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (s->cfg.reserved_i[1] == 1 ? 4 : 0) | (s->cfg.reserved_i[1] == 2 ? 8 : 0);
+    // Which fused kernel runs a block decides its tiling.  The cell-centred kernel (flux_kernel_v3.cuh) takes the
+    // uniform-Cartesian blocks of the reference's default configuration (same conditions as in flux_inst.cu) when
+    // their tiles can be staged by TMA.
+    const bool tma_ok = tma_available(s);
+    const bool v3_config = tma_ok && s->cfg.reserved_i[1] == 0 && s->cfg.gas_model == EB200_GAS_IDEAL &&
+                           s->P.interpolation_order == 2 && s->P.apply_limiter != 0 && s->P.thermo_interp == EB200_INTERP_RHOU;
+    for (size_t n = 0; n < s->local.size(); ++n) s->hdesc[n].v3 = (v3_config && s->hdesc[n].cartesian) ? 1 : 0;
     {
-        // k-chunking (3D): a CTA marches over `chunk` planes of its tile.  Aim at >= 20 waves of CTAs
+        // k-chunking (3D): a CTA marches over `chunk` planes of its tile.  Aim at >= 8 waves of CTAs
         // (148 SMs x 2 resident CTAs) so that the last, partly filled wave costs little; every chunk
-        // adds one redundant k-face per column, so chunks are kept >= 16 planes.
+        // costs a start-up (three planes to stage before the first face) and four extra planes of tile
+        // traffic, so chunks are kept >= 32 planes.
         long long tiles_plane = 0;
         for (size_t n = 0; n < s->local.size(); ++n) {
             EbBlockDesc& D = s->hdesc[n];
-            D.tiles_i = (D.nic + 31) / 32; D.tiles_j = (D.njc + EB_TILE_Y - 1) / EB_TILE_Y;
+            const int ty = D.v3 ? EB_V3_TY : EB_TILE_Y;
+            D.tiles_i = (D.nic + 31) / 32; D.tiles_j = (D.njc + ty - 1) / ty;
             tiles_plane += (long long)D.tiles_i * D.tiles_j;
         }
-        const long long want = 148LL * 2 * 20;
+        // (EB200_CHUNK_WAVES / EB200_CHUNK_MIN: development knobs)
+        const long long waves = getenv("EB200_CHUNK_WAVES") ? atoll(getenv("EB200_CHUNK_WAVES")) : 8;
+        const long long chunk_min = getenv("EB200_CHUNK_MIN") ? atoll(getenv("EB200_CHUNK_MIN")) : 32;
+        const long long want = 148LL * 2 * waves;
         long long tile0 = 0;
         for (size_t n = 0; n < s->local.size(); ++n) {
             EbBlockDesc& D = s->hdesc[n];
             int chunk = D.nkc;
             if (s->threeD && tiles_plane < want) {
                 long long nch = (want + tiles_plane - 1) / tiles_plane;
-                chunk = (int)std::max<long long>(16, (D.nkc + nch - 1) / nch);
+                chunk = (int)std::max<long long>(chunk_min, (D.nkc + nch - 1) / nch);
                 chunk = std::min(chunk, D.nkc);
             }
             D.chunk_m = s->threeD ? chunk : 1;
@@ -1005,10 +1031,13 @@ int eb200_commit(int sim)
             bool remote[6] = { false, false, false, false, false, false };
             for (int f = 0; f < s->nfaces; ++f)
                 if (b->bc[f].kind == EB200_BC_EXCHANGE_FULL_FACE) { Block* ot = get_blk(s, b->bc[f].other_blk); remote[f] = ot && !ot->local; }
+            // a tile is "boundary" when its stencils (two cells beyond its far-edge faces) reach ghost cells that another
+            // rank fills: also the last-but-one tile when the last one is narrower than two cells
+            const int ty = D.v3 ? EB_V3_TY : EB_TILE_Y;
             for (int tm = 0; tm < D.tiles_m; ++tm) for (int tj = 0; tj < D.tiles_j; ++tj) for (int ti = 0; ti < D.tiles_i; ++ti) {
-                const bool bnd = (remote[EB200_WEST] && ti == 0) || (remote[EB200_EAST] && ti == D.tiles_i - 1) ||
-                                 (remote[EB200_SOUTH] && tj == 0) || (remote[EB200_NORTH] && tj == D.tiles_j - 1) ||
-                                 (remote[EB200_BOTTOM] && tm == 0) || (remote[EB200_TOP] && tm == D.tiles_m - 1);
+                const bool bnd = (remote[EB200_WEST] && ti == 0) || (remote[EB200_EAST] && (ti + 1) * 32 + 2 > D.nic) ||
+                                 (remote[EB200_SOUTH] && tj == 0) || (remote[EB200_NORTH] && (tj + 1) * ty + 2 > D.njc) ||
+                                 (remote[EB200_BOTTOM] && tm == 0) || (remote[EB200_TOP] && (tm + 1) * D.chunk_m + 2 > D.nkc);
                 const int id = (int)(D.tile0 + ((long long)tm * D.tiles_j + tj) * D.tiles_i + ti);
                 (bnd ? t_bnd : t_int).push_back(id);
             }

@@ -25,6 +25,9 @@
 #define EB_V2_TY 8            // rows of cells per CTA tile of the tuned kernel (CTA = 32 x EB_V2_TY threads)
 #endif
 #define EB_V2_COLS 36         // tile width with its two-cell halo
+#ifndef EB_V3_TY
+#define EB_V3_TY 16           // rows of cells per CTA tile of the cell-centred kernel (CTA = 32 x (EB_V3_TY + 1) threads, one per SM)
+#endif
 
 struct EbWeights {
     double aL0, aR0, lenL0, lenR0;
@@ -42,6 +45,7 @@ struct EbBlockDesc {
     int nic, njc, nkc;
     int NI, NJ, NK, kg;
     int cartesian;
+    int v3;                   // 1: the block is tiled for (and run by) the cell-centred kernel flux_update_kernel_v3
     int bc_kind[6];
     long long cell0;          // offset into the arena
     long long stride[3];

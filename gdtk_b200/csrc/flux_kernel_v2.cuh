@@ -477,7 +477,7 @@ flux_update_kernel_v2(const EbParams P, const EbGas* __restrict__ gas, const EbB
         for (int n = tid; n < (int)(sizeof(EbBlockDesc) / sizeof(int)); n += NT) dst[n] = src[n];
     }
     __syncthreads();
-    if ((D.cartesian != 0) != CART) return;
+    if ((D.cartesian != 0) != CART || D.v3) return;      // v3: tiled for (and run by) flux_update_kernel_v3
 
     const long long t = cta - D.tile0;
     const int ti = (int)(t % D.tiles_i);

@@ -21,8 +21,14 @@
 #pragma once
 #include "flux_kernel_v2.cuh"
 
+#ifndef EB_V3_VOTEFB
+#define EB_V3_VOTEFB 1        // first-order fall-back behind a warp vote (a branch instead of selects)
+#endif
+#ifndef EB_V3_TRYSPLIT
+#define EB_V3_TRYSPLIT 1      // poll the next plane's barrier early, consume the answer after independent loads
+#endif
 #ifndef EB_V3_MIN_CTAS
-#define EB_V3_MIN_CTAS 2
+#define EB_V3_MIN_CTAS ((EB_V3_TY >= 16) ? 1 : 2)     // 17 warps x 112 registers fill an SM; 9-warp CTAs come in pairs
 #endif
 
 namespace EB_NS {
@@ -99,13 +105,20 @@ __device__ __forceinline__ void recon_cell(const EbBlockDesc& D, int d, double e
     if (DIM == 2) { qM[4] = 0.0; qP[4] = 0.0; }
     fbM = not_positive(qM[1]) || not_positive(qM[0]);
     fbP = not_positive(qP[1]) || not_positive(qP[0]);
-    if (fbM) {
+    // rare: a vote makes the condition warp-uniform, so that this stays a branch around the copies instead of
+    // twenty selects on the main path
+#if EB_V3_VOTEFB
+    if (__any_sync(__activemask(), fbM || fbP))
+#endif
+    {
+        if (fbM) {
 #pragma unroll
-        for (int v = 0; v < 5; ++v) qM[v] = q0[v];
-    }
-    if (fbP) {
+            for (int v = 0; v < 5; ++v) qM[v] = q0[v];
+        }
+        if (fbP) {
 #pragma unroll
-        for (int v = 0; v < 5; ++v) qP[v] = q0[v];
+            for (int v = 0; v < 5; ++v) qP[v] = q0[v];
+        }
     }
 }
 
@@ -163,8 +176,20 @@ __device__ __forceinline__ void face_flux_v3(const EbParams& P, const EbGas* __r
     }
 }
 
-// BFE_SimpleOutflowFlux on a block-boundary face (bc/boundary_flux_effect.d:573-643): returns true and fills F when
-// the face with plus-side cell cf (stride st along DIR) lies on a boundary that carries this boundary condition.
+// BFE_SimpleOutflowFlux on a block-boundary face (bc/boundary_flux_effect.d:573-643).  Rare (faces on an outflow
+// boundary only): kept out of line, one copy for every call site, so that the hot loop stays small.
+template <int DIM>
+__device__ __noinline__ void outflow_flux_nl(const double* __restrict__ prim, long long total, long long cell, int outsign,
+                                             double nx, double ny, double nz, double* F)
+{
+    Prim<1> fs;
+    load_prim<1>(fs, prim, total, cell);
+    if (DIM == 2) fs.vz = 0.0;
+    outflow_flux<DIM, 1>(fs, outsign, nx, ny, nz, F);
+}
+
+// returns true and fills F when the face with plus-side cell cf (index idx of n along DIR, stride st) lies on a
+// boundary that carries this boundary condition
 template <int DIM, int DIR>
 __device__ __forceinline__ bool outflow_override(const EbParams& P, const EbBlockDesc& D, const double* __restrict__ prim,
                                                  int idx, int n, long long cf, long long st, double* F)
@@ -174,10 +199,10 @@ __device__ __forceinline__ bool outflow_override(const EbParams& P, const EbBloc
     if (idx == 0) bcf = 2 * DIR; else if (idx == n) bcf = 2 * DIR + 1;
     if (bcf < 0 || D.bc_kind[bcf] != EB200_BC_OUTFLOW_SIMPLE_FLUX) return false;
     const int hi = bcf & 1;
-    Prim<1> fs;
-    load_prim<1>(fs, prim, P.total, hi ? cf - st : cf);
-    if (DIM == 2) fs.vz = 0.0;
-    outflow_flux<DIM, 1>(fs, hi ? 1 : -1, D.nvec[DIR][0], D.nvec[DIR][1], D.nvec[DIR][2], F);
+    double Ft[Layout<DIM, 1>::NCQ];
+    outflow_flux_nl<DIM>(prim, P.total, hi ? cf - st : cf, hi ? 1 : -1, D.nvec[DIR][0], D.nvec[DIR][1], D.nvec[DIR][2], Ft);
+#pragma unroll
+    for (int q = 0; q < Layout<DIM, 1>::NCQ; ++q) F[q] = Ft[q];
     return true;
 }
 
@@ -200,23 +225,96 @@ __device__ __forceinline__ bool unfold_flag(double& u)
 #endif
 }
 
+// finish_cell of flux_kernel.cuh in two halves, so that only the new U (not U0, the residuals and the fluxes)
+// has to survive between them.  First half: stage update (simcore_gasdynamic_step.d:1250-1357).
+template <int NCQ>
+__device__ __forceinline__ void stage_update_v3(const EbStageArgs& S, long long total, long long c, const double* U0, const double* d0,
+                                                const double* dUdt, double* U)
+{
+    if (S.stage == 1) {
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) U[q] = U0[q] + S.dt_g[0] * dUdt[q];
+    } else if (S.stage == 2) {
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) U[q] = U0[q] + S.dt_g[3] * (S.dt_g[0] * d0[q] + S.dt_g[1] * dUdt[q]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q)
+            U[q] = U0[q] + S.dt_g[3] * (S.dt_g[0] * d0[q] + S.dt_g[1] * ldg(S.dUdt_prev[1] + q * total + c) + S.dt_g[2] * dUdt[q]);
+    }
+    if (S.dUdt_out) {
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) S.dUdt_out[q * total + c] = dUdt[q];
+    }
+}
+
+// Second half: decode_conserved (fvcell.d:586-821), check_data (fluidblock.d:607-675), stores, ghost-cell pushes.
+template <int DIM>
+__device__ __forceinline__ void decode_store_v3(const EbParams& P, const EbGas* __restrict__ gas, const EbStageArgs& S, long long total,
+                                                long long c, double* U, long long push0, long long push1, long long push2)
+{
+    constexpr int NCQ = Layout<DIM, 1>::NCQ;
+    Prim<1> Q;
+    Q.T = 0.0;
+    bool modified;
+    const int rc = decode_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, U, Q, modified);
+    if (rc) atomicOr(&S.status[0], 1);          // rare: report at once, no flag to carry through the plane loop
+    else {
+        store_prim<1>(Q, S.prim_out, total, c);
+        if ((push0 & push1 & push2) >= 0 || push0 >= 0 || push1 >= 0 || push2 >= 0) {     // ghost cells of same-GPU neighbours
+#pragma unroll 1
+            for (int n = 0; n < 3; ++n) {
+                const long long pt = (n == 0) ? push0 : ((n == 1) ? push1 : push2);
+                if (pt >= 0) store_prim<1>(Q, S.prim_out, total, pt);
+            }
+        }
+        if (!check_data<1>(P, Q)) atomicAdd(&S.status[S.stage], 1);
+    }
+    if (S.U_out) {
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) S.U_out[q * total + c] = U[q];
+    }
+}
+
 template <int DIM, int TY>
 struct V3Smem {
     typedef Tile<DIM, TY> T;
     static constexpr int NCQ = Layout<DIM, 1>::NCQ;
-    static constexpr int NBUF = (DIM == 3) ? 4 : 1;
+    static constexpr int NBUF = (DIM == 3) ? 3 : 1;
     static constexpr int O_TILE = 0;
     static constexpr int O_QPJ = O_TILE + NBUF * T::SIZE;        // [TY+1][5][32]: slot r = plus state (along j) of row r-1
-    static constexpr int O_QPIH = O_QPJ + (TY + 1) * 5 * 32;     // [5][TY]: plus state (along i) of the cell west of the tile
-    static constexpr int O_QPIX = O_QPIH + 5 * TY;               // [5][TY]: plus state of lane 31, for the east-edge face
-    static constexpr int O_FS = O_QPIX + 5 * TY;                 // [NCQ][TY+1][32]: south-face fluxes; row TY = north edge
-    static constexpr int O_FX = O_FS + NCQ * (TY + 1) * 32;      // [NCQ][TY]: east-edge fluxes
-    static constexpr int O_DESC = O_FX + NCQ * TY;
+    static constexpr int O_QPIH = O_QPJ + (TY + 1) * 5 * 32;     // [3][5][TY]: plus state (along i) of the cell west of the tile, slot = plane % 3
+    static constexpr int O_FS = O_QPIH + 3 * 5 * TY;             // [NCQ][TY+1][32]: south-face fluxes; row TY = north edge
+    static constexpr int O_FX = O_FS + NCQ * (TY + 1) * 32;      // [2][NCQ][TY]: east-edge fluxes, by plane parity (written a phase early)
+    static constexpr int O_US = O_FX + 2 * NCQ * TY;                 // [2 NCQ][TY*32] (3D): U0 and dUdt0 of the cell to finish, staged by cp.async
+    static constexpr int O_DESC = O_US + ((DIM == 3) ? 2 * NCQ * TY * 32 : 0);
     static constexpr size_t BYTES = sizeof(double) * O_DESC + sizeof(EbBlockDesc);
 };
 
+// one try of the barrier's phase; the result is consumed later so that independent work hides its latency
+__device__ __forceinline__ unsigned mbar_try(unsigned long long* bar, unsigned parity)
+{
+    unsigned done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done;
+}
+
+// CTA-wide split-phase barrier on an mbarrier with one arrival per warp: arrive() after the warp's own writes,
+// wait() before reading what the other warps wrote; independent work goes in between.
+__device__ __forceinline__ void cta_arrive(unsigned long long* bar, int lane)
+{
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int DIM, int FLUX, bool CLIP, int TY>
-__global__ void __launch_bounds__(32 * (TY + 1), EB_V3_MIN_CTAS)
+__global__ void
+#ifdef EB_V3_MAXNREG
+__maxnreg__(EB_V3_MAXNREG)
+#else
+__launch_bounds__(32 * (TY + 1), EB_V3_MIN_CTAS)
+#endif
 flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc* __restrict__ descs, int nblocks,
                       const EbArena A, const EbStageArgs S)
 {
@@ -230,12 +328,14 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
     double* const tile = smem + SM::O_TILE;
     double* const qPj = smem + SM::O_QPJ;
     double* const qPiH = smem + SM::O_QPIH;
-    double* const qPiX = smem + SM::O_QPIX;
     double* const fS = smem + SM::O_FS;
     double* const fX = smem + SM::O_FX;
+    double* const uS = smem + SM::O_US;
     EbBlockDesc& D = *reinterpret_cast<EbBlockDesc*>(smem + SM::O_DESC);
     __shared__ int s_blk;
-    __shared__ __align__(8) unsigned long long s_bar[4];
+    __shared__ int s_ij[2];                                  // i0, j0 of the tile
+    __shared__ __align__(8) unsigned long long s_bar[3];     // tile buffers (TMA transaction barriers)
+    __shared__ __align__(8) unsigned long long s_sync[3];    // R: plus states along j published; F: fluxes published; K: k-stencil read
 
     const int lane = threadIdx.x, wy = threadIdx.y;
     const int tid = wy * 32 + lane;
@@ -247,6 +347,7 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
         s_blk = lo;
 #pragma unroll
         for (int b = 0; b < NBUF; ++b) mbar_init(&s_bar[b], 1);
+        mbar_init(&s_sync[0], TY + 1); mbar_init(&s_sync[1], TY + 1); mbar_init(&s_sync[2], TY);
         mbar_fence_init();
     }
     __syncthreads();
@@ -256,13 +357,17 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
         for (int n = tid; n < (int)(sizeof(EbBlockDesc) / sizeof(int)); n += NT) dst[n] = src[n];
     }
     __syncthreads();
-    if (!D.cartesian) return;
+    if (!D.v3) return;
+    unsigned long long* const barR = &s_sync[0];
+    unsigned long long* const barF = &s_sync[1];
+    unsigned long long* const barK = &s_sync[2];
 
     const long long t = cta - D.tile0;
     const int ti = (int)(t % D.tiles_i);
     const int tj = (int)((t / D.tiles_i) % D.tiles_j);
     const int tm = (int)(t / ((long long)D.tiles_i * D.tiles_j));
     const int i0 = ti * 32, j0 = tj * TY;
+    if (tid == 0) { s_ij[0] = i0; s_ij[1] = j0; }           // read after the start-up barrier
     const int nic = D.nic, njc = D.njc, nkc = D.nkc;
     const int NI = D.NI, NJ = D.NJ;
     const long long sj = D.stride[1], sk = D.stride[2];
@@ -277,9 +382,9 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
 #endif
 
     // planes are numbered m = k - (k0 - 2) (3D; the first plane a chunk touches is k0 - 2): plane m lives in
-    // tile[m & 3], its barrier completes phase (m >> 2) & 1.  2D: one plane, one buffer.
+    // tile[m % 3], its barrier completes phase (m / 3) & 1.  2D: one plane, one buffer.
     auto issue_plane = [&](int m) {        // one thread
-        const int b = m & (NBUF - 1);
+        const int b = (DIM == 3) ? m % 3 : 0;
         double* dst = tile + b * T::SIZE;
         const void* tmap = reinterpret_cast<const char*>(S.tmaps) + (size_t)s_blk * 128;
         const int kp = (DIM == 3) ? (k0 - 2 + m) + D.kg : 0;
@@ -288,78 +393,115 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
         tma_load_4d(dst + 2 * T::FSZ, tmap, &s_bar[b], i0, j0, kp, 4);
         tma_load_4d(dst + 4 * T::FSZ, tmap, &s_bar[b], i0, j0, kp, 6);
     };
-    auto wait_plane = [&](int m) { mbar_wait(&s_bar[m & (NBUF - 1)], (unsigned)((m >> 2) & 1)); };
-    auto tile_of = [&](int m) -> const double* { return tile + (m & (NBUF - 1)) * T::SIZE; };
-    const int m_last = (DIM == 3) ? (k1 + 1) - (k0 - 2) : 0;           // last plane this chunk touches
+    auto wait_plane = [&](int m) { mbar_wait(&s_bar[(DIM == 3) ? m % 3 : 0], (unsigned)((m / 3) & 1)); };
+    auto tile_of = [&](int m) -> const double* { return tile + ((DIM == 3) ? m % 3 : 0) * T::SIZE; };
 
     if (helper && lane == 0) {
-        if (DIM == 3) { issue_plane(0); issue_plane(1); issue_plane(2); issue_plane(3); }
-        else issue_plane(0);
+        issue_plane(0);
+        if (DIM == 3) { issue_plane(1); issue_plane(2); }
     }
 
     // =============================== helper warp ===============================================================
+    // per plane k: the plus state (along i) of the cells west of the tile for plane k + 1 (published a plane ahead,
+    // so that the main warps need no barrier for their west faces), the east-edge faces of plane k from its own
+    // reconstruction of the columns i0 + 31 and i0 + 32, the plus state (along j) of the row south of the tile, the
+    // north-edge faces, and the TMA refill of the buffer whose plane has left the k-stencil.
     if (helper) {
-        const int hr = lane & (TY - 1);                 // row served in the i-halo pass (lanes 0 .. 2 TY - 1)
-        const int hg = lane / TY;                       // 0: cell west of the tile (col 1), 1: cell east of it (col 34)
-        const int oX = (hr + 2) * T::COLS + ((hg == 0) ? 1 : 34);
-        const int oS = 1 * T::COLS + (lane + 2);        // south halo row
+        const int hr = lane & (TY - 1);                 // row served in the i-halo jobs
+        const int hg = (lane / TY) & 1;                 // job 1: 0 = column i0 + 31 (col 33), 1 = column i0 + 32 (col 34)
         const int oN = (TY + 2) * T::COLS + (lane + 2); // north halo row
+        const int oE = (hr + 2) * T::COLS + 34;         // cell east of the tile in row hr
         const int i = i0 + lane;
         const bool eastE = (lane >= TY) && (lane < 2 * TY) && (i0 + 32 <= nic) && (j0 + hr < njc);
         const bool northE = (j0 + TY <= njc) && (i < nic);
-        if (DIM == 3) { wait_plane(0); wait_plane(1); wait_plane(2); __syncthreads(); }
-        for (int k = k0; k < k1; ++k) {
-            const int m = (DIM == 3) ? k - k0 + 2 : 0;
-            if (DIM == 3 && lane == 0 && m + 2 <= m_last) issue_plane(m + 2);      // plane k + 2 -> the buffer plane k - 2 has left
-            wait_plane(m);
-            const double* t0 = tile_of(m);
-            double xM[5], nM[5];
-            bool xfb = false, nfb = false;
-            if (lane < 2 * TY) {
-                double qm[5], q0[5], qp[5], qP[5];
-                bool fbP;
-                load_cell5<DIM, TY>(t0, oX - 1, qm); load_cell5<DIM, TY>(t0, oX, q0); load_cell5<DIM, TY>(t0, oX + 1, qp);
-                recon_cell<DIM, CLIP>(D, 0, eps_i, qm, q0, qp, xM, qP, xfb, fbP);
-                if (hg == 0) {
-                    qP[1] = fold_flag(qP[1], fbP);
+        // One reconstruction, four jobs per plane (one copy of the arithmetic keeps the code small):
+        //   0: along i, cell west of the tile (lanes < TY), plane `kw`: plus state -> qPiH[kw & 1]
+        //   1: along i, columns i0 + 31 and i0 + 32 (lanes < 2 TY): plus state of the first moves to the lanes of
+        //      the second, which keep their minus state: the east-edge face
+        //   2: along j, row south of the tile: plus state -> qPj[0]
+        //   3: along j, row north of the tile: minus state kept for the north-edge face
+        double eM[5], eL[5], nM[5];
+        bool efb = false, nfb = false;
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) qPiH[v * TY + hr] = qP[v];
+        for (int v = 0; v < 5; ++v) { eM[v] = 0.0; eL[v] = 0.0; nM[v] = 0.0; }
+        auto halo_jobs = [&](int job_lo, int job_hi, const double* t0, const double* tw, int kw) {
+#pragma unroll 1
+            for (int job = job_lo; job <= job_hi; ++job) {
+                const int d = job >> 1;
+                const double* tp = (job == 0) ? tw : t0;
+                const int so = (d == 0) ? 1 : T::COLS;
+                int oc;
+                bool act;
+                if (job == 0) { oc = (hr + 2) * T::COLS + 1; act = lane < TY; }
+                else if (job == 1) { oc = (hr + 2) * T::COLS + 33 + hg; act = lane < 2 * TY; }
+                else if (job == 2) { oc = T::COLS + (lane + 2); act = true; }
+                else { oc = oN; act = true; }
+                double qM[5], qP[5];
+                bool fbM = false, fbP = false;
+#pragma unroll
+                for (int v = 0; v < 5; ++v) { qM[v] = 0.0; qP[v] = 0.0; }
+                if (act) {
+                    double qm[5], q0[5], qp[5];
+                    load_cell5<DIM, TY>(tp, oc - so, qm); load_cell5<DIM, TY>(tp, oc, q0); load_cell5<DIM, TY>(tp, oc + so, qp);
+                    recon_cell<DIM, CLIP>(D, d, (d == 0) ? eps_i : eps_j, qm, q0, qp, qM, qP, fbM, fbP);
+                    qP[1] = fold_flag(qP[1], fbP);
+                }
+                if (job == 0) {
+                    if (act) {
+#pragma unroll
+                        for (int v = 0; v < 5; ++v) qPiH[(((kw % 3) * 5) + v) * TY + hr] = qP[v];
+                    }
+                } else if (job == 1) {
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) { eL[v] = __shfl_up_sync(0xffffffffu, qP[v], TY); eM[v] = qM[v]; }
+                    efb = fbM;
+                } else if (job == 2) {
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) qPj[v * 32 + lane] = qP[v];
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) nM[v] = qM[v];
+                    nfb = fbM;
                 }
             }
-            {
-                double qm[5], q0[5], qp[5], qM[5], qP[5];
-                bool fbM, fbP;
-                load_cell5<DIM, TY>(t0, oS - T::COLS, qm); load_cell5<DIM, TY>(t0, oS, q0); load_cell5<DIM, TY>(t0, oS + T::COLS, qp);
-                recon_cell<DIM, CLIP>(D, 1, eps_j, qm, q0, qp, qM, qP, fbM, fbP);
-                qP[1] = fold_flag(qP[1], fbP);
-#pragma unroll
-                for (int v = 0; v < 5; ++v) qPj[v * 32 + lane] = qP[v];
-            }
-            {
-                double qm[5], q0[5], qp[5], qP[5];
-                bool fbP;
-                load_cell5<DIM, TY>(t0, oN - T::COLS, qm); load_cell5<DIM, TY>(t0, oN, q0); load_cell5<DIM, TY>(t0, oN + T::COLS, qp);
-                recon_cell<DIM, CLIP>(D, 1, eps_j, qm, q0, qp, nM, qP, nfb, fbP);
-            }
-            __syncthreads();                              // barrier R: plus states are published
-            const long long crow = D.cell0 + ((long long)(k + D.kg) * NJ) * NI;
+        };
+        // west halo of the first plane, before the start-up barrier
+        wait_plane((DIM == 3) ? 2 : 0);
+        halo_jobs(0, 0, nullptr, tile_of((DIM == 3) ? 2 : 0), k0);
+        if (DIM == 3) { wait_plane(0); wait_plane(1); }
+        __syncthreads();                                  // start-up barrier
+        if (DIM == 3 && lane == 0) issue_plane(3);        // plane k0 + 1 -> the buffer plane k0 - 2 has left
+        for (int k = k0; k < k1; ++k) {
+            const int it = k - k0;
+            const int m = (DIM == 3) ? it + 2 : 0;
+            const double* t0 = tile_of(m);
+            const bool next_has_cells = (DIM == 3) && (k + 1 < k1);
+            if (next_has_cells) wait_plane(m + 1);
+            // the jobs along i write buffers nobody reads any more (qPiH: three slots, fX: two; the helper has
+            // passed R of the last plane), so they run ahead of the main warps' last steps of the plane before
+            halo_jobs(next_has_cells ? 0 : 1, 1, t0, tile_of(m + 1), k + 1);
             if (eastE) {
-                const long long cf = crow + (long long)(j0 + hr + EB_NG) * NI + (i0 + 32 + EB_NG);
+                const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (j0 + hr + EB_NG)) * NI + (i0 + 32 + EB_NG);
                 double F[NCQ];
                 if (!outflow_override<DIM, 0>(P, D, S.prim_in, i0 + 32, nic, cf, 1, F)) {
-                    double Ls[5];
-#pragma unroll
-                    for (int v = 0; v < 5; ++v) Ls[v] = qPiX[v * TY + hr];
-                    const bool fbL = unfold_flag(Ls[1]);
+                    const bool fbL = unfold_flag(eL[1]);
                     const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[0][cf] : 0.0;
-                    face_flux_v3<DIM, FLUX, 0>(P, gas, Ls, t0[T::F_A * T::FSZ + oX - 1], fbL, cf - 1, xM, t0[T::F_A * T::FSZ + oX], xfb, cf,
+                    face_flux_v3<DIM, FLUX, 0>(P, gas, eL, t0[T::F_A * T::FSZ + oE - 1], fbL, cf - 1, eM, t0[T::F_A * T::FSZ + oE], efb, cf,
                                                alpha, S.prim_in, F);
                 }
 #pragma unroll
-                for (int q = 0; q < NCQ; ++q) fX[q * TY + hr] = F[q];
+                for (int q = 0; q < NCQ; ++q) fX[((it & 1) * NCQ + q) * TY + hr] = F[q];
             }
+            if (it > 0) mbar_wait(barF, (unsigned)((it - 1) & 1));      // the main warps have read last plane's states along j
+            halo_jobs(2, 3, t0, nullptr, 0);
+            cta_arrive(barR, lane);
+            if (DIM == 3) {
+                mbar_wait(barK, (unsigned)(it & 1));          // every main warp has read plane k - 1
+                if (lane == 0) issue_plane(m + 2);            // plane k + 2 -> its buffer (the last one needed is k1 + 1)
+            }
+            mbar_wait(barR, (unsigned)(it & 1));
             if (northE) {
-                const long long cf = crow + (long long)(j0 + TY + EB_NG) * NI + (i + EB_NG);
+                const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (j0 + TY + EB_NG)) * NI + (i + EB_NG);
                 double F[NCQ];
                 if (!outflow_override<DIM, 1>(P, D, S.prim_in, j0 + TY, njc, cf, sj, F)) {
                     double Ls[5];
@@ -373,17 +515,22 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
 #pragma unroll
                 for (int q = 0; q < NCQ; ++q) fS[(q * (TY + 1) + TY) * 32 + lane] = F[q];
             }
-            __syncthreads();                              // barrier F: fluxes are published
+            cta_arrive(barF, lane);
         }
         return;
     }
 
     // =============================== main warps: one thread per cell of the tile ================================
-    const int i = i0 + lane, j = j0 + wy;
-    const bool cell_ok = (i < nic) && (j < njc);
-    const bool faceW_ok = (i <= nic) && (j < njc);
-    const bool faceS_ok = (i < nic) && (j <= njc);
+    // (i, j and the predicates below are recomputed from shared memory where they are needed: the asm statements of
+    //  the barriers are compiler memory fences, so none of them stays in a register -- or worse, in a spill slot --
+    //  across the plane loop)
+#define i (s_ij[0] + lane)
+#define j (s_ij[1] + wy)
+#define cell_ok ((i < D.nic) && (j < D.njc))
+#define faceW_ok ((i <= D.nic) && (j < D.njc))
+#define faceS_ok ((i < D.nic) && (j <= D.njc))
     const int o = (wy + 2) * T::COLS + (lane + 2);          // own position in a tile field
+    double* const myU = uS + wy * 32 + lane;                // own staging slots, field q at stride TY*32
     double acc[NCQ], FB[NCQ];
     double kP[5];                                           // plus state along k of the cell one plane below
     bool kPfb = false;
@@ -400,137 +547,201 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
         bool fbM;
         load_cell5<DIM, TY>(tile_of(0), o, qm); load_cell5<DIM, TY>(tile_of(1), o, q0); load_cell5<DIM, TY>(tile_of(2), o, qp);
         recon_cell<DIM, CLIP>(D, 2, eps_k, qm, q0, qp, qM, kP, fbM, kPfb);
-        __syncthreads();            // plane k0 - 2 has been read: its buffer may be refilled
+    } else {
+        wait_plane(0);
     }
+    __syncthreads();            // start-up barrier: plane k0 - 2 has been read, the first west halo is published
 
     const int kend = (DIM == 3) ? k1 : 0;
-    for (int k = k0; k <= kend; ++k) {
-        const int m = (DIM == 3) ? k - k0 + 2 : 0;
+    long long c = D.cell0 + ((long long)(k0 + D.kg) * NJ + (j + EB_NG)) * NI + (i + EB_NG);      // own cell, plane k
+    int it = 0;
+    for (int k = k0; k <= kend; ++k, ++it, c += D.stride[2]) {
+        const int m = (DIM == 3) ? it + 2 : 0;
+        const unsigned par = (unsigned)(it & 1);
         const bool has_cells = (DIM == 3) ? (k < k1) : true;
         const double* t0 = tile_of(m);
-        const long long c = D.cell0 + ((long long)(k + D.kg) * NJ + (j + EB_NG)) * NI + (i + EB_NG);
-        double q0[5];
+        const bool finish_below = (DIM == 3) && (k > k0) && cell_ok;
+
+        // ---- 1. along k: own column in three tile buffers; the bottom face of this plane, which is the top face of
+        //         the cell one plane below: that cell's residual is complete, its new U goes to the staging slots
         if (DIM == 3) {
-            wait_plane(m + 1);
+#if EB_V3_TRYSPLIT
+            const unsigned landed = mbar_try(&s_bar[(m + 1) % 3], (unsigned)(((m + 1) / 3) & 1));   // plane k + 1
+#else
+            const unsigned landed = 0;
+#endif
             const double* tb = tile_of(m - 1);
             const double* ta = tile_of(m + 1);
-            double qm[5], qp[5], kM[5], kPn[5];
+            double qm[5], q0[5], qp[5], kM[5], kPn[5];
             bool fbM, fbP;
-            load_cell5<DIM, TY>(tb, o, qm); load_cell5<DIM, TY>(t0, o, q0); load_cell5<DIM, TY>(ta, o, qp);
+            load_cell5<DIM, TY>(tb, o, qm); load_cell5<DIM, TY>(t0, o, q0);
+            if (!landed) wait_plane(m + 1);
+            load_cell5<DIM, TY>(ta, o, qp);
             recon_cell<DIM, CLIP>(D, 2, eps_k, qm, q0, qp, kM, kPn, fbM, fbP);
+            const double aB = tb[T::F_A * T::FSZ + o];
+            if (has_cells) cta_arrive(barK, lane);        // plane k - 1 has left this warp's k-stencil
             if (cell_ok) {
-                if (!outflow_override<DIM, 2>(P, D, S.prim_in, k, nkc, c, sk, FB)) {
+                if (!outflow_override<DIM, 2>(P, D, S.prim_in, k, D.nkc, c, D.stride[2], FB)) {
                     const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[2][c] : 0.0;
-                    face_flux_v3<DIM, FLUX, 2>(P, gas, kP, tb[T::F_A * T::FSZ + o], kPfb, c - sk, kM, t0[T::F_A * T::FSZ + o], fbM, c,
-                                               alpha, S.prim_in, FB);
-                }
-                // finish the cell of the plane below: its top face is this plane's bottom face
-                if (k > k0) {
-                    const long long cp = c - sk;
-                    double dUdt[NCQ];
-#pragma unroll
-                    for (int q = 0; q < NCQ; ++q) { double si = acc[q] - FB[q] * D.area[2]; dUdt[q] = D.vol_inv * si + 0.0; }
-                    long long p0, p1, p2;
-                    push_targets<DIM>(D, i, j, k - 1, cp, p0, p1, p2);
-                    finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, cp, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
+                    face_flux_v3<DIM, FLUX, 2>(P, gas, kP, aB, kPfb, c - D.stride[2], kM, t0[T::F_A * T::FSZ + o], fbM, c, alpha, S.prim_in, FB);
                 }
             }
 #pragma unroll
             for (int v = 0; v < 5; ++v) kP[v] = kPn[v];
             kPfb = fbP;
-            if (!has_cells) break;                  // top face of the chunk: nothing else on this plane (uniform over the CTA)
-        } else {
-            wait_plane(0);
-            load_cell5<DIM, TY>(t0, o, q0);
+            if (finish_below) {
+                cp_async_wait_all();                      // U0 (and the first residual) staged during the last iteration
+                double U0p[NCQ], d0p[NCQ], dUb[NCQ], Un[NCQ];
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) {
+                    double si = acc[q] - FB[q] * D.area[2];
+                    dUb[q] = D.vol_inv * si + 0.0;
+                    U0p[q] = myU[q * TY * 32];
+                    d0p[q] = (S.stage != 1) ? myU[(NCQ + q) * TY * 32] : 0.0;
+                }
+                stage_update_v3<NCQ>(S, total, c - D.stride[2], U0p, d0p, dUb, Un);
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) myU[q * TY * 32] = Un[q];
+            }
+        }
+#ifdef EB_FAST_MATH
+        // throughput build: the surface integral is summed as the fluxes become available (B, W, E, S, N)
+        if (DIM == 3) {
+#pragma unroll
+            for (int q = 0; q < NCQ; ++q) acc[q] = FB[q] * D.area[2];
+        }
+#endif
+
+        double FW[NCQ], FS_[NCQ], FE[NCQ];
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q) { FW[q] = 0.0; FS_[q] = 0.0; FE[q] = 0.0; }
+        if (has_cells) {
+            // ---- 2. along j: own minus state; the plus state goes to the row above through shared memory
+            double jM[5];
+            bool jfbM;
+            {
+                double qm[5], q0[5], qp[5], jP[5];
+                bool fbP;
+                load_cell5<DIM, TY>(t0, o - T::COLS, qm); load_cell5<DIM, TY>(t0, o, q0); load_cell5<DIM, TY>(t0, o + T::COLS, qp);
+                recon_cell<DIM, CLIP>(D, 1, eps_j, qm, q0, qp, jM, jP, jfbM, fbP);
+                jP[1] = fold_flag(jP[1], fbP);
+#pragma unroll
+                for (int v = 0; v < 5; ++v) qPj[((wy + 1) * 5 + v) * 32 + lane] = jP[v];
+                cta_arrive(barR, lane);
+            }
+            // ---- 3. along i: the west neighbour's plus state by shuffle (lane 0: from the helper warp, published a plane ago)
+            {
+                double qm[5], q0[5], qp[5], iM[5], iP[5], Lw[5];
+                bool ifbM, fbP;
+                load_cell5<DIM, TY>(t0, o - 1, qm); load_cell5<DIM, TY>(t0, o, q0); load_cell5<DIM, TY>(t0, o + 1, qp);
+                recon_cell<DIM, CLIP>(D, 0, eps_i, qm, q0, qp, iM, iP, ifbM, fbP);
+                iP[1] = fold_flag(iP[1], fbP);
+#pragma unroll
+                for (int v = 0; v < 5; ++v) Lw[v] = __shfl_up_sync(0xffffffffu, iP[v], 1);
+                if (lane == 0) {
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) Lw[v] = qPiH[(((DIM == 3 ? k : k0) % 3) * 5 + v) * TY + wy];
+                }
+                if (faceW_ok) {
+                    if (!outflow_override<DIM, 0>(P, D, S.prim_in, i, D.nic, c, 1, FW)) {
+                        const bool fbL = unfold_flag(Lw[1]);
+                        const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[0][c] : 0.0;
+                        face_flux_v3<DIM, FLUX, 0>(P, gas, Lw, t0[T::F_A * T::FSZ + o - 1], fbL, c - 1, iM, t0[T::F_A * T::FSZ + o], ifbM, c,
+                                                   alpha, S.prim_in, FW);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) FE[q] = __shfl_down_sync(0xffffffffu, FW[q], 1);
+#ifdef EB_FAST_MATH
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) {
+                    acc[q] = fma(FW[q], D.area[0], acc[q]);
+                    if (lane != 31) acc[q] = fma(-FE[q], D.area[0], acc[q]);
+                }
+#endif
+            }
+            // ---- 4. the south face, once the row below has published its plus state
+            mbar_wait(barR, par);
+            if (faceS_ok) {
+                if (!outflow_override<DIM, 1>(P, D, S.prim_in, j, D.njc, c, D.stride[1], FS_)) {
+                    double Ls[5];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) Ls[v] = qPj[(wy * 5 + v) * 32 + lane];
+                    const bool fbL = unfold_flag(Ls[1]);
+                    const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[1][c] : 0.0;
+                    face_flux_v3<DIM, FLUX, 1>(P, gas, Ls, t0[T::F_A * T::FSZ + o - T::COLS], fbL, c - D.stride[1], jM, t0[T::F_A * T::FSZ + o], jfbM, c,
+                                               alpha, S.prim_in, FS_);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NCQ; ++q) fS[(q * (TY + 1) + wy) * 32 + lane] = FS_[q];
+            cta_arrive(barF, lane);
+#ifdef EB_FAST_MATH
+#pragma unroll
+            for (int q = 0; q < NCQ; ++q) acc[q] = fma(FS_[q], D.area[1], acc[q]);
+#endif
         }
 
-        // ---- along i: own minus state, the west neighbour's plus state by shuffle
-        double iM[5], Lw[5];
-        bool ifbM;
-        {
-            double qm[5], qp[5], iP[5];
-            bool fbP;
-            load_cell5<DIM, TY>(t0, o - 1, qm); load_cell5<DIM, TY>(t0, o + 1, qp);
-            recon_cell<DIM, CLIP>(D, 0, eps_i, qm, q0, qp, iM, iP, ifbM, fbP);
-            iP[1] = fold_flag(iP[1], fbP);
+        // ---- 5. decode and store the cell one plane below while the fluxes of the other rows arrive; then stage U0
+        //         (and the first residual) of this plane's cell for the next iteration
+        if (DIM == 3) {
+            if (finish_below) {
+                double Un[NCQ];
 #pragma unroll
-            for (int v = 0; v < 5; ++v) Lw[v] = __shfl_up_sync(0xffffffffu, iP[v], 1);
-            if (lane == 31) {
-#pragma unroll
-                for (int v = 0; v < 5; ++v) qPiX[v * TY + wy] = iP[v];
-            }
-        }
-        // ---- along j: own minus state, own plus state to the row above through shared memory
-        double jM[5];
-        bool jfbM;
-        {
-            double qm[5], qp[5], jP[5];
-            bool fbP;
-            load_cell5<DIM, TY>(t0, o - T::COLS, qm); load_cell5<DIM, TY>(t0, o + T::COLS, qp);
-            recon_cell<DIM, CLIP>(D, 1, eps_j, qm, q0, qp, jM, jP, jfbM, fbP);
-            jP[1] = fold_flag(jP[1], fbP);
-#pragma unroll
-            for (int v = 0; v < 5; ++v) qPj[((wy + 1) * 5 + v) * 32 + lane] = jP[v];
-        }
-        __syncthreads();                                  // barrier R: plus states are published
-
-        double FW[NCQ], FS_[NCQ];
-#pragma unroll
-        for (int q = 0; q < NCQ; ++q) { FW[q] = 0.0; FS_[q] = 0.0; }
-        if (lane == 0) {
-#pragma unroll
-            for (int v = 0; v < 5; ++v) Lw[v] = qPiH[v * TY + wy];
-        }
-        if (faceW_ok) {
-            if (!outflow_override<DIM, 0>(P, D, S.prim_in, i, nic, c, 1, FW)) {
-                const bool fbL = unfold_flag(Lw[1]);
-                const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[0][c] : 0.0;
-                face_flux_v3<DIM, FLUX, 0>(P, gas, Lw, t0[T::F_A * T::FSZ + o - 1], fbL, c - 1, iM, t0[T::F_A * T::FSZ + o], ifbM, c,
-                                           alpha, S.prim_in, FW);
-            }
-        }
-        if (faceS_ok) {
-            if (!outflow_override<DIM, 1>(P, D, S.prim_in, j, njc, c, sj, FS_)) {
-                double Ls[5];
-#pragma unroll
-                for (int v = 0; v < 5; ++v) Ls[v] = qPj[(wy * 5 + v) * 32 + lane];
-                const bool fbL = unfold_flag(Ls[1]);
-                const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[1][c] : 0.0;
-                face_flux_v3<DIM, FLUX, 1>(P, gas, Ls, t0[T::F_A * T::FSZ + o - T::COLS], fbL, c - sj, jM, t0[T::F_A * T::FSZ + o], jfbM, c,
-                                           alpha, S.prim_in, FS_);
-            }
-        }
-        double FE[NCQ];
-#pragma unroll
-        for (int q = 0; q < NCQ; ++q) {
-            FE[q] = __shfl_down_sync(0xffffffffu, FW[q], 1);
-            fS[(q * (TY + 1) + wy) * 32 + lane] = FS_[q];
-        }
-        __syncthreads();                                  // barrier F: fluxes are published
-
-        if (cell_ok) {
-#pragma unroll
-            for (int q = 0; q < NCQ; ++q) {
-                const double fe = (lane == 31) ? fX[q * TY + wy] : FE[q];
-                const double fn = fS[(q * (TY + 1) + wy + 1) * 32 + lane];
-                double si = FW[q] * D.area[0];          // 0 - F*(-A), summation order W, E, S, N, B, T (fvcell.d:824-854)
-                si = si - fe * D.area[0];
-                si = si + FS_[q] * D.area[1];
-                si = si - fn * D.area[1];
-                if (DIM == 3) si = si + FB[q] * D.area[2];
-                acc[q] = si;
-            }
-            if (DIM == 2) {
-                double dUdt[NCQ];
-#pragma unroll
-                for (int q = 0; q < NCQ; ++q) dUdt[q] = D.vol_inv * acc[q] + 0.0;
+                for (int q = 0; q < NCQ; ++q) Un[q] = myU[q * TY * 32];
+                const long long cp = c - D.stride[2];
                 long long p0, p1, p2;
-                push_targets<DIM>(D, i, j, 0, c, p0, p1, p2);
-                finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, c, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
+                push_targets<DIM>(D, i, j, k - 1, cp, p0, p1, p2);
+                decode_store_v3<DIM>(P, gas, S, total, cp, Un, p0, p1, p2);
+            }
+            if (has_cells && cell_ok) {
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) cp_async8(myU + q * TY * 32, S.U0 + q * total + c);
+                if (S.stage != 1) {
+#pragma unroll
+                    for (int q = 0; q < NCQ; ++q) cp_async8(myU + (NCQ + q) * TY * 32, S.dUdt_prev[0] + q * total + c);
+                }
+                cp_async_commit();
+            }
+        }
+
+        // ---- 6. the rest of the surface integral of this plane's cell (all but the top face)
+        if (has_cells) {
+            mbar_wait(barF, par);
+            if (cell_ok) {
+#pragma unroll
+                for (int q = 0; q < NCQ; ++q) {
+                    const double fe = (lane == 31) ? fX[((int)par * NCQ + q) * TY + wy] : FE[q];
+                    const double fn = fS[(q * (TY + 1) + wy + 1) * 32 + lane];
+#ifdef EB_FAST_MATH
+                    double si = fma(-fn, D.area[1], acc[q]);
+                    if (lane == 31) si = fma(-fe, D.area[0], si);
+#else
+                    double si = FW[q] * D.area[0];          // 0 - F*(-A), summation order W, E, S, N, B, T (fvcell.d:824-854)
+                    si = si - fe * D.area[0];
+                    si = si + FS_[q] * D.area[1];
+                    si = si - fn * D.area[1];
+                    if (DIM == 3) si = si + FB[q] * D.area[2];
+#endif
+                    acc[q] = si;
+                }
+                if (DIM == 2) {
+                    double dUdt[NCQ];
+#pragma unroll
+                    for (int q = 0; q < NCQ; ++q) dUdt[q] = D.vol_inv * acc[q] + 0.0;
+                    long long p0, p1, p2;
+                    push_targets<DIM>(D, i, j, 0, c, p0, p1, p2);
+                    finish_cell<DIM, EB200_GAS_IDEAL, 1>(P, gas, S, total, c, dUdt, fail, n_invalid, nullptr, nullptr, p0, p1, p2);
+                }
             }
         }
     }
 
+#undef i
+#undef j
+#undef cell_ok
+#undef faceW_ok
+#undef faceS_ok
     unsigned any_fail = __ballot_sync(0xffffffffu, fail);
     int inv = n_invalid;
 #pragma unroll
@@ -545,7 +756,7 @@ template <int DIM, int FLUX, bool CLIP>
 void launch_one_v3(const EbParams& P, const EbGas* gas, const EbBlockDesc* desc, int nblocks, long long ncta,
                    const EbArena& A, const EbStageArgs& S, cudaStream_t st)
 {
-    constexpr int TY = EB_V2_TY;
+    constexpr int TY = EB_V3_TY;
     const size_t smem = V3Smem<DIM, TY>::BYTES;
     auto kern = flux_update_kernel_v3<DIM, FLUX, CLIP, TY>;
     static bool configured = false;
