@@ -104,25 +104,44 @@ class ClockSampler:
         return out
 
 
-def build_case(args, workload):
+def spec_of(args, workload=None, **over):
+    """A workload description: the command-line defaults with overrides (used for the `also` entries)."""
+    d = {"workload": workload or args.workload, "n": args.n, "nb": args.nb, "flux": args.flux, "sheared": args.sheared,
+         "dt_scale": args.dt_scale, "ffs_nx": args.ffs_nx, "ffs_ny": args.ffs_ny, "kernel": args.kernel}
+    d.update(over)
+    return d
+
+
+def build_case(spec):
     from gdtk_b200 import cases
-    if workload == "ffs":
-        cfg, gm, blocks = cases.ffs(nx=args.ffs_nx, ny=args.ffs_ny, flux_calculator=args.flux)
-        name = f"synthetic 2D Mach-3 forward-facing step {args.ffs_nx}x{args.ffs_ny}, 3 blocks, ideal air, l2r2+van Albada, {args.flux}, pc"
+    w = spec["workload"]
+    if w == "ffs":
+        cfg, gm, blocks = cases.ffs(nx=spec["ffs_nx"], ny=spec["ffs_ny"], flux_calculator=spec["flux"])
+        name = f"synthetic 2D Mach-3 forward-facing step {spec['ffs_nx']}x{spec['ffs_ny']}, 3 blocks, ideal air, l2r2+van Albada, {spec['flux']}, pc"
         balg = 224.0
-    elif workload == "tpg":
-        cfg, gm, blocks = cases.tpg_box3d(n=args.n, nb=args.nb, flux_calculator=args.flux)
-        name = (f"synthetic 3D {args.n}^3 thermally perfect 5-species air box (frozen chemistry), {args.nb ** 3} blocks of "
-                f"{args.n // args.nb}^3, l2r2+van Albada, {args.flux}, pc")
+    elif w == "tpg":
+        cfg, gm, blocks = cases.tpg_box3d(n=spec["n"], nb=spec["nb"], flux_calculator=spec["flux"])
+        name = (f"synthetic 3D {spec['n']}^3 thermally perfect 5-species air box (frozen chemistry), {spec['nb'] ** 3} blocks of "
+                f"{spec['n'] // spec['nb']}^3, l2r2+van Albada, {spec['flux']}, pc")
         balg = 560.0
     else:
-        cfg, gm, blocks = cases.box3d(n=args.n, nb=args.nb, flux_calculator=args.flux, sheared=args.sheared)
-        name = (f"synthetic 3D {args.n}^3 ideal-air box, {args.nb ** 3} blocks of {args.n // args.nb}^3, "
-                f"{'k-lines sheared by 10 degrees (general-metric path)' if args.sheared else 'uniform Cartesian'}, "
-                f"l2r2+van Albada, {args.flux}, pc")
-        balg = 280.0
-    cfg.force_generic_kernel = {"auto": 0, "generic": 1, "v2": 2}[args.kernel]
+        cfg, gm, blocks = cases.box3d(n=spec["n"], nb=spec["nb"], flux_calculator=spec["flux"], sheared=spec["sheared"])
+        name = (f"synthetic 3D {spec['n']}^3 ideal-air box, {spec['nb'] ** 3} blocks of {spec['n'] // spec['nb']}^3, "
+                f"{'k-lines sheared by 10 degrees (general-metric path)' if spec['sheared'] else 'uniform Cartesian'}, "
+                f"l2r2+van Albada, {spec['flux']}, pc")
+        # BASELINE.md section 2: 280 B per cell-update; general-metric blocks read 272 B of metrics per stage on top
+        balg = 824.0 if spec["sheared"] else 280.0
+    cfg.force_generic_kernel = {"auto": 0, "generic": 1, "v2": 2}[spec["kernel"]]
     return cfg, gm, blocks, name, balg
+
+
+def kernel_name(spec):
+    """Which fused flux+update kernel the library picks for this workload (same rule as gdtk_b200/csrc/flux_inst.cu)."""
+    if spec["kernel"] == "generic" or spec["workload"] == "tpg":
+        return "flux_update_kernel (generic)"
+    if spec["workload"] == "box3d" and spec["sheared"]:
+        return "flux_update_kernel_v2 (face-centred, general metric)"
+    return "flux_update_kernel_v2 (face-centred)" if spec["kernel"] == "v2" else "flux_update_kernel_v3 (cell-centred, uniform Cartesian)"
 
 
 def cfl_dt(sim, scale=1.0):
@@ -131,20 +150,26 @@ def cfl_dt(sim, scale=1.0):
     return dt_allow * scale
 
 
-def run_gpu_workload(args, workload, rank, world, local_rank, with_e2e):
-    import torch
+def make_sim(spec, world, local_rank):
     from gdtk_b200 import Simulation
     from gdtk_b200.distributed import DistributedSimulation, octant_owner, distribute_blocks
-    cfg, gm, blocks, name, balg = build_case(args, workload)
-    t_setup = time.time()
+    cfg, gm, blocks, name, balg = build_case(spec)
     if world > 1:
-        if workload == "box3d" and cfg.block_index:
-            owner = octant_owner({v: next(b for b in blocks if b.id == k) for k, v in cfg.block_index.items()}, args.nb, world)
+        if spec["workload"] in ("box3d", "tpg") and cfg.block_index:
+            owner = octant_owner({v: next(b for b in blocks if b.id == k) for k, v in cfg.block_index.items()}, spec["nb"], world)
         else:
             owner = distribute_blocks(blocks, world)
         sim = DistributedSimulation(cfg, gm, blocks, owner, device=local_rank)
     else:
         sim = Simulation(cfg, gm, blocks, device=local_rank)
+    return sim, name, balg
+
+
+def run_gpu_workload(args, spec, rank, world, local_rank, with_e2e=False, with_real_loop=False, steps=None):
+    import torch
+    steps = steps or args.steps
+    t_setup = time.time()
+    sim, name, balg = make_sim(spec, world, local_rank)
     t_setup = time.time() - t_setup
     lib, h = sim.lib, sim.handle
     ncells_local = int(sim.n_local_cells)
@@ -154,7 +179,7 @@ def run_gpu_workload(args, workload, rank, world, local_rank, with_e2e):
         t = torch.tensor([ncells_local], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         ncells = int(t.item())
-    dt = cfl_dt(sim, args.dt_scale)
+    dt = cfl_dt(sim, spec["dt_scale"])
     ext = torch.cuda.ExternalStream(int(lib.cuda_stream(h)))
 
     def barrier():
@@ -174,7 +199,7 @@ def run_gpu_workload(args, workload, rank, world, local_rank, with_e2e):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
-    sim.run_fixed(args.steps, dt)
+    sim.run_fixed(steps, dt)
     e1.record(ext)
     e1.synchronize()
     barrier()
@@ -190,41 +215,78 @@ def run_gpu_workload(args, workload, rank, world, local_rank, with_e2e):
         t = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         launches = int(t.item())
-    value = ncells * args.steps / (ms * 1e-3)
+    value = ncells * steps / (ms * 1e-3)
     peak, peak_src = measured_peak()
-    # dominant kernel: the fused flux+update kernel, 2 launches (stages) per step per rank
-    flux_bytes = balg * ncells_local * args.steps            # algorithmic bytes this rank's launches moved
+    # dominant kernel: the fused flux+update kernel, one launch per stage and rank
+    flux_bytes = balg * ncells_local * steps                 # algorithmic bytes this rank's launches moved
     achieved = flux_bytes / (flux_ms * 1e-3) / 1e9 if flux_ms > 0 else 0.0
-    # DRAM traffic of the dominant kernel per launch: bytes per cell measured by `ncu --set full`
-    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json) x the cells one launch processes
+    # DRAM traffic and FP64-pipe instructions of the dominant kernel per cell and launch, from the committed
+    # `ncu --set full` capture of the metric configuration (profiles/r2_traffic.json) x the cells one launch processes
     traffic = None
     fp64 = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if workload == "box3d" and args.flux == "ausmdv" and os.path.exists(tpath):
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    is_metric_config = spec["workload"] == "box3d" and spec["flux"] == "ausmdv" and not spec["sheared"] and spec["kernel"] == "auto"
+    if is_metric_config and os.path.exists(tpath):
         with open(tpath) as f:
             prof = json.load(f)
         traffic = prof["dram_bytes_per_cell_per_launch"] * ncells_local
-        # the kernel is bound by the FP64 pipe / instruction issue, not by HBM: place it against the FP64 pipe too.
-        # FP64-pipe instructions per cell and launch come from the same ncu capture, the pipe's peak from
-        # profiles/micro/fp64_peak.cu run on this pool's B200 (thread-level DFMA/s).
-        inst = prof["fp64_pipe_inst_per_cell_per_launch"] * ncells_local * args.steps * 2
-        fp64 = {"achieved": inst / (flux_ms * 1e-3) / 1e12, "peak": prof["fp64_pipe_peak_tinst_s"], "unit": "T inst/s (thread-level FP64-pipe instructions)",
+        # the kernel is bound by the FP64 pipe / instruction issue, not by HBM: place it against the FP64 pipe too
+        # (peak measured with profiles/micro/fp64_peak.cu on this pool's B200, thread-level DFMA/s)
+        inst = prof["fp64_pipe_inst_per_cell_per_launch"] * ncells_local * steps * 2
+        fp64 = {"achieved": inst / (flux_ms * 1e-3) / 1e12, "peak": prof["fp64_pipe_peak_tinst_s"],
+                "unit": "T inst/s (thread-level FP64-pipe instructions)",
                 "frac": inst / (flux_ms * 1e-3) / 1e12 / prof["fp64_pipe_peak_tinst_s"],
                 "note": "instructions per cell from the ncu capture in profiles/ (DFMA+DMUL+DADD+DSETP); peak measured with profiles/micro/fp64_peak.cu"}
     result = {
-        "name": name, "value": value, "ms": ms, "ncells": ncells, "dt": dt, "launches": launches,
+        "name": name, "value": value, "ms": ms, "steps": steps, "ncells": ncells, "dt": dt, "launches": launches,
         "setup_s": t_setup, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per cell (256^3 capture, profiles/r1_traffic.json) x cells per launch; algorithmic = 140 B per cell per launch (280 B per cell-update over the 2 stage launches)", "peak_source": peak_src, "kernel": "flux_update_kernel",
+                     "traffic": traffic,
+                     "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per cell (256^3 capture, profiles/r2_traffic.json) x cells per launch; "
+                                     "algorithmic = half of algorithmic_bytes_per_cell_update per launch (two stage launches per step)",
+                     "peak_source": peak_src, "kernel": kernel_name(spec),
                      "algorithmic_bytes_per_cell_update": balg, "kernel_ms_per_launch": flux_ms / max(1, flux_n),
                      "kernel_share_of_step": flux_ms / ms if ms > 0 else None},
     }
     if fp64:
         result["fp64_pipe"] = fp64
+    if with_real_loop:
+        result["real_loop"] = run_real_loop(args, sim, dt, ncells, world, ext, steps)
     if with_e2e:
         result["e2e"] = run_e2e(args, sim, dt, ncells, world)
     sim.close()
     return result
+
+
+def run_real_loop(args, sim, dt, ncells, world, ext, steps):
+    """The loop the D shim runs (integrate_in_time): determine_time_step_size every cfl_count = 10 steps
+    (eb200_compute_dt + the min over ranks) and eb200_step with its status read-back every step, instead of
+    eb200_run_steps' fixed dt without host synchronisation."""
+    import torch
+    nbad = C.c_int(0)
+    lib, h = sim.lib, sim.handle
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for n in range(steps):
+        if n % 10 == 0:
+            dt = min(dt, cfl_dt(sim))
+        rc = lib.step(h, 0.0, dt, C.byref(nbad))
+        if rc != 0:
+            raise RuntimeError(f"real-loop step returned {rc}: {lib.error()}")
+    e1.record(ext)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"value": ncells * steps / (ms * 1e-3), "unit": "cell-updates/s", "steps": steps,
+            "note": "eb200_compute_dt (+ min over ranks) every 10 steps and eb200_step with status read-back every step"}
 
 
 def run_e2e(args, sim, dt, ncells, world):
@@ -271,9 +333,82 @@ def run_e2e(args, sim, dt, ncells, world):
         t = torch.tensor([el], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         el = float(t[0])
+    if world > 1:
+        h2d_t = torch.tensor([h2d, d2h], dtype=torch.int64, device="cuda")
+        import torch.distributed as dist
+        dist.all_reduce(h2d_t)
+        h2d, d2h = int(h2d_t[0]), int(h2d_t[1])
     return {"value": ncells * nsteps / el, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": nsteps,
-            "note": "eb200_upload_flow + eb200_step + eb200_download_flow per step, pinned host buffers"}
+            "note": "eb200_upload_flow + eb200_step + eb200_download_flow per step, pinned host buffers (bytes summed over ranks)"}
+
+
+def run_parity_check(args, rank, world, local_rank):
+    """N-GPU == 1-GPU, bit for bit: a small box (8 blocks of 32^3, one or more per rank) advanced 10 steps with the
+    blocks spread over the ranks, against the same job with all blocks on this rank's GPU; every rank compares the
+    conserved quantities of its own blocks.  Untimed; the halo exchange is a pure copy, so equality is exact."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gdtk_b200 import Simulation
+    spec = spec_of(args, "box3d", n=64, nb=2, flux=args.flux, sheared=False)
+    nsteps = 10
+    dsim, _, _ = make_sim(spec, world, local_rank)
+    dt = cfl_dt(dsim)
+    dsim.run_fixed(nsteps, dt)
+    mine = {b.id: [a.copy() for a in dsim.download_conserved(b.id)] for b in dsim.local_blocks}
+    dsim.close()
+    cfg, gm, blocks, _, _ = build_case(spec)
+    ssim = Simulation(cfg, gm, blocks, device=local_rank)
+    ssim.run_fixed(nsteps, dt)
+    ok = 1
+    worst = 0.0
+    for bid, arrs in mine.items():
+        for a, r in zip(arrs, ssim.download_conserved(bid)):
+            ia, ir = ssim.interior(bid, a), ssim.interior(bid, r)
+            if not np.array_equal(ia, ir):
+                ok = 0
+                worst = max(worst, float(np.max(np.abs(ia - ir) / np.maximum(np.abs(ir), 1e-300))))
+    ssim.close()
+    t = torch.tensor([ok, -worst], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"case": f"3D 64^3 ideal-air box, 8 blocks of 32^3 over {world} ranks, {args.flux}, pc, {nsteps} steps at the CFL step",
+            "compared": "conserved quantities of every block, multi-rank run vs all blocks on one GPU", "bit_equal": bool(t[0] > 0.5),
+            "max_rel_diff": -float(t[1])}
+
+
+def run_chicken(args, n=256, steps=30):
+    """The reference's own CUDA solver (src/chicken, compiled for sm_100a into oracle/_ref/chkn-run by oracle/Makefile)
+    on the same box: 3D ideal-air box, 2 x 2 x 2 blocks, AUSMDV, second-order van Albada reconstruction, TVD-RK3
+    (three stages per step; the product's predictor-corrector has two -- compare per stage).  Timed from the wall
+    clock chicken prints with its step count."""
+    import re
+    import shutil
+    exe = os.path.join(ROOT, "oracle", "_ref", "chkn-run")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/chkn-run is not built (needs the reference sources: make -C oracle chicken)"}
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "chicken"))
+    from make_job import make_job
+    last_err = "no attempt"
+    for size in (n, n // 2):
+        tmp = tempfile.mkdtemp(prefix="chkn_")
+        try:
+            cells = make_job(os.path.join(tmp, "box"), size, max_step=steps, print_count=max(1, steps // 3))
+            r = subprocess.run([exe, "--job=box", "--binary"], cwd=tmp, capture_output=True, text=True, timeout=600)
+            marks = [(int(m.group(1)), float(m.group(2))) for m in re.finditer(r"Step=(\d+) .*? WC=([0-9.eE+-]+)s", r.stdout)]
+            if len(marks) >= 2 and marks[-1][1] > marks[0][1]:
+                (s0, w0), (s1, w1) = marks[0], marks[-1]
+                per_step = cells * (s1 - s0) / (w1 - w0)
+                return {"value": per_step, "unit": "cell-updates/s", "stages_per_step": 3, "cell_stage_updates_per_s": 3.0 * per_step,
+                        "workload": f"chicken (reference src/chicken, -arch=sm_100a, FP64): 3D {size}^3 ideal-air box, 8 blocks of {size // 2}^3, "
+                                    f"ausmdv, x_order 2, TVD-RK3, steps {s0}..{s1} by its own wall clock",
+                        "n_gpus": 1}
+            last_err = (r.stderr or r.stdout)[-300:].strip().replace("\n", " | ")
+        except Exception as e:
+            last_err = f"{type(e).__name__}: {e}"
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return {"unavailable": f"chkn-run did not produce two progress lines: {last_err}"}
 
 
 def oracle_library():
@@ -289,9 +424,19 @@ def run_cpu_sample(args, target_seconds, steps=None, warmup=1):
     parallel foreach / one block per MPI rank) on a bounded sample of the 3D workload."""
     from gdtk_b200 import Simulation, cases
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    # torchrun exports OMP_NUM_THREADS=1: set the thread count explicitly, before libgomp reads the environment,
+    # and again through the library; what the library then reports is what goes into the JSON line
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     lib = oracle_library()
+    fn = lib.cdll.orc_omp_threads
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int]
     n, nb = args.cpu_n, args.cpu_nb
+    omp_threads = int(fn(cores))
     cfg, gm, blocks = cases.box3d(n=n, nb=nb, flux_calculator=args.flux)
     sim = Simulation(cfg, gm, blocks, lib=lib)
     dt = cfl_dt(sim)
@@ -305,10 +450,11 @@ def run_cpu_sample(args, target_seconds, steps=None, warmup=1):
     sim.run_fixed(steps, dt)
     el = time.perf_counter() - t0
     sim.close()
-    threads = min(cores, nb ** 3)
+    threads = min(omp_threads, nb ** 3)         # the oracle never uses more threads than blocks
     return {"value": ncells * steps / el, "unit": "cell-updates/s", "cores": threads, "kind": "port",
             "sample": f"{n}^3 cells in {nb ** 3} blocks of {n // nb}^3 (same job as the GPU workload at reduced size), "
-                      f"{steps} predictor-corrector steps, {el:.1f} s, OpenMP over blocks on {threads} of {cores} host cores",
+                      f"{steps} predictor-corrector steps, {el:.1f} s, OpenMP over blocks: {threads} threads "
+                      f"(omp_get_max_threads = {omp_threads}, {cores} host cores available to this process)",
             "ms_per_step": el / steps * 1e3, "steps": steps}
 
 
@@ -335,7 +481,7 @@ def main():
     ap.add_argument("--cpu-nb", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE configurations and the multi-GPU parity check")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -372,12 +518,43 @@ def main():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
         except Exception:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    main_res = run_gpu_workload(args, args.workload, rank, world, local_rank, with_e2e=True)
+    main_spec = spec_of(args)
+    main_res = run_gpu_workload(args, main_spec, rank, world, local_rank, with_e2e=True, with_real_loop=True)
     also = {}
-    if world == 1 and args.workload == "box3d" and not args.no_also:
-        r = run_gpu_workload(args, "ffs", rank, world, local_rank, with_e2e=False)
-        also["ffs"] = {"workload": r["name"], "value": r["value"], "unit": "cell-updates/s",
-                       "roofline_frac": r["roofline"]["frac"], "ms_per_step": r["ms"] / args.steps}
+
+    def entry(r, spec):
+        e = {"workload": r["name"], "value": r["value"], "unit": "cell-updates/s", "n_gpus": world,
+             "ms_per_step": r["ms"] / r["steps"], "steps": r["steps"], "kernel": r["roofline"]["kernel"],
+             "algorithmic_bytes_per_cell_update": r["roofline"]["algorithmic_bytes_per_cell_update"],
+             "roofline_frac": r["roofline"]["frac"], "kernel_ms_per_launch": r["roofline"]["kernel_ms_per_launch"]}
+        if spec["dt_scale"] != 1.0:
+            e["dt_scale"] = spec["dt_scale"]
+        return e
+
+    if args.workload == "box3d" and not args.no_also and args.n == 512 and not args.sheared:
+        # the other BASELINE.json configurations, each a short run of the same kind
+        others = []
+        if world == 1:
+            others.append(("ffs_4096x1024", spec_of(args, "ffs", flux="ausmdv")))
+            others.append(("box3d_256_general_metric", spec_of(args, "box3d", n=256, nb=2, sheared=True, flux="ausmdv")))
+            for fx in ("hanel", "ldfss0", "ldfss2", "roe", "ausm_plus_up", "adaptive_hanel_ausmdv"):
+                # ausm_plus_up is not stable at the full CFL step on the noisy box (in the oracle either): a quarter step
+                others.append((f"box3d_256_{fx}", spec_of(args, "box3d", n=256, nb=2, flux=fx, dt_scale=0.25 if fx == "ausm_plus_up" else 1.0)))
+        # configs[4]: thermally perfect 5-species air 256^3, on one GPU and spread over the GPUs of the run
+        others.append(("tpg_256", spec_of(args, "tpg", n=256, nb=(2 if world == 1 else 4), flux="ausmdv")))
+        for key, sp in others:
+            try:
+                r = run_gpu_workload(args, sp, rank, world, local_rank, steps=min(args.steps, 5))
+                also[key] = entry(r, sp)
+            except Exception as e:       # an `also` entry must never take the headline line down with it
+                also[key] = {"error": f"{type(e).__name__}: {e}"}
+    if world == 1 and rank == 0 and args.workload == "box3d" and not args.no_also and args.n == 512 and not args.sheared:
+        also["chicken"] = run_chicken(args)
+        pc_stages = 2.0
+        also["chicken"]["ours_cell_stage_updates_per_s"] = pc_stages * main_res["value"]
+    parity = None
+    if world > 1 and not args.no_also:
+        parity = run_parity_check(args, rank, world, local_rank)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_cpu_sample(args, args.cpu_seconds)
@@ -388,11 +565,14 @@ def main():
             "ms_per_step": main_res["ms"] / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": main_res["name"], "cells": main_res["ncells"], "dt": main_res["dt"],
-                       "parallelism": f"blocks over {world} GPU(s), NCCL halo exchange per stage" if world > 1 else "single GPU",
+                       "parallelism": f"blocks over {world} GPU(s), halo exchange per stage" if world > 1 else "single GPU",
+                       "timed_region": "eb200_run_steps: fixed dt, no host synchronisation between steps; "
+                                       "`real_loop` is the same steps with eb200_compute_dt every 10 steps and eb200_step's status read-back",
                        "l2_policy": "state arrays (tens of GB) far exceed the 126 MB L2; no flush needed",
                        "setup_s": round(main_res["setup_s"], 1)},
             "roofline": main_res["roofline"],
             "e2e": main_res.get("e2e"),
+            "real_loop": main_res.get("real_loop"),
             "gpu_launches": main_res["launches"],
             "clocks": main_res["clocks"],
         }
@@ -400,6 +580,8 @@ def main():
             line["fp64_pipe"] = main_res["fp64_pipe"]
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if parity:
+            line["parity_check"] = parity
         if also:
             line["also"] = also
         print(json.dumps(line))

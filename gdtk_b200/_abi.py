@@ -119,6 +119,10 @@ SIGNATURES = {
     "run_steps": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int)]),
     "block_is_cartesian": (C.c_int, [C.c_int, C.c_int]),
     "cuda_stream": (C.c_void_p, [C.c_int]),
+    "undo_step": (C.c_int, [C.c_int]),
+    "p2p_export": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "p2p_import": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "describe": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     "debug_face_flux": (C.c_int, [C.c_int, C.c_int, DP, DP, DP, DP, C.POINTER(C.c_int)]),
 }
 

@@ -65,6 +65,28 @@ struct Peer {
     std::vector<int> send_idx, recv_idx;      // arena indices
     int *d_send_idx = nullptr, *d_recv_idx = nullptr;
     double *d_send = nullptr, *d_recv = nullptr;
+    // direct halo over NVLink (eb200_p2p_export / eb200_p2p_import): the peer's arena mapped through CUDA IPC
+    bool p2p = false;
+    long long recv_off = 0;                   // byte offset of my recv index list for this peer inside the shared region
+    double* r_prim[3] = { nullptr, nullptr, nullptr };
+    double* r_S = nullptr;
+    unsigned long long* r_flag = nullptr;     // the peer's flag that I raise
+    long long r_total = 0;
+    int* d_dst_idx = nullptr;                 // the peer's ghost cells (its arena indices) in wire order
+    std::vector<void*> opened;
+};
+
+#define EB_P2P_MAGIC 0x65623270u
+#define EB_P2P_MAXPEERS 64
+struct P2PBlob {                              // what a rank tells one peer about itself; plain data, moved by the host layer
+    unsigned magic;
+    int exporter_rank, nprim, has_S;
+    long long total;                          // field stride of the exporter's arena
+    cudaIpcMemHandle_t prim[3]; long long prim_off[3];
+    cudaIpcMemHandle_t S; long long S_off;
+    cudaIpcMemHandle_t shared; long long shared_off;   // the exporter's shared region: flags, then its recv index lists
+    long long flag_off;                       // inside the region: the flag the importer raises
+    long long recv_idx_off, recv_count;       // inside the region: the exporter's ghost cells the importer fills, wire order
 };
 
 struct Sim {
@@ -90,6 +112,10 @@ struct Sim {
     EbFillItem* d_fill = nullptr; long long nfill = 0;
     double* d_params = nullptr;
     std::vector<Peer> peers;
+    char* d_shared = nullptr; size_t shared_bytes = 0;       // flags[EB_P2P_MAXPEERS] + recv index lists, one allocation = one IPC handle
+    unsigned long long** d_remote_flags = nullptr;           // device array: r_flag of every peer
+    unsigned long long halo_seq = 0;
+    bool p2p_ready = false;
     eb200_exchange_fn exchange = nullptr; void* exchange_user = nullptr;
     int* d_status = nullptr; int* h_status = nullptr;
     unsigned long long* d_red = nullptr; double* d_last = nullptr;
@@ -99,6 +125,7 @@ struct Sim {
     cudaEvent_t ev_pack = nullptr, ev_comm = nullptr, ev_ghost = nullptr, ev_bnd = nullptr;
     int* d_tiles_int = nullptr; long long n_tiles_int = 0;   // tiles that read no ghost cell of another rank
     int* d_tiles_bnd = nullptr; long long n_tiles_bnd = 0;   // tiles that do
+    int undo_cur = -1;                        // >= 0: the last step succeeded and can be taken back (eb200_undo_step)
     int cur = 0;                              // index of the primitive buffer holding the current state
     int U0 = 0;                               // index of the U level that currently plays U[0]
     std::vector<int> Ulev;                    // permutation of U levels (swap at the end of a step)
@@ -371,9 +398,25 @@ int drain_flux_events(Sim* s)
 // Halo traffic with other processes (phase 02 of the reference step): pack on the main stream,
 // then callback + unpack on the communication stream so that the main stream can meanwhile work on
 // tiles that do not touch those ghost cells.  ev_comm is recorded when the ghost cells are in place.
-int exchange_remote(Sim* s, double* prim)
+int exchange_remote(Sim* s, double* prim, int buf)
 {
     if (s->peers.empty()) return 0;
+    if (s->p2p_ready) {
+        // direct stores into the neighbours' ghost cells, a flag per peer; no host code, no staging buffers
+        const int np = (int)s->peers.size();
+        const unsigned long long seq = ++s->halo_seq;
+        CUDA_OK(cudaEventRecord(s->ev_pack, s->stream));
+        CUDA_OK(cudaStreamWaitEvent(s->comm_stream, s->ev_pack, 0));
+        for (int p = 0; p < np; ++p) {
+            Peer& pr = s->peers[p];
+            MODE_CALL(s, launch_put, s->P, pr.r_total, prim, s->A.S, pr.r_prim[buf], pr.r_S, pr.d_send_idx, pr.d_dst_idx,
+                      (long long)pr.send_idx.size(), s->comm_stream);
+        }
+        MODE_CALL(s, launch_halo_signal, s->d_remote_flags, np, seq, s->comm_stream);
+        MODE_CALL(s, launch_halo_wait, (const unsigned long long*)s->d_shared, np, seq, s->d_status, s->comm_stream);
+        CUDA_OK(cudaEventRecord(s->ev_comm, s->comm_stream));
+        return 0;
+    }
     if (!s->exchange) { set_err("blocks on other ranks are connected but no exchange callback is installed"); return -5; }
     const int np = (int)s->peers.size();
     std::vector<int> ranks(np);
@@ -490,7 +533,7 @@ int enqueue_step(Sim* s, double dt)
         const int out_buf = work[(stage - 1) & 1];
         double* prim_in = s->A.prim[in_buf];
         double* prim_out = s->A.prim[out_buf];
-        int rc = exchange_remote(s, prim_in);
+        int rc = exchange_remote(s, prim_in, in_buf);
         if (rc) return rc;
         rc = fill_local_ghost_cells(s, prim_in, stage == 1 && s->ghosts_stale);
         if (rc) return rc;
@@ -672,6 +715,7 @@ int eb200_finalize(int sim)
     Sim* s = get_sim(sim); if (!s) return -1;
     cudaSetDevice(s->cfg.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (Peer& pr : s->peers) for (void* q : pr.opened) cudaIpcCloseMemHandle(q);
     for (void* p : s->allocs) cudaFree(p);
     for (auto& e : s->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (s->h_status) cudaFreeHost(s->h_status);
@@ -1023,6 +1067,19 @@ int eb200_commit(int sim)
         s->peers.push_back(std::move(p));
     }
     if (!s->peers.empty()) {
+        // one allocation (one IPC handle) with what the peers need to see: the flags they raise and, per peer, the
+        // arena indices of the ghost cells they fill (wire order)
+        if (s->peers.size() > EB_P2P_MAXPEERS) { set_err("more than %d peer ranks", EB_P2P_MAXPEERS); return -1; }
+        size_t bytes = EB_P2P_MAXPEERS * sizeof(unsigned long long);
+        for (Peer& p : s->peers) { p.recv_off = (long long)bytes; bytes += (p.recv_idx.size() * sizeof(int) + 255) / 256 * 256; }
+        bytes = std::max<size_t>(bytes, (size_t)2 << 20);     // a whole allocation granule: nothing else shares the mapping
+        if (dev_alloc(s, &s->d_shared, bytes)) return -100;
+        s->shared_bytes = bytes;
+        for (Peer& p : s->peers)
+            if (!p.recv_idx.empty())
+                CUDA_OK(cudaMemcpyAsync(s->d_shared + p.recv_off, p.recv_idx.data(), p.recv_idx.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    }
+    if (!s->peers.empty()) {
         // tiles whose stencils reach ghost cells filled by another rank go last (after the halo arrived)
         std::vector<int> t_int, t_bnd;
         for (size_t n = 0; n < s->local.size(); ++n) {
@@ -1067,6 +1124,7 @@ int eb200_upload_flow(int sim, int blk_id, const double* const* prims, int nprim
     const size_t bytes = (size_t)b->ncp * sizeof(double);
     double* prim = s->A.prim[s->cur];
     s->ghosts_stale = true;
+    s->undo_cur = -1;
     for (int v = 0; v < nprims; ++v)
         CUDA_OK(cudaMemcpyAsync(prim + (long long)v * s->P.total + b->cell0, prims[v], bytes, cudaMemcpyHostToDevice, s->stream));
     CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
@@ -1200,9 +1258,21 @@ int eb200_step(int sim, double t0, double dt, int* n_bad_cells)
     int rc = enqueue_step(s, dt);
     if (rc) return rc;
     rc = finish_steps(s, cur0, n_bad_cells, true);
-    if (rc == 0) std::swap(s->Ulev[0], s->Ulev[s->n_stages]);     // :1557-1561 swap(U[0], U[end])
+    s->undo_cur = -1;
+    if (rc == 0) { std::swap(s->Ulev[0], s->Ulev[s->n_stages]); s->undo_cur = cur0; }     // :1557-1561 swap(U[0], U[end])
     if (s->ev_used > 2048) drain_flux_events(s);
     return rc;
+}
+
+int eb200_undo_step(int sim)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (s->undo_cur < 0) { set_err("undo_step: no successful step to take back"); return -1; }
+    // the start-of-step FlowStates (buffer undo_cur) and the old U[0] were never written: point back at them
+    std::swap(s->Ulev[0], s->Ulev[s->n_stages]);
+    s->cur = s->undo_cur;
+    s->undo_cur = -1;
+    return 0;
 }
 
 int eb200_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells)
@@ -1210,6 +1280,7 @@ int eb200_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells)
     (void)t0;
     Sim* s = get_sim(sim); if (!s) return -1;
     if (!s->committed) { set_err("not committed"); return -1; }
+    s->undo_cur = -1;
     CUDA_OK(cudaSetDevice(s->cfg.device));
     CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
     for (int n = 0; n < nsteps; ++n) {
@@ -1281,6 +1352,124 @@ int eb200_debug_face_flux(int sim, int nfaces, const double* cells, const double
     cudaFree(dprim); cudaFree(dlen); cudaFree(dface); cudaFree(dF); cudaFree(dok);
     if (!s->d_gas) cudaFree(dgas);
     return 0;
+}
+
+// ---- direct halo exchange between the processes of one node (CUDA IPC + NVLink peer stores) ------------------------
+namespace {
+// base address and size of the allocation a device pointer lies in (an IPC handle always names the whole allocation)
+int allocation_base(const void* ptr, char** base)
+{
+    typedef CUresult (*GetRange)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static GetRange fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+            (void)cudaGetLastError(); set_err("cuMemGetAddressRange is not available"); return -1;
+        }
+        fn = (GetRange)f;
+    }
+    CUdeviceptr b = 0; size_t sz = 0;
+    if (fn(&b, &sz, (CUdeviceptr)ptr) != CUDA_SUCCESS) { set_err("cuMemGetAddressRange failed"); return -1; }
+    *base = (char*)b;
+    return 0;
+}
+int export_handle(const void* ptr, cudaIpcMemHandle_t* h, long long* off)
+{
+    char* base = nullptr;
+    if (allocation_base(ptr, &base)) return -1;
+    CUDA_OK(cudaIpcGetMemHandle(h, base));
+    *off = (const char*)ptr - base;
+    return 0;
+}
+int open_handle(Peer& pr, const cudaIpcMemHandle_t& h, long long off, void** out)
+{
+    void* base = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    pr.opened.push_back(base);
+    *out = (char*)base + off;
+    return 0;
+}
+}  // namespace
+
+int eb200_p2p_export(int sim, int peer_rank, void* blob, int nbytes)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (!s->committed) { set_err("p2p_export needs a committed simulation"); return -1; }
+    if (!blob || nbytes < (int)sizeof(P2PBlob)) return (int)sizeof(P2PBlob);       // tells the caller how much room it takes
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    int idx = -1;
+    for (size_t p = 0; p < s->peers.size(); ++p) if (s->peers[p].rank == peer_rank) idx = (int)p;
+    if (idx < 0) { set_err("rank %d is not a halo peer of rank %d", peer_rank, s->cfg.rank); return -1; }
+    P2PBlob B; memset(&B, 0, sizeof B);
+    B.magic = EB_P2P_MAGIC; B.exporter_rank = s->cfg.rank; B.nprim = s->P.nprim; B.has_S = s->P.shock_detect ? 1 : 0;
+    B.total = s->P.total;
+    for (int b = 0; b < 3; ++b) if (export_handle(s->A.prim[b], &B.prim[b], &B.prim_off[b])) return -100;
+    if (B.has_S && export_handle(s->A.S, &B.S, &B.S_off)) return -100;
+    if (export_handle(s->d_shared, &B.shared, &B.shared_off)) return -100;
+    B.flag_off = (long long)idx * (long long)sizeof(unsigned long long);
+    B.recv_idx_off = s->peers[idx].recv_off; B.recv_count = (long long)s->peers[idx].recv_idx.size();
+    CUDA_OK(cudaStreamSynchronize(s->stream));          // the index lists are in place before anybody reads them
+    memcpy(blob, &B, sizeof B);
+    return (int)sizeof(P2PBlob);
+}
+
+int eb200_p2p_import(int sim, int peer_rank, const void* blob, int nbytes)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (!s->committed) { set_err("p2p_import needs a committed simulation"); return -1; }
+    if (!blob || nbytes < (int)sizeof(P2PBlob)) { set_err("p2p_import: blob too small"); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    P2PBlob B; memcpy(&B, blob, sizeof B);
+    if (B.magic != EB_P2P_MAGIC || B.exporter_rank != peer_rank) { set_err("p2p_import: not a blob of rank %d", peer_rank); return -1; }
+    Peer* pr = nullptr;
+    for (Peer& p : s->peers) if (p.rank == peer_rank) pr = &p;
+    if (!pr) { set_err("rank %d is not a halo peer of rank %d", peer_rank, s->cfg.rank); return -1; }
+    if (pr->p2p) { set_err("rank %d was imported already", peer_rank); return -1; }
+    if (B.nprim != s->P.nprim || B.has_S != (s->P.shock_detect ? 1 : 0)) { set_err("p2p_import: rank %d runs another configuration", peer_rank); return -1; }
+    if (B.recv_count != (long long)pr->send_idx.size()) {
+        set_err("p2p_import: rank %d expects %lld cells from rank %d, which sends %lld", peer_rank, B.recv_count, s->cfg.rank, (long long)pr->send_idx.size());
+        return -1;
+    }
+    void* q = nullptr;
+    for (int b = 0; b < 3; ++b) { if (open_handle(*pr, B.prim[b], B.prim_off[b], &q)) return -100; pr->r_prim[b] = (double*)q; }
+    if (B.has_S) { if (open_handle(*pr, B.S, B.S_off, &q)) return -100; pr->r_S = (double*)q; }
+    if (open_handle(*pr, B.shared, B.shared_off, &q)) return -100;
+    char* region = (char*)q;
+    pr->r_flag = (unsigned long long*)(region + B.flag_off);
+    pr->r_total = B.total;
+    if (dev_alloc(s, &pr->d_dst_idx, (size_t)B.recv_count, false)) return -100;
+    if (B.recv_count > 0)
+        CUDA_OK(cudaMemcpyAsync(pr->d_dst_idx, region + B.recv_idx_off, (size_t)B.recv_count * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    pr->p2p = true;
+    bool all = true;
+    for (Peer& p : s->peers) all = all && p.p2p;
+    if (all) {
+        std::vector<unsigned long long*> rf;
+        for (Peer& p : s->peers) rf.push_back(p.r_flag);
+        if (dev_upload(s, &s->d_remote_flags, rf)) return -100;
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        s->p2p_ready = true;
+    }
+    return s->p2p_ready ? 1 : 0;
+}
+
+int eb200_describe(int sim, char* dest, int n)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    int ncart = 0, nv3 = 0;
+    for (size_t b = 0; b < s->hdesc.size(); ++b) { ncart += s->hdesc[b].cartesian ? 1 : 0; nv3 += s->hdesc[b].v3 ? 1 : 0; }
+    char buf[512];
+    snprintf(buf, sizeof buf,
+             "rank %d: %zu local blocks (%d uniform-Cartesian, %d run by flux_update_kernel_v3), %lld tiles, tma=%d, "
+             "halo peers=%zu (%s), arithmetic=%s",
+             s->cfg.rank, s->local.size(), ncart, nv3, s->ncta, s->d_tmaps ? 1 : 0, s->peers.size(),
+             s->peers.empty() ? "none" : (s->p2p_ready ? "direct NVLink stores" : "exchange callback"),
+             s->cfg.strict_fp ? "strict (no FMA)" : "throughput");
+    int len = (int)strlen(buf);
+    if (dest && n > 0) { strncpy(dest, buf, n - 1); dest[n - 1] = 0; }
+    return len;
 }
 
 void* eb200_cuda_stream(int sim)

@@ -153,6 +153,10 @@ struct EbFillItem { int dst, param; };
                      double* buf, cudaStream_t st);                                                      \
     void launch_unpack(const EbParams& P, double* prim, double* S, const int* idx, long long n,          \
                        const double* buf, cudaStream_t st);                                              \
+    void launch_put(const EbParams& P, long long total_dst, const double* prim_src, const double* S_src, double* prim_dst,  \
+                    double* S_dst, const int* src_idx, const int* dst_idx, long long n, cudaStream_t st);  \
+    void launch_halo_signal(unsigned long long* const* remote_flags, int npeers, unsigned long long seq, cudaStream_t st); \
+    void launch_halo_wait(const unsigned long long* flags, int npeers, unsigned long long seq, int* status, cudaStream_t st); \
     void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A,             \
                               const double* prim, cudaStream_t st);                                      \
     }

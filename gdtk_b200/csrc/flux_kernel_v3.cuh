@@ -300,6 +300,17 @@ __device__ __forceinline__ unsigned mbar_try(unsigned long long* bar, unsigned p
     return done;
 }
 
+// wait with a suspend-time hint: the warp sleeps in the barrier unit until the phase completes (or the hint, in ns,
+// runs out) instead of spinning on try_wait and taking issue slots from the warps it is waiting for
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+    } while (!done);
+}
+
 // CTA-wide split-phase barrier on an mbarrier with one arrival per warp: arrive() after the warp's own writes,
 // wait() before reading what the other warps wrote; independent work goes in between.
 __device__ __forceinline__ void cta_arrive(unsigned long long* bar, int lane)
@@ -492,14 +503,14 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
 #pragma unroll
                 for (int q = 0; q < NCQ; ++q) fX[((it & 1) * NCQ + q) * TY + hr] = F[q];
             }
-            if (it > 0) mbar_wait(barF, (unsigned)((it - 1) & 1));      // the main warps have read last plane's states along j
+            if (it > 0) mbar_wait_sleep(barF, (unsigned)((it - 1) & 1));      // the main warps have read last plane's states along j
             halo_jobs(2, 3, t0, nullptr, 0);
             cta_arrive(barR, lane);
             if (DIM == 3) {
-                mbar_wait(barK, (unsigned)(it & 1));          // every main warp has read plane k - 1
+                mbar_wait_sleep(barK, (unsigned)(it & 1));          // every main warp has read plane k - 1
                 if (lane == 0) issue_plane(m + 2);            // plane k + 2 -> its buffer (the last one needed is k1 + 1)
             }
-            mbar_wait(barR, (unsigned)(it & 1));
+            mbar_wait_sleep(barR, (unsigned)(it & 1));
             if (northE) {
                 const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (j0 + TY + EB_NG)) * NI + (i + EB_NG);
                 double F[NCQ];
@@ -661,7 +672,7 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
 #endif
             }
             // ---- 4. the south face, once the row below has published its plus state
-            mbar_wait(barR, par);
+            mbar_wait_sleep(barR, par);
             if (faceS_ok) {
                 if (!outflow_override<DIM, 1>(P, D, S.prim_in, j, D.njc, c, D.stride[1], FS_)) {
                     double Ls[5];
@@ -707,7 +718,7 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
 
         // ---- 6. the rest of the surface integral of this plane's cell (all but the top face)
         if (has_cells) {
-            mbar_wait(barF, par);
+            mbar_wait_sleep(barF, par);
             if (cell_ok) {
 #pragma unroll
                 for (int q = 0; q < NCQ; ++q) {

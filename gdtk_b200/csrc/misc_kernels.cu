@@ -335,6 +335,57 @@ __global__ void unpack_kernel(long long total, int nprim, double* __restrict__ p
     for (int v = 0; v < nprim; ++v) prim[v * total + c] = buf[v * n + t];
     if (S) S[c] = buf[(long long)nprim * n + t];
 }
+// Halo over NVLink without staging buffers: the interior cells a neighbouring rank needs go straight into that
+// rank's ghost cells (its arena, mapped through CUDA IPC); total_dst is the field stride of the remote arena.
+__global__ void put_kernel(long long total_src, long long total_dst, int nprim, const double* __restrict__ prim_src,
+                           const double* __restrict__ S_src, double* __restrict__ prim_dst, double* __restrict__ S_dst,
+                           const int* __restrict__ src_idx, const int* __restrict__ dst_idx, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long cs = src_idx[t], cd = dst_idx[t];
+    for (int v = 0; v < nprim; ++v) prim_dst[v * total_dst + cd] = prim_src[v * total_src + cs];
+    if (S_src) S_dst[cd] = S_src[cs];
+}
+// After the puts of one exchange (stream order): tell every peer that exchange `seq` has landed.
+__global__ void halo_signal_kernel(unsigned long long* const* __restrict__ remote_flags, int npeers, unsigned long long seq)
+{
+    const int p = threadIdx.x;
+    if (p >= npeers) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flags[p]), "l"(seq) : "memory");
+}
+// Before the tiles that read those ghost cells: wait until every peer has signalled exchange `seq`.
+// (gives up after ~10 s of GPU clock and raises bit 1 of the step status: a peer that never signals -- a rank that
+//  died or took another number of steps -- must not hang the device)
+__global__ void halo_wait_kernel(const unsigned long long* __restrict__ flags, int npeers, unsigned long long seq, int* status)
+{
+    const int p = threadIdx.x;
+    if (p < npeers) {
+        unsigned long long v;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
+            if (v < seq && clock64() - t0 > 20000000000LL) { atomicOr(status, 3); break; }
+        } while (v < seq);
+    }
+    __threadfence_system();
+}
+void launch_put(const EbParams& P, long long total_dst, const double* prim_src, const double* S_src, double* prim_dst, double* S_dst,
+                const int* src_idx, const int* dst_idx, long long n, cudaStream_t st)
+{
+    if (n > 0) put_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, total_dst, P.nprim, prim_src, P.shock_detect ? S_src : nullptr,
+                                                                      prim_dst, S_dst, src_idx, dst_idx, n);
+}
+void launch_halo_signal(unsigned long long* const* remote_flags, int npeers, unsigned long long seq, cudaStream_t st)
+{
+    halo_signal_kernel<<<1, 64, 0, st>>>(remote_flags, npeers, seq);
+}
+void launch_halo_wait(const unsigned long long* flags, int npeers, unsigned long long seq, int* status, cudaStream_t st)
+{
+    halo_wait_kernel<<<1, 64, 0, st>>>(flags, npeers, seq, status);
+}
+
 void launch_pack(const EbParams& P, const double* prim, const double* S, const int* idx, long long n, double* buf, cudaStream_t st)
 {
     if (n > 0) pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, P.nprim, prim, P.shock_detect ? S : nullptr, idx, n, buf);

@@ -122,13 +122,73 @@ def make_exchange(device_buffers):
 class DistributedSimulation(Simulation):
     """Simulation with blocks spread over the ranks of torch.distributed."""
 
-    def __init__(self, config, gmodel, blocks, block_owner, lib=None, device_buffers=True, device=0):
+    def __init__(self, config, gmodel, blocks, block_owner, lib=None, device_buffers=True, device=0, direct_halo=True):
         import torch.distributed as dist
         self._dist = dist
         self._device_buffers = device_buffers
         rank, world = dist.get_rank(), dist.get_world_size()
         super().__init__(config, gmodel, blocks, lib=lib, rank=rank, world_size=world,
                          block_owner=block_owner, device=device, exchange=make_exchange(device_buffers))
+
+        self.halo_transport = "exchange callback"
+        if device_buffers and direct_halo:
+            self._setup_direct_halo()
+
+    def _peer_ranks(self):
+        from .sim import ExchangeBC_FullFace
+        peers = set()
+        for b in self.local_blocks:
+            for bc in b.bcList.values():
+                if isinstance(bc, ExchangeBC_FullFace) and self.block_owner[bc.otherBlock] != self.rank:
+                    peers.add(self.block_owner[bc.otherBlock])
+        return sorted(peers)
+
+    def _setup_direct_halo(self):
+        """eb200_p2p_export / eb200_p2p_import (include/eb200.h): every rank hands each halo peer a blob with the CUDA
+        IPC handles of its arena; afterwards the library stores halo cells straight into the neighbours' ghost cells
+        over NVLink and this module's exchange callback is no longer called.  All ranks decide together: if any
+        import fails (ranks on different nodes, IPC not permitted), everybody stays on the callback."""
+        dist, lib, h = self._dist, self.lib, self.handle
+        peers = self._peer_ranks()
+        size = lib.p2p_export(h, -1, None, 0) if peers else 0
+        mine = {}
+        ok = True
+        for p in peers:
+            buf = C.create_string_buffer(max(size, 1))
+            if lib.p2p_export(h, p, buf, size) != size:
+                ok = False
+                break
+            mine[p] = buf.raw
+        everyone = [None] * self.world_size
+        dist.all_gather_object(everyone, mine if ok else None)
+        ok = ok and all(e is not None for e in everyone)
+        ready = not peers
+        if ok:
+            for p in peers:
+                blob = everyone[p].get(self.rank)
+                rc = lib.p2p_import(h, p, blob, len(blob)) if blob is not None else -1
+                if rc < 0:
+                    ok = False
+                    break
+                ready = rc == 1
+        import torch
+        t = torch.tensor([1 if (ok and ready) else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) != 1:
+            if ok and ready and peers:
+                raise RuntimeError("direct halo exchange is set up on this rank but not on all ranks: "
+                                   f"{lib.error()} -- rerun with direct_halo=False")
+            return
+        self.halo_transport = "direct NVLink stores (CUDA IPC)"
+
+    def reduce_step_status(self, rc):
+        import torch
+        t = torch.tensor([2 if rc < 0 else rc], dtype=torch.int32)
+        if self._device_buffers:
+            t = t.cuda()
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX)
+        worst = int(t.cpu()[0])
+        return -2 if worst >= 2 else worst
 
     def reduce_dt(self, dt_allow, cfl_max):
         import torch

@@ -25,7 +25,10 @@ FACES = ["west", "east", "south", "north", "bottom", "top"]          # _abi face
 
 # options that must have these values for a job to be on the accelerated path
 REQUIRED = {"viscous": False, "reacting": False, "MHD": False, "grid_motion": "none", "turbulence_model": "none",
-            "udf_source_terms": False, "solver_mode": None}
+            "udf_source_terms": False, "solver_mode": None,
+            # options of the explicit update that this path does not implement: refuse them instead of ignoring them
+            "with_local_time_stepping": False, "with_super_time_stepping": False, "with_super_time_stepping_flexible_stages": False,
+            "residual_smoothing": False, "adjust_invalid_cell_data": False, "nsolidblock": 0, "n_ghost_cell_layers": 2}
 
 
 def _flowstate_from_json(gm, d):
@@ -116,6 +119,13 @@ def load_job(job_dir, job, tindx=0, **overrides):
     for key, val in J.items():
         if hasattr(cfg, key) and not isinstance(val, (dict, list)):
             setattr(cfg, key, val)
+    # the reference's writer never emits cfl_value: it writes the schedule (output.lua:173-198)
+    if "cfl_schedule_values" in J:
+        values, times = list(J["cfl_schedule_values"]), list(J.get("cfl_schedule_times", []))
+        if len(values) != len(times) or not values:
+            raise ValueError("cfl_schedule_values and cfl_schedule_times must be two non-empty lists of equal length")
+        cfg.cfl_schedule = [(float(t), float(v)) for t, v in zip(times, values)]
+        cfg.cfl_value = float(values[0])
     for key, val in overrides.items():
         setattr(cfg, key, val)
     gas_file = J["gas_model_file"]
@@ -130,6 +140,8 @@ def load_job(job_dir, job, tindx=0, **overrides):
             raise ValueError(f"block {n}: only structured fluid blocks are on this path")
         if not B.get("active", True):
             raise ValueError(f"block {n}: inactive blocks are not supported")
+        if float(B.get("omegaz", 0.0)) != 0.0:
+            raise ValueError(f"block {n}: rotating frames (omegaz != 0) are not on this path")
         grid = io.read_grid(io.job_file(job_dir, job, "grid", n, 0))
         flow = io.read_flow(io.job_file(job_dir, job, "flow", n, tindx))
         sim_time = flow["sim_time"]
@@ -161,9 +173,18 @@ def write_job(job_dir, job, cfg, gm, gas_model_file, blocks, sim, history_points
          "viscous": False, "reacting": False, "MHD": False, "grid_motion": "none", "turbulence_model": "none", "udf_source_terms": False,
          "n_ghost_cell_layers": 2}
     skip = {"strict_fp", "force_general_path", "force_generic_kernel", "no_tma", "no_push", "block_index", "title", "viscous", "reacting"}
+    skip |= {"cfl_value", "cfl_schedule"}
     for key, val in vars(cfg).items():
         if key not in skip and isinstance(val, (bool, int, float, str)):
             J[key] = val
+    # like write_config_file (output.lua:173-198): the schedule, never cfl_value
+    sched = cfg.cfl_schedule or [(0.0, cfg.cfl_value)]
+    J["cfl_schedule_length"] = len(sched)
+    J["cfl_schedule_values"] = [float(p[1]) for p in sched]
+    J["cfl_schedule_times"] = [float(p[0]) for p in sched]
+    for key in ("with_local_time_stepping", "with_super_time_stepping", "residual_smoothing", "adjust_invalid_cell_data"):
+        J[key] = False
+    J["nsolidblock"] = 0
     for b in blocks:
         g = b.geom
         B = {"type": "fluid_block", "label": getattr(b, "label", "") or "", "active": True, "fluidBlockArrayId": -1, "omegaz": 0.0,

@@ -49,6 +49,10 @@ class Config:
         self.shock_detector_smoothing = 0                  # :1127
         self.gasdynamic_update_scheme = "predictor-corrector"  # :936
         self.cfl_value = 0.5
+        # config.cfl_schedule = {{t0, cfl0}, {t1, cfl1}, ...}: when given it replaces cfl_value, as in the reference's
+        # write_config_file (output.lua:173-198); the .control file's cfl_scale_factor multiplies either
+        self.cfl_schedule = None
+        self.cfl_scale_factor = 1.0
         self.cfl_count = 10                                # :1294
         self.fixed_time_step = False
         self.dt_init = 1.0e-3                              # :1281
@@ -77,6 +81,24 @@ class Config:
             if not hasattr(self, k):
                 raise AttributeError(f"unknown config option {k!r}")
             setattr(self, k, v)
+
+    def cfl_at(self, t):
+        """cfl_schedule.interpolate_value(SimState.time) * cfl_scale_factor (simcore_gasdynamic_step.d:77-78, with
+        Schedule.interpolate_value of src/nm/schedule.d:39-56: constant outside the table, linear inside)."""
+        sched = self.cfl_schedule or [(0.0, self.cfl_value)]
+        times = [float(p[0]) for p in sched]
+        values = [float(p[1]) for p in sched]
+        if t <= times[0]:
+            v = values[0]
+        elif t >= times[-1]:
+            v = values[-1]
+        else:
+            i = len(times) - 1
+            while i > 0 and t < times[i]:
+                i -= 1
+            frac = (t - times[i]) / (times[i + 1] - times[i])
+            v = (1.0 - frac) * values[i] + frac * values[i + 1]
+        return v * self.cfl_scale_factor
 
     def check(self):
         fc = self.flux_calculator
@@ -624,7 +646,7 @@ class Simulation:
     # -- time marching -----------------------------------------------------
     def compute_dt(self, check_cfl):
         out = (C.c_double * 3)()
-        self.lib.check(self.lib.compute_dt(self.handle, self.dt_global, self.config.cfl_value,
+        self.lib.check(self.lib.compute_dt(self.handle, self.dt_global, self.config.cfl_at(self.time),
                                            int(check_cfl), out), "compute_dt")
         return out[0], out[1]
 
@@ -649,17 +671,27 @@ class Simulation:
             self.dt_global = min(self.dt_global * 1.5, dt_allow)
             self.dt_global = min(self.dt_global, cfg.dt_max)
 
+    def reduce_step_status(self, rc):
+        """Hook for multi-process runs: the worst status over ranks (MPI_Allreduce of step_failed, :1545-1554)."""
+        return rc
+
     def gasdynamic_step(self):
-        """One step with the reference's retry policy (:988-999, :1545-1554)."""
+        """One step with the reference's retry policy (:988-999, :1545-1554).  The decision is collective: if the
+        step failed on any rank, every rank restores the start-of-step state (a rank whose own step went through
+        takes it back), scales dt and tries again; a fatal error on one rank ends the run on all of them."""
         nbad = C.c_int(0)
         attempt = 0
         while True:
             attempt += 1
-            rc = self.lib.step(self.handle, self.time, self.dt_global, C.byref(nbad))
+            rc_local = self.lib.step(self.handle, self.time, self.dt_global, C.byref(nbad))
+            rc = self.reduce_step_status(rc_local)
             if rc < 0:
-                raise RuntimeError(f"step failed fatally ({rc}): {self.lib.error()}")
+                why = self.lib.error() if rc_local < 0 else "another rank reported a fatal error"
+                raise RuntimeError(f"step failed fatally ({rc}): {why}")
             if rc == 0:
                 break
+            if rc_local == 0:
+                self.lib.check(self.lib.undo_step(self.handle), "undo_step")
             self.dt_global *= 0.2
             if attempt >= self.config.max_attempts_for_step:
                 raise RuntimeError(

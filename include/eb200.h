@@ -165,7 +165,8 @@ typedef struct eb200_config {
     int rank;                       /* this process's rank (0 when single process) */
     int device;                     /* CUDA device ordinal used by this process */
     int reserved_i[4];              /* testing knobs: [0] != 0 never use the uniform-Cartesian fast path;
-                                       [1] != 0 always use the generic flux kernel;
+                                       [1] == 1 always use the generic flux kernel, == 2 the face-centred tuned
+                                       kernel where the cell-centred one would run;
                                        [2] != 0 stage tiles with cp.async even where TMA could be used;
                                        [3] != 0 fill every ghost cell with the ghost-cell kernel (no stores into
                                        neighbouring blocks from the flux kernel) */
@@ -318,6 +319,32 @@ int eb200_flux_kernel_time(int sim, int reset, double* ms, long long* launches);
  * between them (bench inner loop; same work as nsteps calls of eb200_step).
  * Returns like eb200_step. */
 int eb200_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells);
+
+/* Take back the last eb200_step, which must have returned 0 and must be the last call that changed the state:
+ * FlowStates and U[0] are again those of the start of that step (nothing is copied: the start-of-step buffers are
+ * intact until the next step).  For multi-process runs, where the reference decides collectively
+ * (MPI_Allreduce of step_failed, simcore_gasdynamic_step.d:1545-1554): a rank whose own step succeeded while
+ * another rank's failed takes its step back and retries with the smaller dt like everybody else.  0 or < 0. */
+int eb200_undo_step(int sim);
+
+/* ---- direct halo exchange between the processes of one node ---------------------------
+ * Replaces MPI_Irecv/MPI_Send/MPI_Wait of full_face_copy.d:1681,1803-1842 (and the exchange callback above) by
+ * stores over NVLink: after eb200_commit every process exports one opaque blob per halo peer
+ * (eb200_p2p_export), the host layer moves the blobs (MPI_Alltoall / torch.distributed in the Python host), and
+ * every process imports the blobs its peers made for it (eb200_p2p_import).  From then on eb200_step writes the
+ * cells a peer needs straight into that peer's ghost cells (CUDA IPC mapping of its arena) and raises a flag in
+ * the peer's memory; no host code runs per stage.  Until every peer has been imported the callback is used.
+ *
+ * eb200_p2p_export: writes the blob this process makes for `peer_rank` into `blob` (nbytes of room) and returns
+ * its size; with blob == NULL or too little room it only returns the size needed.  < 0 on error.
+ * eb200_p2p_import: returns 1 when all peers are imported (direct exchange is on), 0 when some are missing,
+ * < 0 on error (e.g. the processes do not share a node, or the peer runs another configuration). */
+int eb200_p2p_export(int sim, int peer_rank, void* blob, int nbytes);
+int eb200_p2p_import(int sim, int peer_rank, const void* blob, int nbytes);
+
+/* One line of text about how the simulation was set up (blocks per kernel, tiles, TMA, halo transport):
+ * copied into dest (NUL-terminated, truncated to n); returns its full length.  Diagnostics only. */
+int eb200_describe(int sim, char* dest, int n);
 
 /* The cudaStream_t (as void*) on which the library enqueues all its work; lets the caller
  * record CUDA events around calls and order its own transfers.  NULL on error. */

@@ -104,6 +104,7 @@ typedef struct {
     int lists_built;
     int shock_detect;        /* do_shock_detect (set by the adaptive flux calculators) */
     int mutate_cell_vel;     /* reproduce e4 onedinterp.d:766-769,983-986 in-place round trips */
+    double** undo_saved;     /* FlowStates at the start of the last successful step (orc_undo_step), or NULL */
     int n_stages;
 } Sim;
 
@@ -1714,6 +1715,10 @@ static void free_blk(Blk* b)
 int orc_finalize(int sim)
 {
     Sim* s = get_sim(sim); if (!s) return -1;
+    if (s->undo_saved) {
+        for (int ib = 0; ib < s->nblk; ++ib) free(s->undo_saved[ib]);
+        free(s->undo_saved); s->undo_saved = NULL;
+    }
     for (int i = 0; i < s->nblk; ++i) free_blk(s->blks[i]);
     for (int i = 0; i < s->nrem; ++i) free(s->rem[i]);
     for (int p = 0; p < s->npeers; ++p) {
@@ -1826,6 +1831,39 @@ int orc_set_exchange(int sim, eb200_exchange_fn fn, void* user)
     Sim* s = get_sim(sim); if (!s) return -1;
     s->exchange = fn; s->exchange_user = user;
     return 0;
+}
+
+/* The direct (CUDA IPC) halo exchange has no meaning on the CPU: the oracle always uses the exchange callback. */
+int orc_p2p_export(int sim, int peer_rank, void* blob, int nbytes)
+{
+    (void)sim; (void)peer_rank; (void)blob; (void)nbytes;
+    set_err("the CPU oracle has no direct halo exchange"); return -1;
+}
+int orc_p2p_import(int sim, int peer_rank, const void* blob, int nbytes)
+{
+    (void)sim; (void)peer_rank; (void)blob; (void)nbytes;
+    set_err("the CPU oracle has no direct halo exchange"); return -1;
+}
+int orc_describe(int sim, char* dest, int n)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    char buf[128];
+    snprintf(buf, sizeof buf, "CPU oracle: %d blocks, exchange callback", s->nblk);
+    if (dest && n > 0) { strncpy(dest, buf, (size_t)n - 1); dest[n - 1] = 0; }
+    return (int)strlen(buf);
+}
+
+/* Oracle-only: set (n > 0) and report the number of OpenMP threads the block loops will use; 1 when the
+ * library was built without OpenMP.  bench.py states this number beside the CPU baseline. */
+int orc_omp_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 
 int orc_set_option(int sim, const char* name, int value)
@@ -1946,6 +1984,10 @@ int orc_step(int sim, double t0, double dt, int* n_bad_cells)
     (void)t0;
     Sim* s = get_sim(sim); if (!s) return -1;
     int step_failed = 0, total_bad = 0;
+    if (s->undo_saved) {
+        for (int ib = 0; ib < s->nblk; ++ib) free(s->undo_saved[ib]);
+        free(s->undo_saved); s->undo_saved = NULL;
+    }
     for (int ib = 0; ib < s->nblk; ++ib) memset(s->blks[ib]->bad, 0, s->blks[ib]->ncp);   /* :941-945 */
     /* keep the start-of-step FlowStates so that a failed step leaves them intact (ABI contract) */
     double** saved = (double**)calloc(s->nblk, sizeof(double*));
@@ -1996,9 +2038,35 @@ int orc_step(int sim, double t0, double dt, int* n_bad_cells)
         for (int ib = 0; ib < s->nblk; ++ib) memcpy(s->blks[ib]->prim, saved[ib], (size_t)s->nprim * s->blks[ib]->ncp * sizeof(double));
         if (step_failed == -2) set_err("Too many bad cells during explicit gasdynamic update.");
     }
-    for (int ib = 0; ib < s->nblk; ++ib) free(saved[ib]);
-    free(saved);
+    if (step_failed == 0) s->undo_saved = saved;          /* kept until the next step for orc_undo_step */
+    else {
+        for (int ib = 0; ib < s->nblk; ++ib) free(saved[ib]);
+        free(saved);
+    }
     return step_failed == -2 ? -2 : step_failed;
+}
+
+static void drop_undo(Sim* s)
+{
+    if (!s->undo_saved) return;
+    for (int ib = 0; ib < s->nblk; ++ib) free(s->undo_saved[ib]);
+    free(s->undo_saved);
+    s->undo_saved = NULL;
+}
+
+/* Take back the last successful step (another rank's step failed: simcore_gasdynamic_step.d:1545-1554 retries on all
+ * ranks together): FlowStates and U[0] are those of the start of that step again. */
+int orc_undo_step(int sim)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (!s->undo_saved) { set_err("undo_step: no successful step to take back"); return -1; }
+    for (int ib = 0; ib < s->nblk; ++ib) {
+        Blk* b = s->blks[ib];
+        memcpy(b->prim, s->undo_saved[ib], (size_t)s->nprim * b->ncp * sizeof(double));
+        double* t = b->U[0]; b->U[0] = b->U[s->n_stages]; b->U[s->n_stages] = t;
+    }
+    drop_undo(s);
+    return 0;
 }
 
 int orc_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells)

@@ -165,3 +165,48 @@ def test_config_options_added_for_the_wider_path():
         pass
     assert OutFlowBC_FixedP(2.0e4).params() == [2.0e4] and OutFlowBC_FixedP.kind == 5
     assert OutFlowBC_FixedPT(2.0e4, 300).params() == [2.0e4, 300.0] and OutFlowBC_FixedPT.kind == 6
+
+
+def test_cfl_schedule_interpolation():
+    """Schedule.interpolate_value (src/nm/schedule.d:39-56) times cfl_scale_factor (simcore_gasdynamic_step.d:77-78)."""
+    from gdtk_b200.sim import Config
+    c = Config(flux_calculator="ausmdv", cfl_value=0.4)
+    assert c.cfl_at(0.0) == 0.4 and c.cfl_at(1.0) == 0.4
+    c.cfl_schedule = [(0.0, 0.1), (1.0e-3, 0.5), (3.0e-3, 0.9)]
+    assert c.cfl_at(-1.0) == 0.1 and c.cfl_at(0.0) == 0.1
+    assert c.cfl_at(0.5e-3) == pytest.approx(0.3, rel=1e-14)
+    assert c.cfl_at(2.0e-3) == pytest.approx(0.7, rel=1e-14)
+    assert c.cfl_at(3.0e-3) == 0.9 and c.cfl_at(1.0) == 0.9
+    c.cfl_scale_factor = 0.5
+    assert c.cfl_at(1.0) == 0.45
+
+
+def test_step_status_is_decided_collectively():
+    """A rank whose own step succeeded while another rank's failed takes its step back (eb200_undo_step), scales
+    dt and retries with everybody else; a fatal error elsewhere ends the run here too."""
+    cfg, gm, blocks = cases.sod(dims=2, ncells=8, nj=2)
+
+    class Lib(_StubLib):
+        def __init__(self):
+            super().__init__([], fail_steps=[0, 0, 0])
+            self.undone = 0
+
+        def __getattr__(self, name):
+            if name == "undo_step":
+                def f(*a):
+                    self.undone += 1
+                    return 0
+                return f
+            return super().__getattr__(name)
+
+    lib = Lib()
+    sim = Simulation.__new__(Simulation)
+    sim.config, sim.lib, sim.handle = cfg, lib, 0
+    sim.time, sim.step, sim.dt_global, sim.dt_history = 0.0, 0, 1.0e-6, []
+    others = [1, 0]                       # the other rank fails the first attempt, then succeeds
+    sim.reduce_step_status = lambda rc: max(rc, others.pop(0))
+    sim.gasdynamic_step()
+    assert lib.undone == 1 and lib.calls == [1.0e-6, 1.0e-6 * 0.2] and sim.step == 1
+    sim.reduce_step_status = lambda rc: -2
+    with pytest.raises(RuntimeError, match="another rank"):
+        sim.gasdynamic_step()
