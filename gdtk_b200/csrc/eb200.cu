@@ -77,7 +77,7 @@ struct Peer {
 };
 
 #define EB_P2P_MAGIC 0x65623270u
-#define EB_P2P_MAXPEERS 64
+
 struct P2PBlob {                              // what a rank tells one peer about itself; plain data, moved by the host layer
     unsigned magic;
     int exporter_rank, nprim, has_S;
@@ -407,13 +407,18 @@ int exchange_remote(Sim* s, double* prim, int buf)
         const unsigned long long seq = ++s->halo_seq;
         CUDA_OK(cudaEventRecord(s->ev_pack, s->stream));
         CUDA_OK(cudaStreamWaitEvent(s->comm_stream, s->ev_pack, 0));
+        if (s->P.shock_detect) {
+            // FlowState.S has a single buffer: the peers may overwrite my S ghost cells only after my previous stage
+            MODE_CALL(s, launch_halo_signal, s->d_remote_flags, np, seq, 1, s->comm_stream);
+            MODE_CALL(s, launch_halo_wait, (const unsigned long long*)s->d_shared, np, seq, 1, s->d_status, s->comm_stream);
+        }
         for (int p = 0; p < np; ++p) {
             Peer& pr = s->peers[p];
             MODE_CALL(s, launch_put, s->P, pr.r_total, prim, s->A.S, pr.r_prim[buf], pr.r_S, pr.d_send_idx, pr.d_dst_idx,
                       (long long)pr.send_idx.size(), s->comm_stream);
         }
-        MODE_CALL(s, launch_halo_signal, s->d_remote_flags, np, seq, s->comm_stream);
-        MODE_CALL(s, launch_halo_wait, (const unsigned long long*)s->d_shared, np, seq, s->d_status, s->comm_stream);
+        MODE_CALL(s, launch_halo_signal, s->d_remote_flags, np, seq, 0, s->comm_stream);
+        MODE_CALL(s, launch_halo_wait, (const unsigned long long*)s->d_shared, np, seq, 0, s->d_status, s->comm_stream);
         CUDA_OK(cudaEventRecord(s->ev_comm, s->comm_stream));
         return 0;
     }
@@ -1070,7 +1075,7 @@ int eb200_commit(int sim)
         // one allocation (one IPC handle) with what the peers need to see: the flags they raise and, per peer, the
         // arena indices of the ghost cells they fill (wire order)
         if (s->peers.size() > EB_P2P_MAXPEERS) { set_err("more than %d peer ranks", EB_P2P_MAXPEERS); return -1; }
-        size_t bytes = EB_P2P_MAXPEERS * sizeof(unsigned long long);
+        size_t bytes = 2 * EB_P2P_MAXPEERS * sizeof(unsigned long long);     // "landed" and "ready" flags
         for (Peer& p : s->peers) { p.recv_off = (long long)bytes; bytes += (p.recv_idx.size() * sizeof(int) + 255) / 256 * 256; }
         bytes = std::max<size_t>(bytes, (size_t)2 << 20);     // a whole allocation granule: nothing else shares the mapping
         if (dev_alloc(s, &s->d_shared, bytes)) return -100;

@@ -127,6 +127,7 @@ struct EbStageArgs {
 // ghost-cell work lists (indices into the arena)
 struct EbCopyItem { int dst, src; };
 struct EbReflectItem { int dst, src, fidx, meta; };   // meta = blk*4 + dir
+#define EB_P2P_MAXPEERS 64                    /* flags per slot in the region the halo peers of one rank share */
 struct EbFillItem { int dst, param; };
 
 // launchers implemented once per arithmetic mode (namespaces eb_strict / eb_fast)
@@ -155,8 +156,8 @@ struct EbFillItem { int dst, param; };
                        const double* buf, cudaStream_t st);                                              \
     void launch_put(const EbParams& P, long long total_dst, const double* prim_src, const double* S_src, double* prim_dst,  \
                     double* S_dst, const int* src_idx, const int* dst_idx, long long n, cudaStream_t st);  \
-    void launch_halo_signal(unsigned long long* const* remote_flags, int npeers, unsigned long long seq, cudaStream_t st); \
-    void launch_halo_wait(const unsigned long long* flags, int npeers, unsigned long long seq, int* status, cudaStream_t st); \
+    void launch_halo_signal(unsigned long long* const* remote_flags, int npeers, unsigned long long seq, int slot, cudaStream_t st); \
+    void launch_halo_wait(const unsigned long long* flags, int npeers, unsigned long long seq, int slot, int* status, cudaStream_t st); \
     void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A,             \
                               const double* prim, cudaStream_t st);                                      \
     }

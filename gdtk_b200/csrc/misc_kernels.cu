@@ -348,24 +348,27 @@ __global__ void put_kernel(long long total_src, long long total_dst, int nprim, 
     if (S_src) S_dst[cd] = S_src[cs];
 }
 // After the puts of one exchange (stream order): tell every peer that exchange `seq` has landed.
-__global__ void halo_signal_kernel(unsigned long long* const* __restrict__ remote_flags, int npeers, unsigned long long seq)
+// slot 0 = "my puts of exchange seq are in your memory", slot 1 = "I am done reading what exchange seq - 1 brought"
+// (raised before the puts: FlowState.S has one buffer only, so a peer must not overwrite it while the previous
+// stage still reads it; the three FlowState buffers need no such handshake).
+__global__ void halo_signal_kernel(unsigned long long* const* __restrict__ remote_flags, int npeers, unsigned long long seq, int slot)
 {
     const int p = threadIdx.x;
     if (p >= npeers) return;
     __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flags[p]), "l"(seq) : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flags[p] + slot * EB_P2P_MAXPEERS), "l"(seq) : "memory");
 }
 // Before the tiles that read those ghost cells: wait until every peer has signalled exchange `seq`.
 // (gives up after ~10 s of GPU clock and raises bit 1 of the step status: a peer that never signals -- a rank that
 //  died or took another number of steps -- must not hang the device)
-__global__ void halo_wait_kernel(const unsigned long long* __restrict__ flags, int npeers, unsigned long long seq, int* status)
+__global__ void halo_wait_kernel(const unsigned long long* __restrict__ flags, int npeers, unsigned long long seq, int slot, int* status)
 {
     const int p = threadIdx.x;
     if (p < npeers) {
         unsigned long long v;
         const long long t0 = clock64();
         do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + slot * EB_P2P_MAXPEERS + p) : "memory");
             if (v < seq && clock64() - t0 > 20000000000LL) { atomicOr(status, 3); break; }
         } while (v < seq);
     }
@@ -377,13 +380,13 @@ void launch_put(const EbParams& P, long long total_dst, const double* prim_src, 
     if (n > 0) put_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.total, total_dst, P.nprim, prim_src, P.shock_detect ? S_src : nullptr,
                                                                       prim_dst, S_dst, src_idx, dst_idx, n);
 }
-void launch_halo_signal(unsigned long long* const* remote_flags, int npeers, unsigned long long seq, cudaStream_t st)
+void launch_halo_signal(unsigned long long* const* remote_flags, int npeers, unsigned long long seq, int slot, cudaStream_t st)
 {
-    halo_signal_kernel<<<1, 64, 0, st>>>(remote_flags, npeers, seq);
+    halo_signal_kernel<<<1, 64, 0, st>>>(remote_flags, npeers, seq, slot);
 }
-void launch_halo_wait(const unsigned long long* flags, int npeers, unsigned long long seq, int* status, cudaStream_t st)
+void launch_halo_wait(const unsigned long long* flags, int npeers, unsigned long long seq, int slot, int* status, cudaStream_t st)
 {
-    halo_wait_kernel<<<1, 64, 0, st>>>(flags, npeers, seq, status);
+    halo_wait_kernel<<<1, 64, 0, st>>>(flags, npeers, seq, slot, status);
 }
 
 void launch_pack(const EbParams& P, const double* prim, const double* S, const int* idx, long long n, double* buf, cudaStream_t st)
