@@ -107,7 +107,7 @@ class ClockSampler:
 def spec_of(args, workload=None, **over):
     """A workload description: the command-line defaults with overrides (used for the `also` entries)."""
     d = {"workload": workload or args.workload, "n": args.n, "nb": args.nb, "flux": args.flux, "sheared": args.sheared,
-         "dt_scale": args.dt_scale, "ffs_nx": args.ffs_nx, "ffs_ny": args.ffs_ny, "kernel": args.kernel}
+         "dt_scale": args.dt_scale, "M_inf": None, "ffs_nx": args.ffs_nx, "ffs_ny": args.ffs_ny, "kernel": args.kernel}
     d.update(over)
     return d
 
@@ -125,10 +125,11 @@ def build_case(spec):
                 f"{spec['n'] // spec['nb']}^3, l2r2+van Albada, {spec['flux']}, pc")
         balg = 560.0
     else:
-        cfg, gm, blocks = cases.box3d(n=spec["n"], nb=spec["nb"], flux_calculator=spec["flux"], sheared=spec["sheared"])
+        extra = {"M_inf": spec["M_inf"]} if spec.get("M_inf") else {}
+        cfg, gm, blocks = cases.box3d(n=spec["n"], nb=spec["nb"], flux_calculator=spec["flux"], sheared=spec["sheared"], **extra)
         name = (f"synthetic 3D {spec['n']}^3 ideal-air box, {spec['nb'] ** 3} blocks of {spec['n'] // spec['nb']}^3, "
                 f"{'k-lines sheared by 10 degrees (general-metric path)' if spec['sheared'] else 'uniform Cartesian'}, "
-                f"l2r2+van Albada, {spec['flux']}, pc")
+                f"l2r2+van Albada, {spec['flux']}, pc" + (f", config.M_inf = {spec['M_inf']}" if spec.get("M_inf") else ""))
         # 280 B per cell-update; general-metric blocks read 272 B of metrics per stage on top
         balg = 824.0 if spec["sheared"] else 280.0
     cfg.force_generic_kernel = {"auto": 0, "generic": 1, "v2": 2}[spec["kernel"]]
@@ -291,32 +292,51 @@ def run_real_loop(args, sim, dt, ncells, world, ext, steps):
 
 def run_e2e(args, sim, dt, ncells, world):
     """Same metric through the C ABI with host buffers: per step upload (pinned host -> device),
-    step, download (device -> pinned host)."""
+    step, download (device -> pinned host).  A single-species job sends the five independent FlowState variables
+    (eb200_upload_flow's short form: rho, u, velocity; p, T, a follow on the device) and reads back the five conserved
+    quantities (eb200_download_conserved); a multi-species job moves whole FlowStates both ways."""
     import torch
     lib, h = sim.lib, sim.handle
     nprim = sim.nprim
+    short = nprim == 8
+    ncq = 5 if sim.config.dimensions == 3 else 4
     host = {}
     h2d = d2h = 0
+
+    def pinned(n, count):
+        bufs = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(count)]
+        return bufs, (C.POINTER(C.c_double) * count)(*[C.cast(t.data_ptr(), C.POINTER(C.c_double)) for t in bufs])
+
     for b in sim.local_blocks:
         g = b.geom
         n = g.NK * g.NJ * g.NI
-        bufs = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(nprim)]
-        ptrs = (C.POINTER(C.c_double) * nprim)(*[C.cast(t.data_ptr(), C.POINTER(C.c_double)) for t in bufs])
+        bufs, ptrs = pinned(n, nprim)
         lib.check(lib.download_flow(h, b.id, ptrs, nprim), "download_flow")
-        host[b.id] = (bufs, ptrs)
-        h2d += n * nprim * 8
-        d2h += n * nprim * 8
+        if short:
+            up = [bufs[0], bufs[1], bufs[5], bufs[6], bufs[7]]
+            up_ptrs = (C.POINTER(C.c_double) * 5)(*[C.cast(t.data_ptr(), C.POINTER(C.c_double)) for t in up])
+            down, down_ptrs = pinned(n, ncq)
+            host[b.id] = (up, up_ptrs, 5, down, down_ptrs, ncq)
+            h2d += n * 5 * 8
+            d2h += n * ncq * 8
+        else:
+            host[b.id] = (bufs, ptrs, nprim, bufs, ptrs, nprim)
+            h2d += n * nprim * 8
+            d2h += n * nprim * 8
     nbad = C.c_int(0)
     nsteps = max(1, min(args.steps, args.e2e_steps))
 
     def one_step():
-        for bid, (_, ptrs) in host.items():
-            lib.check(lib.upload_flow(h, bid, ptrs, nprim), "upload_flow")
+        for bid, (_, up_ptrs, nup, _, _, _) in host.items():
+            lib.check(lib.upload_flow(h, bid, up_ptrs, nup), "upload_flow")
         rc = lib.step(h, 0.0, dt, C.byref(nbad))
         if rc != 0:
             raise RuntimeError(f"e2e step returned {rc}: {lib.error()}")
-        for bid, (_, ptrs) in host.items():
-            lib.check(lib.download_flow(h, bid, ptrs, nprim), "download_flow")
+        for bid, (_, _, _, _, down_ptrs, ndown) in host.items():
+            if short:
+                lib.check(lib.download_conserved(h, bid, down_ptrs, ndown), "download_conserved")
+            else:
+                lib.check(lib.download_flow(h, bid, down_ptrs, ndown), "download_flow")
 
     one_step()          # warm
     torch.cuda.synchronize()
@@ -340,7 +360,8 @@ def run_e2e(args, sim, dt, ncells, world):
         h2d, d2h = int(h2d_t[0]), int(h2d_t[1])
     return {"value": ncells * nsteps / el, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": nsteps,
-            "note": "eb200_upload_flow + eb200_step + eb200_download_flow per step, pinned host buffers (bytes summed over ranks)"}
+            "note": ("eb200_upload_flow (rho, u, velocity) + eb200_step + eb200_download_conserved" if short else
+                     "eb200_upload_flow + eb200_step + eb200_download_flow") + " per step, pinned host buffers (bytes summed over ranks)"}
 
 
 def run_parity_check(args, rank, world, local_rank):
@@ -409,6 +430,26 @@ def run_chicken(args, n=256, steps=30):
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
     return {"unavailable": f"chkn-run did not produce two progress lines: {last_err}"}
+
+
+def bind_near_gpu(local_rank):
+    """Multi-rank runs: keep this rank's threads (and with them its pinned host buffers, first touch) on the CPUs
+    the driver names as closest to its GPU, so that the host<->device copies of the e2e figure do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hdl, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def oracle_library():
@@ -511,6 +552,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         try:     # halo messages on a high-priority NCCL stream: they run beside the interior tiles
@@ -538,8 +580,9 @@ def main():
             others.append(("ffs_4096x1024", spec_of(args, "ffs", flux="ausmdv")))
             others.append(("box3d_256_general_metric", spec_of(args, "box3d", n=256, nb=2, sheared=True, flux="ausmdv")))
             for fx in ("hanel", "ldfss0", "ldfss2", "roe", "ausm_plus_up", "adaptive_hanel_ausmdv"):
-                # ausm_plus_up is not stable at the full CFL step on the noisy box (in the oracle either): a quarter step
-                others.append((f"box3d_256_{fx}", spec_of(args, "box3d", n=256, nb=2, flux=fx, dt_scale=0.25 if fx == "ausm_plus_up" else 1.0)))
+                # ausm_plus_up needs its representative Mach number: with the default config.M_inf = 0.01 the Mach-1.5 box
+                # blows up within eight steps (in the oracle too); with the inflow Mach number it runs at the CFL step
+                others.append((f"box3d_256_{fx}", spec_of(args, "box3d", n=256, nb=2, flux=fx, M_inf=1.5 if fx == "ausm_plus_up" else None)))
         # configs[4]: thermally perfect 5-species air 256^3, on one GPU and spread over the GPUs of the run
         others.append(("tpg_256", spec_of(args, "tpg", n=256, nb=(2 if world == 1 else 4), flux="ausmdv")))
         for key, sp in others:

@@ -23,15 +23,16 @@ FACE_NAMES = ["west", "east", "south", "north", "bottom", "top"]
 FLUX_CALCULATORS = {
     "ausmdv": 0, "hanel": 1, "ldfss0": 2, "ldfss2": 3, "ausm_plus_up": 4, "roe": 5,
     "adaptive_hanel_ausmdv": 6, "adaptive_hanel_ausm_plus_up": 7, "adaptive_ldfss0_ldfss2": 8,
-    "efm": 9, "adaptive_efm_ausmdv": 10, "adaptive": 10,
+    "efm": 9, "adaptive_efm_ausmdv": 10, "adaptive": 10, "hllc": 11, "hlle2": 12,
 }
 # config.gasdynamic_update_scheme names (reference src/eilmer/globalconfig.d:126-200)
 UPDATE_SCHEMES = {
     "euler": 0, "pc": 1, "predictor-corrector": 1, "predictor_corrector": 1,
     "midpoint": 2, "classic-rk3": 3, "classic_rk3": 3, "tvd-rk3": 4, "tvd_rk3": 4,
+    "denman-rk3": 5, "denman_rk3": 5, "classic-rk4": 6, "classic_rk4": 6,
 }
 THERMO_INTERPOLATORS = {"rhou": 0, "pt": 1, "rhop": 2, "rhot": 3}
-N_STAGES = {0: 1, 1: 2, 2: 2, 3: 3, 4: 3}
+N_STAGES = {0: 1, 1: 2, 2: 2, 3: 3, 4: 3, 5: 3, 6: 4}
 
 GAS_IDEAL, GAS_THERMALLY_PERFECT = 0, 1
 

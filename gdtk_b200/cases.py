@@ -28,20 +28,20 @@ def ideal_air():
     return IdealGas(mMass=0.02896, gamma=1.4, name="air")
 
 
-def cone20(flux_calculator="ausmdv", nx0=10, nx1=30, ny=40, fbarray=False, **cfg_kw):
+def cone20(flux_calculator="ausmdv", nx0=10, nx1=30, ny=40, fbarray=False, gmodel=None, inflow=None, initial=None, **cfg_kw):
     """Mach 1.5 flow over a 20-degree cone, 2D axisymmetric, 2 blocks (C1).
 
     Geometry, states and settings of cone20.lua:26-66.  Differences, both forced by
     scope: config.flux_calculator is set explicitly (the reference default is the
     adaptive hanel/ausmdv blend) and the second patch uses the same
     straight-edged Coons patch as the first one instead of gridType="ao"."""
-    gm = ideal_air()
+    gm = gmodel or ideal_air()
     cfg = Config(dimensions=2, axisymmetric=True, flux_calculator=flux_calculator,
                  max_time=5.0e-3, max_step=3000, cfl_value=0.5, extrema_clipping=False)
     for k, v in cfg_kw.items():
         setattr(cfg, k, v)
-    initial = FlowState(gm, p=5955.0, T=304.0, velx=0.0)
-    inflow = FlowState(gm, p=95.84e3, T=1103.0, velx=1000.0)
+    initial = initial or FlowState(gm, p=5955.0, T=304.0, velx=0.0)
+    inflow = inflow or FlowState(gm, p=95.84e3, T=1103.0, velx=1000.0)
     a, b, c = (0.0, 0.0), (0.2, 0.0), (1.0, 0.29118)
     d, e, f = (1.0, 1.0), (0.2, 1.0), (0.0, 1.0)
     grid0 = quad_patch_grid(a, b, e, f, nx0, ny)
@@ -216,19 +216,45 @@ def tpg_box3d(n=32, nb=2, gas_file=None, **kw):
     return box3d(n=n, nb=nb, gmodel=gm, inflow=inflow, **kw)
 
 
-def ffs(nx=384, ny=128, flux_calculator="ausmdv", uniform_fast=True, **cfg_kw):
+def tpg_air(gas_file=None):
+    """The 5-species thermally perfect air of C5 and its free-stream composition."""
+    gas_file = gas_file or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                        "tests", "golden", "gas", "therm-perf-5-species-air.json")
+    gm = set_gas_model(gas_file)
+    massf = {"N2": 0.767 * 0.99, "O2": 0.233 * 0.99, "NO": 0.004, "N": 0.003, "O": 0.003}
+    return gm, massf
+
+
+def tpg_ffs(nx=120, ny=40, **kw):
+    """The forward-facing step with the thermally perfect 5-species air (2D, uniform-Cartesian blocks)."""
+    gm, massf = tpg_air()
+    probe = FlowState(gm, p=101.325e3, T=2500.0, massf=massf)
+    inflow = FlowState(gm, p=101.325e3, T=2500.0, velx=3.0 * probe.gas.a, massf=massf)
+    return ffs(nx=nx, ny=ny, gmodel=gm, inflow=inflow, **kw)
+
+
+def tpg_cone20(**kw):
+    """cone20's geometry (2D axisymmetric, general-metric blocks) with the thermally perfect 5-species air."""
+    gm, massf = tpg_air()
+    initial = FlowState(gm, p=5955.0, T=2000.0, massf=massf)
+    inflow = FlowState(gm, p=95.84e3, T=3000.0, velx=1500.0, massf=massf)
+    return cone20(gmodel=gm, inflow=inflow, initial=initial, **kw)
+
+
+def ffs(nx=384, ny=128, flux_calculator="ausmdv", uniform_fast=True, gmodel=None, inflow=None, **cfg_kw):
     """Mach-3 forward-facing step (C2): domain [0,3]x[0,1], step at x=0.6, height 0.2
     (examples/eilmer/2D/forward-facing-step/ffs.lua:21-32), three blocks like the example:
     blk0 [0,0.6]x[0,0.2], blk1 [0,0.6]x[0.2,1], blk2 [0.6,3]x[0.2,1].  nx, ny are the cell
     counts of the bounding grid (4096 x 1024 for the benchmark); dx = 3/nx, dy = 1/ny."""
-    gm = ideal_air()
+    gm = gmodel or ideal_air()
     cfg = Config(dimensions=2, flux_calculator=flux_calculator, max_step=10, max_time=1.0,
                  dt_init=1.0e-3, cfl_value=0.5)
     for k, v in cfg_kw.items():
         setattr(cfg, k, v)
-    T0 = 300.0
-    a0 = math.sqrt(gm.gamma * gm.Rgas * T0)
-    inflow = FlowState(gm, p=101.325e3, T=T0, velx=3.0 * a0)
+    if inflow is None:
+        T0 = 300.0
+        a0 = math.sqrt(gm.gamma * gm.Rgas * T0)
+        inflow = FlowState(gm, p=101.325e3, T=T0, velx=3.0 * a0)
     dx, dy = 3.0 / nx, 1.0 / ny
     i_step, j_step = int(round(0.6 / dx)), int(round(0.2 / dy))
     specs = [(0, i_step, 0, j_step), (0, i_step, j_step, ny), (i_step, nx, j_step, ny)]

@@ -888,6 +888,121 @@ __device__ __forceinline__ void flux_roe(const Prim<NSP>& L, const Prim<NSP>& R,
 }
 
 
+// fluxcalc.d:650-816 hllc (Toro's HLLC with Einfeldt's wave speeds); single temperature, no turbulence, factor = 1
+template <int DIM, int NSP>
+__device__ __forceinline__ void flux_hllc(const Prim<NSP>& L, const Prim<NSP>& R, double gL, double gR, double* F)
+{
+    typedef Layout<DIM, NSP> Lay;
+    const double rL = L.rho, pL = L.p, uL = L.vx, vL = L.vy, wL = (DIM == 3 ? L.vz : 0.0), eL = L.u, aL = L.a;
+    const double keL = 0.5 * (uL * uL + vL * vL + wL * wL);
+    const double EL = rL * eL + rL * keL;
+    const double rR = R.rho, pR = R.p, uR = R.vx, vR = R.vy, wR = (DIM == 3 ? R.vz : 0.0), eR = R.u, aR = R.a;
+    const double keR = 0.5 * (uR * uR + vR * vR + wR * wR);
+    const double ER = rR * eR + rR * keR;
+    const double sL = eb_sqrt(rL), sR = eb_sqrt(rR), sden = sL + sR;          // recomputed in the reference; same values
+    const double uhat = eb_div((sL * uL + sR * uR), sden);
+    const double ghat = eb_div((sL * gL + sR * gR), sden);
+    const double ahat2 = (eb_div((sL * aL * aL + sR * aR * aR), sden)) +
+                         0.5 * (ghat - 1.0) * (eb_div(sden, eb_sqrt(sden))) * (uR - uL) * (uR - uL);
+    const double ahat = eb_sqrt(ahat2);
+    const double SL = fmin(uL - aL, uhat - ahat);
+    const double SR = fmax(uR + aR, uhat + ahat);
+    const double S_star = eb_div((pR - pL + rL * uL * (SL - uL) - rR * uR * (SR - uR)), (rL * (SL - uL) - rR * (SR - uR)));
+    bool star_region;
+    double coeff, r, p, u, v, w, E, S;
+    if (S_star > 0.0) {
+        r = rL; p = pL; u = uL; v = vL; w = wL; E = EL; S = SL;
+        if (SL > 0.0) { star_region = false; coeff = 0.0; }
+        else { star_region = true; coeff = eb_div(rL * (SL - uL), (SL - S_star)); }
+    } else {
+        r = rR; p = pR; u = uR; v = vR; w = wR; E = ER; S = SR;
+        if (SR < 0.0) { star_region = false; coeff = 0.0; }
+        else { star_region = true; coeff = eb_div(rR * (SR - uR), (SR - S_star)); }
+    }
+    const double F_mass = r * u;
+    const double ru_half = star_region ? F_mass + S * (coeff - r) : F_mass;
+    F[Lay::iMass] = ru_half;
+    const double F_momx = r * u * u + p, F_momy = r * u * v, F_momz = r * u * w;
+    if (star_region) {
+        F[Lay::iXMom] = (F_momx + S * (coeff * S_star - r * u));
+        F[Lay::iYMom] = (F_momy + S * (coeff * v - r * v));
+        if (DIM == 3) F[Lay::iZMom] = (F_momz + S * (coeff * w - r * w));
+    } else {
+        F[Lay::iXMom] = F_momx;
+        F[Lay::iYMom] = F_momy;
+        if (DIM == 3) F[Lay::iZMom] = F_momz;
+    }
+    const double F_totenergy = u * (E + p);
+    if (star_region) {
+        const double U_star_totenergy = coeff * (eb_div(E, r) + (S_star - u) * (S_star + eb_div(p, (r * (S - u)))));
+        F[Lay::iEnergy] = (F_totenergy + S * (U_star_totenergy - E));
+    } else F[Lay::iEnergy] = (F_totenergy);
+    if (NSP > 1) {
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) F[Lay::iSpecies + i] = (ru_half * ((ru_half >= 0.0) ? L.massf[i] : R.massf[i]));
+    }
+}
+
+// fluxcalc.d:1779-1926 hlle2 (HLL with Einfeldt's wave speeds).  In the subsonic branch the reference adds the
+// z-momentum flux to the y-momentum entry (:1901) and leaves the z entry at zero: reproduced.
+template <int DIM, int NSP>
+__device__ __forceinline__ void flux_hlle2(const Prim<NSP>& L, const Prim<NSP>& R, double gL, double gR, double* F)
+{
+    typedef Layout<DIM, NSP> Lay;
+    EB_UNPACK_LR
+    const double sL = eb_sqrt(rL), sR = eb_sqrt(rR), sden = sL + sR;
+    const double uhat = eb_div((sL * uL + sR * uR), sden);
+    const double ghat = eb_div((sL * gL + sR * gR), sden);
+    const double ahat2 = (eb_div((sL * aL * aL + sR * aR * aR), sden)) +
+                         0.5 * (ghat - 1.0) * (eb_div(sden, eb_sqrt(sden))) * (uR - uL) * (uR - uL);
+    const double ahat = eb_sqrt(ahat2);
+    const double SLm = fmin(uL - aL, uhat - ahat);
+    const double SRp = fmax(uR + aR, uhat + ahat);
+    if (SLm >= 0) {
+        F[Lay::iMass] = (rL * uL);
+        F[Lay::iXMom] = (rL * uL * uL + pL);
+        F[Lay::iYMom] = (rL * uL * vL);
+        if (DIM == 3) F[Lay::iZMom] = (rL * uL * wL);
+        F[Lay::iEnergy] = (rL * uL * HL);
+        if (NSP > 1) {
+#pragma unroll
+            for (int i = 0; i < NSP; ++i) F[Lay::iSpecies + i] = (rL * uL * L.massf[i]);
+        }
+    } else if (SRp <= 0) {
+        F[Lay::iMass] = (rR * uR);
+        F[Lay::iXMom] = (rR * uR * uR + pR);
+        F[Lay::iYMom] = (rR * uR * vR);
+        if (DIM == 3) F[Lay::iZMom] = (rR * uR * wR);
+        F[Lay::iEnergy] = (rR * uR * HR);
+        if (NSP > 1) {
+#pragma unroll
+            for (int i = 0; i < NSP; ++i) F[Lay::iSpecies + i] = (rR * uR * R.massf[i]);
+        }
+    } else {
+#ifdef EB_FAST_MATH
+        const double rdS = eb_rcp(SRp - SLm);
+#define EB_HLLE_DIV(x) ((x) * rdS)
+#else
+#define EB_HLLE_DIV(x) ((x) / (SRp - SLm))
+#endif
+        const double ru_half = EB_HLLE_DIV(SRp * rL * uL - SLm * rR * uR + SLm * SRp * (rR - rL));
+        F[Lay::iMass] = ru_half;
+        F[Lay::iXMom] = EB_HLLE_DIV(SRp * (rL * uL * uL + pL) - SLm * (rR * uR * uR + pR) + SLm * SRp * (rR * uR - rL * uL));
+        double fy = EB_HLLE_DIV(SRp * (rL * uL * vL) - SLm * (rR * uR * vR) + SLm * SRp * (rR * vR - rL * vL));
+        if (DIM == 3) {
+            fy += EB_HLLE_DIV(SRp * (rL * uL * wL) - SLm * (rR * uR * wR) + SLm * SRp * (rR * wR - rL * wL));
+            F[Lay::iZMom] = 0.0;
+        }
+        F[Lay::iYMom] = fy;
+        F[Lay::iEnergy] = EB_HLLE_DIV(SRp * (rL * uL * HL) - SLm * (rR * uR * HR) + SLm * SRp * (rR * HR - rL * HL));
+#undef EB_HLLE_DIV
+        if (NSP > 1) {
+#pragma unroll
+            for (int i = 0; i < NSP; ++i) F[Lay::iSpecies + i] = (ru_half * ((ru_half >= 0.0) ? L.massf[i] : R.massf[i]));
+        }
+    }
+}
+
 // fluxcalc.d:1280-1312 exxef: exp(-x^2) and erf(x) by a polynomial approximation
 __device__ __forceinline__ void exxef(double sn, double& exx, double& ef)
 {
@@ -987,6 +1102,8 @@ __device__ __forceinline__ void basic_flux(const EbParams& P, const EbGas* __res
     else if (BASE == EB200_FLUX_LDFSS2) flux_ldfss<DIM, NSP, 2>(L, R, F);
     else if (BASE == EB200_FLUX_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, NSP>(L, R, P.M_inf, F);
     else if (BASE == EB200_FLUX_ROE) flux_roe<DIM, NSP>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
+    else if (BASE == EB200_FLUX_HLLC) flux_hllc<DIM, NSP>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
+    else if (BASE == EB200_FLUX_HLLE2) flux_hlle2<DIM, NSP>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
     else flux_efm<DIM, NSP, GASM>(gas, L, R, F);
 }
 

@@ -125,6 +125,7 @@ struct Sim {
     cudaEvent_t ev_pack = nullptr, ev_comm = nullptr, ev_ghost = nullptr, ev_bnd = nullptr;
     int* d_tiles_int = nullptr; long long n_tiles_int = 0;   // tiles that read no ghost cell of another rank
     int* d_tiles_bnd = nullptr; long long n_tiles_bnd = 0;   // tiles that do
+    bool upload_unchecked = false;            // eb200_upload_flow was called since the status was last read
     int undo_cur = -1;                        // >= 0: the last step succeeded and can be taken back (eb200_undo_step)
     int cur = 0;                              // index of the primitive buffer holding the current state
     int U0 = 0;                               // index of the U level that currently plays U[0]
@@ -154,18 +155,21 @@ int n_stages_for(int scheme)
     switch (scheme) {
     case EB200_UPDATE_EULER: return 1;
     case EB200_UPDATE_PC: case EB200_UPDATE_MIDPOINT: return 2;
-    case EB200_UPDATE_CLASSIC_RK3: case EB200_UPDATE_TVD_RK3: return 3;
+    case EB200_UPDATE_CLASSIC_RK3: case EB200_UPDATE_TVD_RK3: case EB200_UPDATE_DENMAN_RK3: return 3;
+    case EB200_UPDATE_CLASSIC_RK4: return 4;
     }
     return 0;
 }
 // gamma tables of simcore_gasdynamic_step.d:1235-1395
-void stage_gammas(int scheme, int stage, double g[3])
+void stage_gammas(int scheme, int stage, double g[4])
 {
-    g[0] = g[1] = g[2] = 0.0;
+    g[0] = g[1] = g[2] = g[3] = 0.0;
     if (stage == 1) {
         switch (scheme) {
         case EB200_UPDATE_EULER: case EB200_UPDATE_PC: case EB200_UPDATE_TVD_RK3: g[0] = 1.0; break;
         case EB200_UPDATE_MIDPOINT: case EB200_UPDATE_CLASSIC_RK3: g[0] = 0.5; break;
+        case EB200_UPDATE_DENMAN_RK3: g[0] = 8.0 / 15.0; break;
+        case EB200_UPDATE_CLASSIC_RK4: g[0] = 1.0 / 2.0; break;
         }
     } else if (stage == 2) {
         switch (scheme) {
@@ -173,12 +177,18 @@ void stage_gammas(int scheme, int stage, double g[3])
         case EB200_UPDATE_MIDPOINT: g[0] = 0.0; g[1] = 1.0; break;
         case EB200_UPDATE_CLASSIC_RK3: g[0] = -1.0; g[1] = 2.0; break;
         case EB200_UPDATE_TVD_RK3: g[0] = 0.25; g[1] = 0.25; break;
+        case EB200_UPDATE_DENMAN_RK3: g[0] = -17.0 / 60.0; g[1] = 5.0 / 12.0; break;
+        case EB200_UPDATE_CLASSIC_RK4: g[0] = 0.0; g[1] = 1.0 / 2.0; break;
         }
-    } else {
+    } else if (stage == 3) {
         switch (scheme) {
         case EB200_UPDATE_CLASSIC_RK3: g[0] = 1.0 / 6.0; g[1] = 4.0 / 6.0; g[2] = 1.0 / 6.0; break;
         case EB200_UPDATE_TVD_RK3: g[0] = 1.0 / 6.0; g[1] = 1.0 / 6.0; g[2] = 4.0 / 6.0; break;
+        case EB200_UPDATE_DENMAN_RK3: g[0] = 0.0; g[1] = -5.0 / 12.0; g[2] = 3.0 / 4.0; break;
+        case EB200_UPDATE_CLASSIC_RK4: g[0] = 0.0; g[1] = 0.0; g[2] = 1.0; break;
         }
+    } else {
+        g[0] = 1.0 / 6.0; g[1] = 1.0 / 3.0; g[2] = 1.0 / 3.0; g[3] = 1.0 / 6.0;       // classic_rk4
     }
 }
 
@@ -511,7 +521,7 @@ int fill_local_ghost_cells(Sim* s, double* prim, bool all_copies)
 // at least four cells per direction (a cell has at most one target per direction).
 bool face_pushes(const Sim* s, const Block* b, int f, const Block** other)
 {
-    if (s->cfg.reserved_i[3] || s->P.shock_detect) return false;
+    if (s->cfg.reserved_i[3]) return false;
     const BC& bc = b->bc[f];
     if (bc.kind != EB200_BC_EXCHANGE_FULL_FACE) return false;
     const Block* ot = nullptr;
@@ -554,14 +564,18 @@ int enqueue_step(Sim* s, double dt)
         EbStageArgs S;
         memset(&S, 0, sizeof S);
         S.prim_in = prim_in; S.prim_out = prim_out;
+        S.cellS = s->P.shock_detect ? s->A.S : nullptr;      // FlowState.S goes with the FlowState (the ghost-cell kernel copies it too)
         S.tmaps = s->d_tmaps ? (const void*)(s->d_tmaps + (size_t)in_buf * s->local.size()) : nullptr;
-        S.U0 = s->A.U[s->Ulev[0]];
-        S.U_out = (stage == ns) ? s->A.U[s->Ulev[ns]] : nullptr;
+        // Denman's scheme builds every stage on the U of the stage before (U_old = cell.U[1], cell.U[2],
+        // simcore_gasdynamic_step.d:1303,1352), so every stage stores its U; the others start from U[0]
+        const bool denman = s->cfg.update_scheme == EB200_UPDATE_DENMAN_RK3;
+        S.U0 = s->A.U[s->Ulev[denman ? stage - 1 : 0]];
+        S.U_out = (stage == ns || denman) ? s->A.U[s->Ulev[stage]] : nullptr;
         for (int m = 0; m < 3; ++m) S.dUdt_prev[m] = (m < stage - 1) ? s->A.dUdt[m] : nullptr;
         S.dUdt_out = (stage < ns) ? s->A.dUdt[stage - 1] : nullptr;
-        double g[3]; stage_gammas(s->cfg.update_scheme, stage, g);
-        if (stage == 1) { S.dt_g[0] = dt * g[0]; S.dt_g[3] = dt; }
-        else { S.dt_g[0] = g[0]; S.dt_g[1] = g[1]; S.dt_g[2] = g[2]; S.dt_g[3] = dt; }
+        double g[4]; stage_gammas(s->cfg.update_scheme, stage, g);
+        if (stage == 1) { S.dt_g[0] = dt * g[0]; S.dt_g[4] = dt; }
+        else { S.dt_g[0] = g[0]; S.dt_g[1] = g[1]; S.dt_g[2] = g[2]; S.dt_g[3] = g[3]; S.dt_g[4] = dt; }
         S.stage = stage; S.n_stages = ns; S.status = s->d_status;
         cudaEvent_t e0, e1;
         if (record_flux_events(s, &e0, &e1)) return -100;
@@ -622,11 +636,10 @@ int eb200_init(const eb200_config* cfg)
     if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT && cfg->n_species != 5) {
         set_err("thermally perfect gas: kernels are built for 5 species (got %d)", cfg->n_species); return -1;
     }
-    if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT && cfg->dimensions != 3) {
-        set_err("thermally perfect gas: kernels are built for 3D only"); return -1;
+    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_HLLE2) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
+    if ((cfg->flux_calculator == EB200_FLUX_ROE || cfg->flux_calculator == EB200_FLUX_HLLC || cfg->flux_calculator == EB200_FLUX_HLLE2) && cfg->n_species > 1) {
+        set_err("roe, hllc and hlle2 with multiple species are not on this path yet"); return -1;
     }
-    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_ADAPTIVE_EFM_AUSMDV) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
-    if (cfg->flux_calculator == EB200_FLUX_ROE && cfg->n_species > 1) { set_err("roe with multiple species is not on this path yet"); return -1; }
     if (!n_stages_for(cfg->update_scheme)) { set_err("unsupported update scheme %d", cfg->update_scheme); return -1; }
     const bool adaptive = (cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV && cfg->flux_calculator <= EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) ||
                           cfg->flux_calculator == EB200_FLUX_ADAPTIVE_EFM_AUSMDV;
@@ -1119,24 +1132,44 @@ int eb200_commit(int sim)
     return 0;
 }
 
+// the deferred verdict on the uploads since the last check (status word 7)
+static int check_uploads(Sim* s, bool status_is_fresh)
+{
+    if (!s->upload_unchecked) return 0;
+    if (!status_is_fresh && read_status(s)) return -100;
+    s->upload_unchecked = false;
+    if (s->h_status[7]) {
+        CUDA_OK(cudaMemsetAsync(s->d_status + 7, 0, sizeof(int), s->stream));
+        set_err("decode_conserved failed for a FlowState given to eb200_upload_flow");
+        return -1;
+    }
+    return 0;
+}
+
 int eb200_upload_flow(int sim, int blk_id, const double* const* prims, int nprims)
 {
     Sim* s = get_sim(sim); if (!s) return -1;
     Block* b = get_blk(s, blk_id); if (!b) return -1;
     if (!s->committed || !b->local) { set_err("upload_flow needs a committed local block"); return -1; }
-    if (nprims != s->P.nprim) { set_err("expected %d primitive arrays", s->P.nprim); return -1; }
+    // short form (single-species gas): rho, u, velx, vely, velz -- the independent variables; p, T and a follow from
+    // them on the device (the encode + decode pass below computes them anyway), 5/8 of the bytes over PCIe
+    const bool short_form = (nprims == EB200_NPRIM_SHORT && s->P.nprim == EB200_NPRIM_BASE);
+    if (nprims != s->P.nprim && !short_form) { set_err("expected %d primitive arrays", s->P.nprim); return -1; }
     CUDA_OK(cudaSetDevice(s->cfg.device));
     const size_t bytes = (size_t)b->ncp * sizeof(double);
     double* prim = s->A.prim[s->cur];
     s->ghosts_stale = true;
     s->undo_cur = -1;
-    for (int v = 0; v < nprims; ++v)
-        CUDA_OK(cudaMemcpyAsync(prim + (long long)v * s->P.total + b->cell0, prims[v], bytes, cudaMemcpyHostToDevice, s->stream));
-    CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
-    MODE_CALL(s, launch_decode, s->P, s->cfg.gas_model, s->d_gas, s->hdesc[b->local_index], prim, prim, s->A.U[s->Ulev[0]], 1, s->d_status, s->stream);
+    static const int short_field[EB200_NPRIM_SHORT] = { 0, 1, 5, 6, 7 };
+    for (int v = 0; v < nprims; ++v) {
+        const int f = short_form ? short_field[v] : v;
+        CUDA_OK(cudaMemcpyAsync(prim + (long long)f * s->P.total + b->cell0, prims[v], bytes, cudaMemcpyHostToDevice, s->stream));
+    }
+    // no host synchronisation here: a cell that cannot be decoded raises status word 7, which the next eb200_step /
+    // eb200_run_steps / eb200_compute_dt reports (uploading 64 blocks then costs 64 copies, not 64 round trips)
+    MODE_CALL(s, launch_decode, s->P, s->cfg.gas_model, s->d_gas, s->hdesc[b->local_index], prim, prim, s->A.U[s->Ulev[0]], 1, s->d_status + 7, s->stream);
     CUDA_OK(cudaGetLastError());
-    if (read_status(s)) return -100;
-    if (s->h_status[0]) { set_err("decode_conserved failed at upload, block %d", blk_id); return -1; }
+    s->upload_unchecked = true;
     return 0;
 }
 
@@ -1198,6 +1231,7 @@ int eb200_compute_dt(int sim, double dt_current, double cfl_value, int check_cfl
     Sim* s = get_sim(sim); if (!s) return -1;
     if (!s->committed) { set_err("not committed"); return -1; }
     CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (check_uploads(s, false)) return -1;
     double cfl_allow;
     switch (s->n_stages) { case 1: cfl_allow = 0.9; break; case 2: cfl_allow = 1.2; break; case 3: cfl_allow = 1.6; break; default: cfl_allow = 0.9; }
     const double cfl_adjust = 0.5;
@@ -1234,6 +1268,7 @@ int eb200_compute_dt(int sim, double dt_current, double cfl_value, int check_cfl
 static int finish_steps(Sim* s, int cur0, int* n_bad_cells, bool can_restore)
 {
     if (read_status(s)) return -100;
+    if (check_uploads(s, true)) return -1;
     const int ns = s->n_stages;
     int bad = s->h_status[ns];
     int worst = 0;
@@ -1258,7 +1293,7 @@ int eb200_step(int sim, double t0, double dt, int* n_bad_cells)
     Sim* s = get_sim(sim); if (!s) return -1;
     if (!s->committed) { set_err("not committed"); return -1; }
     CUDA_OK(cudaSetDevice(s->cfg.device));
-    CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
+    CUDA_OK(cudaMemsetAsync(s->d_status, 0, 7 * sizeof(int), s->stream));
     const int cur0 = s->cur;
     int rc = enqueue_step(s, dt);
     if (rc) return rc;
@@ -1287,7 +1322,7 @@ int eb200_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells)
     if (!s->committed) { set_err("not committed"); return -1; }
     s->undo_cur = -1;
     CUDA_OK(cudaSetDevice(s->cfg.device));
-    CUDA_OK(cudaMemsetAsync(s->d_status, 0, 8 * sizeof(int), s->stream));
+    CUDA_OK(cudaMemsetAsync(s->d_status, 0, 7 * sizeof(int), s->stream));
     for (int n = 0; n < nsteps; ++n) {
         int rc = enqueue_step(s, dt);
         if (rc) return rc;

@@ -117,10 +117,11 @@ struct EbStageArgs {
     const double* U0; double* U_out;       // U_out: only written in the final stage (else nullptr)
     const double* dUdt_prev[3];            // residuals of earlier stages (nullptr when unused)
     double* dUdt_out;                      // nullptr when no later stage needs it
-    double dt_g[4];                        // stage 1: dt*g0 ; stage>1: g[0..2] and dt in [3]
+    double dt_g[5];                        // stage 1: dt*g0 in [0]; later stages: g[0..3]; dt in [4]
     int stage, n_stages;
     int* status;                           // [0] step-failed flag, [1..4] invalid-cell count per stage
     const int* tile_list;                  // CTA -> tile id (nullptr: identity); used to run interior tiles first
+    double* cellS;                         // FlowState.S per cell when the shock detector is on (travels with pushed ghost cells), else nullptr
     const void* tmaps;                     // CUtensorMap[local block] over prim_in (i, j, k, field), or nullptr: stage with cp.async
 };
 

@@ -258,12 +258,17 @@ __device__ __forceinline__ void finish_cell(const EbParams& P, const EbGas* __re
     } else if (S.stage == 2) {
 #pragma unroll
         for (int q = 0; q < NCQ; ++q)
-            U[q] = U0[q] + S.dt_g[3] * (S.dt_g[0] * d0[q] + S.dt_g[1] * dUdt[q]);
-    } else {
+            U[q] = U0[q] + S.dt_g[4] * (S.dt_g[0] * d0[q] + S.dt_g[1] * dUdt[q]);
+    } else if (S.stage == 3) {
 #pragma unroll
         for (int q = 0; q < NCQ; ++q)
-            U[q] = U0[q] + S.dt_g[3] * (S.dt_g[0] * d0[q] +
+            U[q] = U0[q] + S.dt_g[4] * (S.dt_g[0] * d0[q] +
                                         S.dt_g[1] * ldg(S.dUdt_prev[1] + q * total + c) + S.dt_g[2] * dUdt[q]);
+    } else {            // classic_rk4, simcore_gasdynamic_step.d:1376-1408
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q)
+            U[q] = U0[q] + S.dt_g[4] * (S.dt_g[0] * d0[q] + S.dt_g[1] * ldg(S.dUdt_prev[1] + q * total + c) +
+                                        S.dt_g[2] * ldg(S.dUdt_prev[2] + q * total + c) + S.dt_g[3] * dUdt[q]);
     }
     if (S.dUdt_out) {
 #pragma unroll
@@ -277,9 +282,9 @@ __device__ __forceinline__ void finish_cell(const EbParams& P, const EbGas* __re
     else {
         store_prim<NSP>(Q, S.prim_out, total, c);
         // ghost cells of same-GPU neighbours that mirror this cell (EbBlockDesc::push_off)
-        if (push0 >= 0) store_prim<NSP>(Q, S.prim_out, total, push0);
-        if (push1 >= 0) store_prim<NSP>(Q, S.prim_out, total, push1);
-        if (push2 >= 0) store_prim<NSP>(Q, S.prim_out, total, push2);
+        if (push0 >= 0) { store_prim<NSP>(Q, S.prim_out, total, push0); if (S.cellS) S.cellS[push0] = S.cellS[c]; }
+        if (push1 >= 0) { store_prim<NSP>(Q, S.prim_out, total, push1); if (S.cellS) S.cellS[push1] = S.cellS[c]; }
+        if (push2 >= 0) { store_prim<NSP>(Q, S.prim_out, total, push2); if (S.cellS) S.cellS[push2] = S.cellS[c]; }
         if (!check_data<NSP>(P, Q)) n_invalid++;
     }
     if (S.U_out) {
@@ -514,7 +519,7 @@ void launch_face_debug_impl(const EbParams& P, int gas_model, const EbGas* gas, 
     if (gas_model == EB200_GAS_IDEAL) { if (P.dims == 3) EB_DBG(3, EB200_GAS_IDEAL, 1); else EB_DBG(2, EB200_GAS_IDEAL, 1); }
     else {
 #if EB_FLUX_HAS_TPG
-        if (P.nsp == 5 && P.dims == 3) EB_DBG(3, EB200_GAS_THERMALLY_PERFECT, 5);
+        if (P.nsp == 5) { if (P.dims == 3) EB_DBG(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_DBG(2, EB200_GAS_THERMALLY_PERFECT, 5); }
 #endif
     }
 #undef EB_DBG
@@ -535,7 +540,9 @@ void launch_flux_update_impl(const EbParams& P, int gas_model, const EbGas* gas,
         if (P.dims == 3) EB_LAUNCH(3, EB200_GAS_IDEAL, 1); else EB_LAUNCH(2, EB200_GAS_IDEAL, 1);
     } else {
 #if EB_FLUX_HAS_TPG
-        if (P.nsp == 5 && P.dims == 3) EB_LAUNCH(3, EB200_GAS_THERMALLY_PERFECT, 5);     // C5 is 3D; 2D TPG kernels are not built
+#ifndef EB_TP_DEV3D
+        if (P.nsp == 5) { if (P.dims == 3) EB_LAUNCH(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_LAUNCH(2, EB200_GAS_THERMALLY_PERFECT, 5); }
+#endif
 #endif
     }
 #undef EB_LAUNCH

@@ -27,6 +27,15 @@
 #ifndef EB_V3_TRYSPLIT
 #define EB_V3_TRYSPLIT 1      // poll the next plane's barrier early, consume the answer after independent loads
 #endif
+#ifndef EB_V3_CLIPVOTE
+#define EB_V3_CLIPVOTE 0      // throughput build: extrema clipping behind a warp vote (measured: slower, 3.9 vs 5.1 G on the noisy box)
+#endif
+#ifndef EB_V3_NH
+#define EB_V3_NH 2            // helper warps: 1 = one warp owns the whole tile halo, 2 = one for the halo along i (and the TMA issue), one along j
+#endif
+#ifndef EB_V3_SPIN
+#define EB_V3_SPIN 1          // waiting on a CTA barrier: 0 = poll, 1 = try_wait with a suspend-time hint, 2 = poll with nanosleep back-off
+#endif
 #ifndef EB_V3_MIN_CTAS
 #define EB_V3_MIN_CTAS ((EB_V3_TY >= 16) ? 1 : 2)     // 17 warps x 112 registers fill an SM; 9-warp CTAs come in pairs
 #endif
@@ -82,6 +91,45 @@ __device__ __forceinline__ void load_cell5(const double* __restrict__ t, int o, 
     q[4] = (DIM == 3) ? t[(T::F_V + 2) * T::FSZ + o] : 0.0;
 }
 
+#if defined(EB_FAST_MATH) && EB_V3_CLIPVOTE
+// The same reconstruction with the extrema clipping behind a warp vote: in smooth flow no lane of a warp needs it
+// (an increment points away from its neighbour only at a local extremum, and overshoots only where epsilon rules
+// the limiter), so the selects leave the main path.  Same values as recon_cell_scalar<true>.
+__device__ __forceinline__ bool clip_needed(double inc, double d)
+{
+    return ((__double2hiint(inc) ^ __double2hiint(d)) < 0) || (fabs(inc) > fabs(d));
+}
+template <int NV>
+__device__ __forceinline__ void recon_cell_voted(const EbBlockDesc& D, int d, double eps, const double* qm, const double* q0,
+                                                 const double* qp, double* qM, double* qP)
+{
+    const double* __restrict__ K = D.uq[d];
+    double iP[NV], iM[NV];
+    bool need = false;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const double a = q0[v] - qm[v], b = qp[v] - q0[v];
+        const double ab = a * b;
+        const double n = (ab + fabs(ab)) + eps;
+        const double dn = fma(a, a, fma(b, b, eps));
+        const double s = n * eb_rcp(dn);
+        iP[v] = s * fma(a, K[1], b * K[0]);
+        iM[v] = s * fma(a, K[3], b * K[2]);
+        need = need || clip_needed(iP[v], b) || clip_needed(iM[v], a);
+    }
+    if (__any_sync(__activemask(), need)) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const double a = q0[v] - qm[v], b = qp[v] - q0[v];
+            iP[v] = ((__double2hiint(iP[v]) ^ __double2hiint(b)) < 0) ? 0.0 : ((fabs(iP[v]) > fabs(b)) ? b : iP[v]);
+            iM[v] = ((__double2hiint(iM[v]) ^ __double2hiint(a)) < 0) ? 0.0 : ((fabs(iM[v]) > fabs(a)) ? a : iM[v]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { qP[v] = q0[v] + iP[v]; qM[v] = q0[v] - iM[v]; }
+}
+#endif
+
 // positive?  (sign bit clear and not zero; the integer compare keeps the FP64 pipe out of it in the throughput build)
 __device__ __forceinline__ bool not_positive(double x)
 {
@@ -100,8 +148,14 @@ __device__ __forceinline__ void recon_cell(const EbBlockDesc& D, int d, double e
                                            const double* qp, double* qM, double* qP, bool& fbM, bool& fbP)
 {
     constexpr int NV = (DIM == 3) ? 5 : 4;
+#if defined(EB_FAST_MATH) && EB_V3_CLIPVOTE
+    if (CLIP) recon_cell_voted<NV>(D, d, eps, qm, q0, qp, qM, qP);
+    else
+#endif
+    {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) recon_cell_scalar<CLIP>(D, d, eps, qm[v], q0[v], qp[v], qM[v], qP[v]);
+        for (int v = 0; v < NV; ++v) recon_cell_scalar<CLIP>(D, d, eps, qm[v], q0[v], qp[v], qM[v], qP[v]);
+    }
     if (DIM == 2) { qM[4] = 0.0; qP[4] = 0.0; }
     fbM = not_positive(qM[1]) || not_positive(qM[0]);
     fbP = not_positive(qP[1]) || not_positive(qP[0]);
@@ -236,11 +290,16 @@ __device__ __forceinline__ void stage_update_v3(const EbStageArgs& S, long long 
         for (int q = 0; q < NCQ; ++q) U[q] = U0[q] + S.dt_g[0] * dUdt[q];
     } else if (S.stage == 2) {
 #pragma unroll
-        for (int q = 0; q < NCQ; ++q) U[q] = U0[q] + S.dt_g[3] * (S.dt_g[0] * d0[q] + S.dt_g[1] * dUdt[q]);
+        for (int q = 0; q < NCQ; ++q) U[q] = U0[q] + S.dt_g[4] * (S.dt_g[0] * d0[q] + S.dt_g[1] * dUdt[q]);
+    } else if (S.stage == 3) {
+#pragma unroll
+        for (int q = 0; q < NCQ; ++q)
+            U[q] = U0[q] + S.dt_g[4] * (S.dt_g[0] * d0[q] + S.dt_g[1] * ldg(S.dUdt_prev[1] + q * total + c) + S.dt_g[2] * dUdt[q]);
     } else {
 #pragma unroll
         for (int q = 0; q < NCQ; ++q)
-            U[q] = U0[q] + S.dt_g[3] * (S.dt_g[0] * d0[q] + S.dt_g[1] * ldg(S.dUdt_prev[1] + q * total + c) + S.dt_g[2] * dUdt[q]);
+            U[q] = U0[q] + S.dt_g[4] * (S.dt_g[0] * d0[q] + S.dt_g[1] * ldg(S.dUdt_prev[1] + q * total + c) +
+                                        S.dt_g[2] * ldg(S.dUdt_prev[2] + q * total + c) + S.dt_g[3] * dUdt[q]);
     }
     if (S.dUdt_out) {
 #pragma unroll
@@ -265,7 +324,7 @@ __device__ __forceinline__ void decode_store_v3(const EbParams& P, const EbGas* 
 #pragma unroll 1
             for (int n = 0; n < 3; ++n) {
                 const long long pt = (n == 0) ? push0 : ((n == 1) ? push1 : push2);
-                if (pt >= 0) store_prim<1>(Q, S.prim_out, total, pt);
+                if (pt >= 0) { store_prim<1>(Q, S.prim_out, total, pt); if (S.cellS) S.cellS[pt] = S.cellS[c]; }
             }
         }
         if (!check_data<1>(P, Q)) atomicAdd(&S.status[S.stage], 1);
@@ -306,8 +365,15 @@ __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigne
 {
     unsigned done;
     do {
+#if EB_V3_SPIN == 1
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+#else
+        done = mbar_try(bar, parity);
+#if EB_V3_SPIN == 2
+        if (!done) __nanosleep(40);
+#endif
+#endif
     } while (!done);
 }
 
@@ -324,7 +390,7 @@ __global__ void
 #ifdef EB_V3_MAXNREG
 __maxnreg__(EB_V3_MAXNREG)
 #else
-__launch_bounds__(32 * (TY + 1), EB_V3_MIN_CTAS)
+__launch_bounds__(32 * (TY + EB_V3_NH), EB_V3_MIN_CTAS)
 #endif
 flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc* __restrict__ descs, int nblocks,
                       const EbArena A, const EbStageArgs S)
@@ -334,7 +400,8 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
     typedef V3Smem<DIM, TY> SM;
     constexpr int NCQ = Lay::NCQ;
     constexpr int NBUF = SM::NBUF;
-    constexpr int NT = 32 * (TY + 1);
+    constexpr int NH = EB_V3_NH;
+    constexpr int NT = 32 * (TY + NH);
     extern __shared__ __align__(128) double smem[];
     double* const tile = smem + SM::O_TILE;
     double* const qPj = smem + SM::O_QPJ;
@@ -350,7 +417,7 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
 
     const int lane = threadIdx.x, wy = threadIdx.y;
     const int tid = wy * 32 + lane;
-    const bool helper = (wy == TY);
+    const bool helper = (wy >= TY);
     const long long cta = S.tile_list ? (long long)S.tile_list[blockIdx.x] : (long long)blockIdx.x;
     if (tid == 0) {
         int lo = 0, hi = nblocks - 1;
@@ -358,7 +425,7 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
         s_blk = lo;
 #pragma unroll
         for (int b = 0; b < NBUF; ++b) mbar_init(&s_bar[b], 1);
-        mbar_init(&s_sync[0], TY + 1); mbar_init(&s_sync[1], TY + 1); mbar_init(&s_sync[2], TY);
+        mbar_init(&s_sync[0], TY + 1); mbar_init(&s_sync[1], TY + NH); mbar_init(&s_sync[2], TY);
         mbar_fence_init();
     }
     __syncthreads();
@@ -407,7 +474,7 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
     auto wait_plane = [&](int m) { mbar_wait(&s_bar[(DIM == 3) ? m % 3 : 0], (unsigned)((m / 3) & 1)); };
     auto tile_of = [&](int m) -> const double* { return tile + ((DIM == 3) ? m % 3 : 0) * T::SIZE; };
 
-    if (helper && lane == 0) {
+    if (wy == TY && lane == 0) {
         issue_plane(0);
         if (DIM == 3) { issue_plane(1); issue_plane(2); }
     }
@@ -476,57 +543,73 @@ flux_update_kernel_v3(const EbParams P, const EbGas* __restrict__ gas, const EbB
                 }
             }
         };
+        const bool helpI = (NH == 1) || (wy == TY);       // owns the halo along i and the TMA refills
+        const bool helpJ = (NH == 1) || (wy == TY + 1);   // owns the halo along j
         // west halo of the first plane, before the start-up barrier
-        wait_plane((DIM == 3) ? 2 : 0);
-        halo_jobs(0, 0, nullptr, tile_of((DIM == 3) ? 2 : 0), k0);
-        if (DIM == 3) { wait_plane(0); wait_plane(1); }
+        if (helpI) {
+            wait_plane((DIM == 3) ? 2 : 0);
+            halo_jobs(0, 0, nullptr, tile_of((DIM == 3) ? 2 : 0), k0);
+            if (DIM == 3) { wait_plane(0); wait_plane(1); }
+        }
         __syncthreads();                                  // start-up barrier
-        if (DIM == 3 && lane == 0) issue_plane(3);        // plane k0 + 1 -> the buffer plane k0 - 2 has left
+        if (DIM == 3 && helpI && lane == 0) issue_plane(3);        // plane k0 + 1 -> the buffer plane k0 - 2 has left
         for (int k = k0; k < k1; ++k) {
             const int it = k - k0;
             const int m = (DIM == 3) ? it + 2 : 0;
             const double* t0 = tile_of(m);
             const bool next_has_cells = (DIM == 3) && (k + 1 < k1);
-            if (next_has_cells) wait_plane(m + 1);
-            // the jobs along i write buffers nobody reads any more (qPiH: three slots, fX: two; the helper has
-            // passed R of the last plane), so they run ahead of the main warps' last steps of the plane before
-            halo_jobs(next_has_cells ? 0 : 1, 1, t0, tile_of(m + 1), k + 1);
-            if (eastE) {
-                const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (j0 + hr + EB_NG)) * NI + (i0 + 32 + EB_NG);
-                double F[NCQ];
-                if (!outflow_override<DIM, 0>(P, D, S.prim_in, i0 + 32, nic, cf, 1, F)) {
-                    const bool fbL = unfold_flag(eL[1]);
-                    const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[0][cf] : 0.0;
-                    face_flux_v3<DIM, FLUX, 0>(P, gas, eL, t0[T::F_A * T::FSZ + oE - 1], fbL, cf - 1, eM, t0[T::F_A * T::FSZ + oE], efb, cf,
-                                               alpha, S.prim_in, F);
+            if (helpI) {
+                if (next_has_cells) wait_plane(m + 1);
+                // the jobs along i write buffers nobody reads any more (qPiH: three slots, fX: two; this warp has
+                // passed K of the last plane), so they run ahead of the main warps' last steps of the plane before
+                halo_jobs(next_has_cells ? 0 : 1, 1, t0, tile_of(m + 1), k + 1);
+                if (eastE) {
+                    const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (j0 + hr + EB_NG)) * NI + (i0 + 32 + EB_NG);
+                    double F[NCQ];
+                    if (!outflow_override<DIM, 0>(P, D, S.prim_in, i0 + 32, nic, cf, 1, F)) {
+                        const bool fbL = unfold_flag(eL[1]);
+                        const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[0][cf] : 0.0;
+                        face_flux_v3<DIM, FLUX, 0>(P, gas, eL, t0[T::F_A * T::FSZ + oE - 1], fbL, cf - 1, eM, t0[T::F_A * T::FSZ + oE], efb, cf,
+                                                   alpha, S.prim_in, F);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NCQ; ++q) fX[((it & 1) * NCQ + q) * TY + hr] = F[q];
                 }
-#pragma unroll
-                for (int q = 0; q < NCQ; ++q) fX[((it & 1) * NCQ + q) * TY + hr] = F[q];
-            }
-            if (it > 0) mbar_wait_sleep(barF, (unsigned)((it - 1) & 1));      // the main warps have read last plane's states along j
-            halo_jobs(2, 3, t0, nullptr, 0);
-            cta_arrive(barR, lane);
-            if (DIM == 3) {
-                mbar_wait_sleep(barK, (unsigned)(it & 1));          // every main warp has read plane k - 1
-                if (lane == 0) issue_plane(m + 2);            // plane k + 2 -> its buffer (the last one needed is k1 + 1)
-            }
-            mbar_wait_sleep(barR, (unsigned)(it & 1));
-            if (northE) {
-                const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (j0 + TY + EB_NG)) * NI + (i + EB_NG);
-                double F[NCQ];
-                if (!outflow_override<DIM, 1>(P, D, S.prim_in, j0 + TY, njc, cf, sj, F)) {
-                    double Ls[5];
-#pragma unroll
-                    for (int v = 0; v < 5; ++v) Ls[v] = qPj[(TY * 5 + v) * 32 + lane];
-                    const bool fbL = unfold_flag(Ls[1]);
-                    const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[1][cf] : 0.0;
-                    face_flux_v3<DIM, FLUX, 1>(P, gas, Ls, t0[T::F_A * T::FSZ + oN - T::COLS], fbL, cf - sj, nM, t0[T::F_A * T::FSZ + oN], nfb, cf,
-                                               alpha, S.prim_in, F);
+                if (NH == 2) {
+                    if (DIM == 3) {
+                        mbar_wait_sleep(barK, (unsigned)(it & 1));      // every main warp has read plane k - 1 (and, having passed F of
+                        if (lane == 0) issue_plane(m + 2);              // the plane before, so has the other helper): refill its buffer
+                    }
+                    cta_arrive(barF, lane);
                 }
-#pragma unroll
-                for (int q = 0; q < NCQ; ++q) fS[(q * (TY + 1) + TY) * 32 + lane] = F[q];
             }
-            cta_arrive(barF, lane);
+            if (helpJ) {
+                if (NH == 2) wait_plane(m);
+                if (it > 0) mbar_wait_sleep(barF, (unsigned)((it - 1) & 1));      // the main warps have read last plane's states along j
+                halo_jobs(2, 3, t0, nullptr, 0);
+                cta_arrive(barR, lane);
+                if (NH == 1 && DIM == 3) {
+                    mbar_wait_sleep(barK, (unsigned)(it & 1));          // every main warp has read plane k - 1
+                    if (lane == 0) issue_plane(m + 2);            // plane k + 2 -> its buffer (the last one needed is k1 + 1)
+                }
+                mbar_wait_sleep(barR, (unsigned)(it & 1));
+                if (northE) {
+                    const long long cf = D.cell0 + ((long long)(k + D.kg) * NJ + (j0 + TY + EB_NG)) * NI + (i + EB_NG);
+                    double F[NCQ];
+                    if (!outflow_override<DIM, 1>(P, D, S.prim_in, j0 + TY, njc, cf, sj, F)) {
+                        double Ls[5];
+#pragma unroll
+                        for (int v = 0; v < 5; ++v) Ls[v] = qPj[(TY * 5 + v) * 32 + lane];
+                        const bool fbL = unfold_flag(Ls[1]);
+                        const double alpha = FluxPair<FLUX>::adaptive ? A.Sf[1][cf] : 0.0;
+                        face_flux_v3<DIM, FLUX, 1>(P, gas, Ls, t0[T::F_A * T::FSZ + oN - T::COLS], fbL, cf - sj, nM, t0[T::F_A * T::FSZ + oN], nfb, cf,
+                                                   alpha, S.prim_in, F);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NCQ; ++q) fS[(q * (TY + 1) + TY) * 32 + lane] = F[q];
+                }
+                cta_arrive(barF, lane);
+            }
         }
         return;
     }
@@ -776,7 +859,7 @@ void launch_one_v3(const EbParams& P, const EbGas* gas, const EbBlockDesc* desc,
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    kern<<<(unsigned)ncta, dim3(32, TY + 1), smem, st>>>(P, gas, desc, nblocks, A, S);
+    kern<<<(unsigned)ncta, dim3(32, TY + EB_V3_NH), smem, st>>>(P, gas, desc, nblocks, A, S);
 }
 
 // uniform-Cartesian blocks, ideal gas, interpolation_order = 2, apply_limiter = true, TMA staging available

@@ -14,7 +14,7 @@ namespace EB_NS {
 EB_DECL_FLUX(0)
 #ifndef EB_DEV_FLUX0_ONLY
 EB_DECL_FLUX(1) EB_DECL_FLUX(2) EB_DECL_FLUX(3) EB_DECL_FLUX(4) EB_DECL_FLUX(5)
-EB_DECL_FLUX(6) EB_DECL_FLUX(7) EB_DECL_FLUX(8) EB_DECL_FLUX(9) EB_DECL_FLUX(10)
+EB_DECL_FLUX(6) EB_DECL_FLUX(7) EB_DECL_FLUX(8) EB_DECL_FLUX(9) EB_DECL_FLUX(10) EB_DECL_FLUX(11) EB_DECL_FLUX(12)
 #endif
 #define EB_DECL_DBG(k)                                                                                         \
     void launch_face_debug_k##k(const EbParams& P, int gas_model, const EbGas* gas, const EbArena& A,           \
@@ -22,7 +22,7 @@ EB_DECL_FLUX(6) EB_DECL_FLUX(7) EB_DECL_FLUX(8) EB_DECL_FLUX(9) EB_DECL_FLUX(10)
 EB_DECL_DBG(0)
 #ifndef EB_DEV_FLUX0_ONLY
 EB_DECL_DBG(1) EB_DECL_DBG(2) EB_DECL_DBG(3) EB_DECL_DBG(4) EB_DECL_DBG(5)
-EB_DECL_DBG(6) EB_DECL_DBG(7) EB_DECL_DBG(8) EB_DECL_DBG(9) EB_DECL_DBG(10)
+EB_DECL_DBG(6) EB_DECL_DBG(7) EB_DECL_DBG(8) EB_DECL_DBG(9) EB_DECL_DBG(10) EB_DECL_DBG(11) EB_DECL_DBG(12)
 #endif
 
 void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* gas, const EbArena& A, const double* prim,
@@ -41,6 +41,8 @@ void launch_face_debug(int flux_calc, int gm, const EbParams& P, const EbGas* ga
     case 8: launch_face_debug_k8(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 9: launch_face_debug_k9(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
     case 10: launch_face_debug_k10(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 11: launch_face_debug_k11(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
+    case 12: launch_face_debug_k12(P, gm, gas, A, prim, nfaces, Fout, ok_out, st); break;
 #endif
     }
 }
@@ -64,6 +66,8 @@ void launch_flux_update(int flux_calc, int gm, const EbParams& P, const EbGas* g
     case 8: launch_flux_update_k8(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 9: launch_flux_update_k9(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
     case 10: launch_flux_update_k10(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 11: launch_flux_update_k11(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
+    case 12: launch_flux_update_k12(P, gm, gas, desc, nblocks, ncta, A, S, ty, which, st); break;
 #endif
     }
 }
@@ -123,7 +127,7 @@ void launch_decode(const EbParams& P, int gas_model, const EbGas* gas, const EbB
 #define EB_DEC(DIM, GASM, NSP) decode_kernel<DIM, GASM, NSP><<<blocks, threads, 0, st>>>(P, gas, hdesc, prim_in, prim_out, U, do_encode, status)
     if (gas_model == EB200_GAS_IDEAL) { if (P.dims == 3) EB_DEC(3, EB200_GAS_IDEAL, 1); else EB_DEC(2, EB200_GAS_IDEAL, 1); }
 #ifndef EB_NO_TPG
-    else if (P.nsp == 5 && P.dims == 3) EB_DEC(3, EB200_GAS_THERMALLY_PERFECT, 5);
+    else if (P.nsp == 5) { if (P.dims == 3) EB_DEC(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_DEC(2, EB200_GAS_THERMALLY_PERFECT, 5); }
 #endif
 #undef EB_DEC
 }

@@ -208,19 +208,30 @@ def write_job(job_dir, job, cfg, gm, gas_model_file, blocks, sim, history_points
     io.write_solution_files(job_dir, job, sim, 0)
 
 
-def run_job(job_dir, job, lib=None, tindx_start=0, n_solutions=1, **overrides):
-    """integrate_in_time for a prepared job: load, run to config.max_time / max_step, write flow/tNNNN,
-    the history files and the .times entries.  Returns the Simulation (closed by the caller)."""
+def run_job(job_dir, job, lib=None, tindx_start=0, n_solutions=None, **overrides):
+    """integrate_in_time for a prepared job: load, run to config.max_time / max_step, write flow/tNNNN every
+    config.dt_plot of simulated time (n_solutions, when given, spaces that many solutions evenly instead) and at
+    the end, the history files and the .times entries.  A restart (tindx_start > 0) takes its time step from
+    config/<job>.times like init_simulation (simcore.d:257-268).  Returns the Simulation (closed by the caller)."""
     from .sim import Simulation
     cfg, gm, blocks, hist, t0 = load_job(job_dir, job, tindx_start, **overrides)
     sim = Simulation(cfg, gm, blocks, lib=lib) if lib is not None else Simulation(cfg, gm, blocks)
     sim.time = t0
+    if tindx_start > 0:
+        try:
+            sim.dt_global = io.read_times(job_dir, job)[tindx_start][1]
+        except (OSError, KeyError):
+            pass
     keys = [sim.set_history_point(*h) for h in hist]
-    t_end, dt_plot = cfg.max_time, (cfg.max_time - t0) / max(1, n_solutions)
-    for n in range(1, n_solutions + 1):
+    t_end = cfg.max_time
+    dt_plot = (t_end - t0) / max(1, n_solutions) if n_solutions else float(getattr(cfg, "dt_plot", t_end - t0))
+    dt_plot = max(dt_plot, 1.0e-300)
+    n = 0
+    while sim.time < t_end and sim.step < cfg.max_step:
+        n += 1
         sim.run(max_time=min(t_end, t0 + n * dt_plot))
         io.write_solution_files(job_dir, job, sim, tindx_start + n)
-        if sim.step >= cfg.max_step:
+        if n_solutions and n >= n_solutions:
             break
     os.makedirs(os.path.join(job_dir, "hist"), exist_ok=True)
     for key in keys:

@@ -59,6 +59,7 @@ class Config:
         self.dt_max = 1.0e-3                               # :1282
         self.max_time = 1.0e-3
         self.dt_history = 1.0e-3                           # history cells are sampled at this interval of simulated time
+        self.dt_plot = 1.0e-3                              # flow solutions are written at this interval (simcore.d:1196-1216)
         self.max_step = 100
         self.max_attempts_for_step = 3                     # :947
         self.max_invalid_cells = 0                         # :1014

@@ -68,7 +68,9 @@ enum eb200_flux_calculator {
     EB200_FLUX_ADAPTIVE_HANEL_AUSM_PLUS_UP = 7,
     EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2 = 8,
     EB200_FLUX_EFM = 9,                          /* fluxcalc.d:1131-1312 (equilibrium flux method) */
-    EB200_FLUX_ADAPTIVE_EFM_AUSMDV = 10          /* config.flux_calculator = "adaptive" (globalconfig.d:333) */
+    EB200_FLUX_ADAPTIVE_EFM_AUSMDV = 10,         /* config.flux_calculator = "adaptive" (globalconfig.d:333) */
+    EB200_FLUX_HLLC = 11,                        /* fluxcalc.d:650-816 (single-species gas on this path, like roe) */
+    EB200_FLUX_HLLE2 = 12                        /* fluxcalc.d:1779-1926, with the reference's y/z momentum slip at :1901 */
 };
 
 /* config.thermo_interpolator (globalconfig.d:1073, onedinterp.d:771-978) */
@@ -83,7 +85,9 @@ enum eb200_update_scheme {
     EB200_UPDATE_PC = 1,          /* predictor-corrector, the default */
     EB200_UPDATE_MIDPOINT = 2,
     EB200_UPDATE_CLASSIC_RK3 = 3,
-    EB200_UPDATE_TVD_RK3 = 4
+    EB200_UPDATE_TVD_RK3 = 4,
+    EB200_UPDATE_DENMAN_RK3 = 5,  /* every stage continues from the U of the stage before (:1303, :1352) */
+    EB200_UPDATE_CLASSIC_RK4 = 6  /* four stages */
 };
 
 enum eb200_gas_model {
@@ -132,6 +136,7 @@ enum eb200_bc_kind {
 #define EB200_PRIM_VELY 6
 #define EB200_PRIM_VELZ 7
 #define EB200_NPRIM_BASE 8
+#define EB200_NPRIM_SHORT 5   /* eb200_upload_flow, single-species gas: rho, u, velx, vely, velz only */
 
 /* NASA/CEA thermo curve of one species
  * (src/gas/thermo/cea_thermo_curves.d:24-55, data e.g.
@@ -269,7 +274,12 @@ int eb200_set_exchange(int sim, eb200_exchange_fn fn, void* user);
 /* Upload primitive variables of a local block: prims[v] is a padded array for
  * variable v in the EB200_PRIM_* order (ghost values ignored).  Then, like
  * init_simulation (simcore.d:325-334), encode_conserved (fvcell.d:511-583)
- * and decode_conserved (fvcell.d:586-821) are applied to every cell. */
+ * and decode_conserved (fvcell.d:586-821) are applied to every cell.
+ * For a single-species gas nprims may also be EB200_NPRIM_SHORT: prims = { rho, u, velx, vely, velz }, the
+ * variables decode_conserved starts from; p, T and a are then computed on the device (5/8 of the bytes cross PCIe).
+ * The call only enqueues the copies and the kernel (page-locked host arrays must stay untouched until the next
+ * call that returns results; pageable ones are staged before the call returns); a FlowState that cannot be decoded is reported by the next
+ * eb200_compute_dt, eb200_step or eb200_run_steps (return < 0, eb200_last_error names the upload). */
 int eb200_upload_flow(int sim, int blk_id, const double* const* prims, int nprims);
 
 /* Download primitive variables (interior + current ghost values). */

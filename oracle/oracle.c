@@ -938,6 +938,115 @@ static void roe(const Sim* s, const FS* Lft, const FS* Rght, double* F)
                                     - (fabs(lambda[2]) * ((dp - rhat * ahat * du) / (2.0 * ahat2)) * (Hhat - uhat * ahat)));
 }
 
+/* fluxcalc.d:650-816 hllc: Toro's HLLC solver with Einfeldt's wave speeds (single temperature, no turbulence).
+ * F starts cleared, factor = 1. */
+static void hllc(const Sim* s, const FS* Lft, const FS* Rght, double* F)
+{
+    const double factor = 1.0;
+    double gL = gas_gamma(s, &Lft->gas);
+    double rL = Lft->gas.rho, pL = Lft->gas.p, uL = Lft->vx, vL = Lft->vy, wL = Lft->vz;
+    double eL = Lft->gas.u, aL = Lft->gas.a;
+    double keL = 0.5 * (uL * uL + vL * vL + wL * wL);
+    double EL = rL * eL + rL * keL;
+    double gR = gas_gamma(s, &Rght->gas);
+    double rR = Rght->gas.rho, pR = Rght->gas.p, uR = Rght->vx, vR = Rght->vy, wR = Rght->vz;
+    double eR = Rght->gas.u, aR = Rght->gas.a;
+    double keR = 0.5 * (uR * uR + vR * vR + wR * wR);
+    double ER = rR * eR + rR * keR;
+    double uhat = (sqrt(rL) * uL + sqrt(rR) * uR) / (sqrt(rL) + sqrt(rR));
+    double ghat = (sqrt(rL) * gL + sqrt(rR) * gR) / (sqrt(rL) + sqrt(rR));
+    double ahat2 = ((sqrt(rL) * aL * aL + sqrt(rR) * aR * aR) / (sqrt(rL) + sqrt(rR))) +
+        0.5 * (ghat - 1.0) * ((sqrt(rL) + sqrt(rR)) / sqrt((sqrt(rL) + sqrt(rR)))) * (uR - uL) * (uR - uL);
+    double ahat = sqrt(ahat2);
+    double SL = fmin(uL - aL, uhat - ahat);
+    double SR = fmax(uR + aR, uhat + ahat);
+    double S_star = (pR - pL + rL * uL * (SL - uL) - rR * uR * (SR - uR)) / (rL * (SL - uL) - rR * (SR - uR));
+    int star_region; double coeff, r, p, u, v, w, E, S;
+    if (S_star > 0.0) {
+        r = rL; p = pL; u = uL; v = vL; w = wL; E = EL; S = SL;
+        if (SL > 0.0) { star_region = 0; coeff = 0.0; }
+        else { star_region = 1; coeff = rL * (SL - uL) / (SL - S_star); }
+    } else {
+        r = rR; p = pR; u = uR; v = vR; w = wR; E = ER; S = SR;
+        if (SR < 0.0) { star_region = 0; coeff = 0.0; }
+        else { star_region = 1; coeff = rR * (SR - uR) / (SR - S_star); }
+    }
+    /* hllc_flux_function (:724-794) */
+    double F_mass = r * u, U_mass = r, U_star_mass = coeff, ru_half;
+    if (star_region) ru_half = F_mass + S * (U_star_mass - U_mass); else ru_half = F_mass;
+    F[s->iMass] += factor * ru_half;
+    double F_momx = r * u * u + p, U_momx = r * u, U_star_momx = coeff * S_star;
+    double F_momy = r * u * v, U_momy = r * v, U_star_momy = coeff * v;
+    double F_momz = r * u * w, U_momz = r * w, U_star_momz = coeff * w;
+    if (star_region) {
+        F[s->iXMom] += factor * (F_momx + S * (U_star_momx - U_momx));
+        F[s->iYMom] += factor * (F_momy + S * (U_star_momy - U_momy));
+        if (s->threeD) F[s->iZMom] += factor * (F_momz + S * (U_star_momz - U_momz));
+    } else {
+        F[s->iXMom] += factor * F_momx;
+        F[s->iYMom] += factor * F_momy;
+        if (s->threeD) F[s->iZMom] += factor * F_momz;
+    }
+    double F_totenergy = u * (E + p), U_totenergy = E;
+    double U_star_totenergy = coeff * (E / r + (S_star - u) * (S_star + p / (r * (S - u))));
+    if (star_region) F[s->iEnergy] += factor * (F_totenergy + S * (U_star_totenergy - U_totenergy));
+    else F[s->iEnergy] += factor * (F_totenergy);
+    if (s->nsp > 1) {
+        const FS* up = (ru_half >= 0.0) ? Lft : Rght;
+        for (int i = 0; i < s->nsp; ++i) F[s->iSpecies + i] += factor * (ru_half * up->gas.massf[i]);
+    }
+}
+
+/* fluxcalc.d:1779-1926 hlle2: HLL with Einfeldt's wave speeds.  In the subsonic branch the reference adds the
+ * z-momentum flux to the y-momentum entry (:1901) and leaves the z entry at zero: reproduced. */
+static void hlle2(const Sim* s, const FS* Lft, const FS* Rght, double* F)
+{
+    const double factor = 1.0;
+    double gL = gas_gamma(s, &Lft->gas);
+    double rL = Lft->gas.rho, pL = Lft->gas.p, pLrL = pL / rL, uL = Lft->vx, vL = Lft->vy, wL = Lft->vz;
+    double eL = Lft->gas.u, aL = Lft->gas.a;
+    double keL = 0.5 * (uL * uL + vL * vL + wL * wL);
+    double HL = eL + pLrL + keL;
+    double gR = gas_gamma(s, &Rght->gas);
+    double rR = Rght->gas.rho, pR = Rght->gas.p, pRrR = pR / rR, uR = Rght->vx, vR = Rght->vy, wR = Rght->vz;
+    double eR = Rght->gas.u, aR = Rght->gas.a;
+    double keR = 0.5 * (uR * uR + vR * vR + wR * wR);
+    double HR = eR + pRrR + keR;
+    double uhat = (sqrt(rL) * uL + sqrt(rR) * uR) / (sqrt(rL) + sqrt(rR));
+    double ghat = (sqrt(rL) * gL + sqrt(rR) * gR) / (sqrt(rL) + sqrt(rR));
+    double ahat2 = ((sqrt(rL) * aL * aL + sqrt(rR) * aR * aR) / (sqrt(rL) + sqrt(rR))) +
+        0.5 * (ghat - 1.0) * ((sqrt(rL) + sqrt(rR)) / sqrt((sqrt(rL) + sqrt(rR)))) * (uR - uL) * (uR - uL);
+    double ahat = sqrt(ahat2);
+    double SLm = fmin(uL - aL, uhat - ahat);
+    double SRp = fmax(uR + aR, uhat + ahat);
+    if (SLm >= 0) {
+        F[s->iMass] += factor * (rL * uL);
+        F[s->iXMom] += factor * (rL * uL * uL + pL);
+        F[s->iYMom] += factor * (rL * uL * vL);
+        if (s->threeD) F[s->iZMom] += factor * (rL * uL * wL);
+        F[s->iEnergy] += factor * (rL * uL * HL);
+        if (s->nsp > 1) for (int i = 0; i < s->nsp; ++i) F[s->iSpecies + i] += factor * (rL * uL * Lft->gas.massf[i]);
+    } else if (SRp <= 0) {
+        F[s->iMass] += factor * (rR * uR);
+        F[s->iXMom] += factor * (rR * uR * uR + pR);
+        F[s->iYMom] += factor * (rR * uR * vR);
+        if (s->threeD) F[s->iZMom] += factor * (rR * uR * wR);
+        F[s->iEnergy] += factor * (rR * uR * HR);
+        if (s->nsp > 1) for (int i = 0; i < s->nsp; ++i) F[s->iSpecies + i] += factor * (rR * uR * Rght->gas.massf[i]);
+    } else {
+        double ru_half = (SRp * rL * uL - SLm * rR * uR + SLm * SRp * (rR - rL)) / (SRp - SLm);
+        F[s->iMass] += factor * ru_half;
+        F[s->iXMom] += factor * ((SRp * (rL * uL * uL + pL) - SLm * (rR * uR * uR + pR) + SLm * SRp * (rR * uR - rL * uL)) / (SRp - SLm));
+        F[s->iYMom] += factor * ((SRp * (rL * uL * vL) - SLm * (rR * uR * vR) + SLm * SRp * (rR * vR - rL * vL)) / (SRp - SLm));
+        if (s->threeD) F[s->iYMom] += factor * ((SRp * (rL * uL * wL) - SLm * (rR * uR * wR) + SLm * SRp * (rR * wR - rL * wL)) / (SRp - SLm));
+        F[s->iEnergy] += factor * ((SRp * (rL * uL * HL) - SLm * (rR * uR * HR) + SLm * SRp * (rR * HR - rL * HL)) / (SRp - SLm));
+        if (s->nsp > 1) {
+            const FS* up = (ru_half >= 0.0) ? Lft : Rght;
+            for (int i = 0; i < s->nsp; ++i) F[s->iSpecies + i] += factor * (ru_half * up->gas.massf[i]);
+        }
+    }
+}
+
 /* fluxcalc.d:1280-1312 exxef: exp(-x^2) and erf(x) by a polynomial approximation */
 static void exxef(double sn, double* exx, double* ef)
 {
@@ -1032,6 +1141,8 @@ static void compute_interface_flux_interior(const Sim* s, FS* Lft, FS* Rght, con
     case EB200_FLUX_LDFSS2: ldfss(s, Lft, Rght, F, 2); break;
     case EB200_FLUX_AUSM_PLUS_UP: ausm_plus_up(s, Lft, Rght, F); break;
     case EB200_FLUX_ROE: roe(s, Lft, Rght, F); break;
+    case EB200_FLUX_HLLC: hllc(s, Lft, Rght, F); break;
+    case EB200_FLUX_HLLE2: hlle2(s, Lft, Rght, F); break;
     /* fluxcalc.d:1332-1372.  The detector on this path yields alpha = 0 or 1 (PJ, no smoothing), for which the
      * `factor` argument of the reference's calculators is exactly 1. */
     case EB200_FLUX_ADAPTIVE_HANEL_AUSMDV:
@@ -1578,30 +1689,39 @@ static int n_stages_for(int scheme)
     switch (scheme) {
     case EB200_UPDATE_EULER: return 1;
     case EB200_UPDATE_PC: case EB200_UPDATE_MIDPOINT: return 2;
-    case EB200_UPDATE_CLASSIC_RK3: case EB200_UPDATE_TVD_RK3: return 3;
+    case EB200_UPDATE_CLASSIC_RK3: case EB200_UPDATE_TVD_RK3: case EB200_UPDATE_DENMAN_RK3: return 3;
+    case EB200_UPDATE_CLASSIC_RK4: return 4;               /* globalconfig.d:126-143 */
     }
     return 0;
 }
-static void stage_gammas(int scheme, int stage, double g[3])
+static void stage_gammas(int scheme, int stage, double g[4])
 {
-    g[0] = g[1] = g[2] = 0.0;
-    if (stage == 1) {
+    g[0] = g[1] = g[2] = g[3] = 0.0;
+    if (stage == 1) {                                      /* :1235-1248 */
         switch (scheme) {
         case EB200_UPDATE_EULER: case EB200_UPDATE_PC: case EB200_UPDATE_TVD_RK3: g[0] = 1.0; break;
         case EB200_UPDATE_MIDPOINT: case EB200_UPDATE_CLASSIC_RK3: g[0] = 0.5; break;
+        case EB200_UPDATE_DENMAN_RK3: g[0] = 8.0 / 15.0; break;
+        case EB200_UPDATE_CLASSIC_RK4: g[0] = 1.0 / 2.0; break;
         }
-    } else if (stage == 2) {
+    } else if (stage == 2) {                               /* :1285-1297 */
         switch (scheme) {
         case EB200_UPDATE_PC: g[0] = 0.5; g[1] = 0.5; break;
         case EB200_UPDATE_MIDPOINT: g[0] = 0.0; g[1] = 1.0; break;
         case EB200_UPDATE_CLASSIC_RK3: g[0] = -1.0; g[1] = 2.0; break;
         case EB200_UPDATE_TVD_RK3: g[0] = 0.25; g[1] = 0.25; break;
+        case EB200_UPDATE_DENMAN_RK3: g[0] = -17.0 / 60.0; g[1] = 5.0 / 12.0; break;
+        case EB200_UPDATE_CLASSIC_RK4: g[0] = 0.0; g[1] = 1.0 / 2.0; break;
         }
-    } else {
+    } else if (stage == 3) {                               /* :1323-1347 */
         switch (scheme) {
         case EB200_UPDATE_CLASSIC_RK3: g[0] = 1.0 / 6.0; g[1] = 4.0 / 6.0; g[2] = 1.0 / 6.0; break;
         case EB200_UPDATE_TVD_RK3: g[0] = 1.0 / 6.0; g[1] = 1.0 / 6.0; g[2] = 4.0 / 6.0; break;
+        case EB200_UPDATE_DENMAN_RK3: g[0] = 0.0; g[1] = -5.0 / 12.0; g[2] = 3.0 / 4.0; break;
+        case EB200_UPDATE_CLASSIC_RK4: g[0] = 0.0; g[1] = 0.0; g[2] = 1.0; break;
         }
+    } else {                                               /* :1376-1395, classic_rk4 only */
+        g[0] = 1.0 / 6.0; g[1] = 1.0 / 3.0; g[2] = 1.0 / 3.0; g[3] = 1.0 / 6.0;
     }
 }
 
@@ -1612,7 +1732,7 @@ static int update_block(const Sim* s, Blk* b, int stage, double dt, int* invalid
 {
     int ncq = s->ncq, ftl = stage - 1, failed = 0;
     long n = b->ncp;
-    double g[3]; stage_gammas(s->cfg.update_scheme, stage, g);
+    double g[4]; stage_gammas(s->cfg.update_scheme, stage, g);
     int nf = s->threeD ? 6 : 4;
     FOR_INTERIOR(b) {
         long c = cidx(b, i, j, k);
@@ -1634,10 +1754,12 @@ static int update_block(const Sim* s, Blk* b, int stage, double dt, int* invalid
         long c = cidx(b, i, j, k);
         for (int q = 0; q < ncq; ++q) {
             long o = (long)q * n + c;
-            double U0 = b->U[0][o];
+            /* U_old = cell.U[0], except that Denman's scheme continues from the stage before (:1303, :1352) */
+            double U0 = b->U[(s->cfg.update_scheme == EB200_UPDATE_DENMAN_RK3) ? stage - 1 : 0][o];
             if (stage == 1) b->U[1][o] = U0 + dt * g[0] * b->dUdt[0][o];
             else if (stage == 2) b->U[2][o] = U0 + dt * (g[0] * b->dUdt[0][o] + g[1] * b->dUdt[1][o]);
-            else b->U[3][o] = U0 + dt * (g[0] * b->dUdt[0][o] + g[1] * b->dUdt[1][o] + g[2] * b->dUdt[2][o]);
+            else if (stage == 3) b->U[3][o] = U0 + dt * (g[0] * b->dUdt[0][o] + g[1] * b->dUdt[1][o] + g[2] * b->dUdt[2][o]);
+            else b->U[4][o] = U0 + dt * (g[0] * b->dUdt[0][o] + g[1] * b->dUdt[1][o] + g[2] * b->dUdt[2][o] + g[3] * b->dUdt[3][o]);
         }
         if (decode_conserved(s, b, c, ftl + 1)) { b->bad[c] = 1; failed = 1; }
     }
@@ -1683,7 +1805,7 @@ int orc_init(const eb200_config* cfg)
     s->nprim = EB200_NPRIM_BASE + (s->nsp > 1 ? 2 * s->nsp : 0);
     s->shock_detect = ((cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV && cfg->flux_calculator <= EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) ||
                        cfg->flux_calculator == EB200_FLUX_ADAPTIVE_EFM_AUSMDV);
-    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_ADAPTIVE_EFM_AUSMDV) { set_err("unknown flux calculator"); return -1; }
+    if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_HLLE2) { set_err("unknown flux calculator"); return -1; }
     if (s->shock_detect && cfg->compression_tolerance > 0.0) { set_err("compression_tolerance should be negative!"); return -1; }
     s->n_stages = n_stages_for(cfg->update_scheme);
     if (!s->n_stages) { set_err("unsupported update scheme"); return -1; }
@@ -1877,8 +1999,10 @@ int orc_upload_flow(int sim, int blk_id, const double* const* prims, int nprims)
 {
     Sim* s = get_sim(sim); if (!s) return -1;
     Blk* b = get_blk(s, blk_id); if (!b) return -1;
-    if (nprims != s->nprim) { set_err("expected %d primitive arrays", s->nprim); return -1; }
-    for (int v = 0; v < nprims; ++v) memcpy(PR(s, b, v), prims[v], b->ncp * sizeof(double));
+    const int short_form = (nprims == EB200_NPRIM_SHORT && s->nprim == EB200_NPRIM_BASE);     /* rho, u, velx, vely, velz */
+    static const int short_field[EB200_NPRIM_SHORT] = { 0, 1, 5, 6, 7 };
+    if (nprims != s->nprim && !short_form) { set_err("expected %d primitive arrays", s->nprim); return -1; }
+    for (int v = 0; v < nprims; ++v) memcpy(PR(s, b, short_form ? short_field[v] : v), prims[v], b->ncp * sizeof(double));
     /* simcore.d:325-334 */
     FOR_INTERIOR(b) {
         long c = cidx(b, i, j, k);

@@ -16,7 +16,7 @@ from gdtk_b200 import Config, cases
 
 pytestmark = pytest.mark.gpu
 
-FLUXES = ["ausmdv", "hanel", "ldfss0", "ldfss2", "ausm_plus_up", "roe", "efm"]
+FLUXES = ["ausmdv", "hanel", "ldfss0", "ldfss2", "ausm_plus_up", "roe", "efm", "hllc", "hlle2"]
 
 
 def random_faces(gm, dims, n, seed):

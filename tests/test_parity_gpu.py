@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from gdtk_b200 import Simulation, cases
-from util import run_case, max_rel_diff, identical
+from util import run_case, max_rel_diff, identical, cellwise_rel_diff
 
 pytestmark = pytest.mark.gpu
 
@@ -20,7 +20,7 @@ REL_TOL_DT = 1.0e-9      # north_star: dt history
 # exp() in efm's error-function approximation differs in the last place between CUDA and glibc, so the FMA-free
 # build cannot be bit-identical for the calculators that use it; they are held to the tolerance in both builds
 NOT_BITWISE = ("efm", "adaptive", "adaptive_efm_ausmdv")
-FLUXES = ["ausmdv", "hanel", "ldfss0", "ldfss2", "ausm_plus_up", "roe", "efm"]
+FLUXES = ["ausmdv", "hanel", "ldfss0", "ldfss2", "ausm_plus_up", "roe", "efm", "hllc", "hlle2"]
 
 
 def _compare(factory, oracle, product, nsteps, expect_bitwise=True, **kw):
@@ -107,6 +107,47 @@ def test_probe_histories(oracle, product):
     assert np.max(np.abs(runs["fast"] - runs["oracle"]) / scale) < 1.0e-9
 
 
+def _full_length(factory, oracle, product, expect_steps, **kw):
+    """A whole job in the oracle and in the throughput build: step count, dt history and the conserved quantities at
+    the end, by both measures (scale of the variable over the whole field / cell by cell)."""
+    cfg, gm, blocks = factory(**kw)
+    runs = {}
+    for name, lib, strict in (("oracle", oracle, True), ("fast", product, False)):
+        cfg, gm, blocks = factory(**kw)
+        cfg.strict_fp = strict
+        sim = Simulation(cfg, gm, blocks, lib=lib)
+        steps = sim.run()
+        runs[name] = (steps, np.array(sim.dt_history),
+                      {b.id: [sim.interior(b.id, a).copy() for a in sim.download_conserved(b.id)] for b in sim.local_blocks})
+        sim.close()
+    so, dto, Uo = runs["oracle"]
+    sf, dtf, Uf = runs["fast"]
+    g, c = max_rel_diff(Uf, Uo), cellwise_rel_diff(Uf, Uo)
+    print(f"{factory.__name__}: {so} steps; throughput build vs oracle: {g:.3e} (field scale), {c:.3e} (cell by cell, mass and energy)")
+    assert so == sf and abs(so - expect_steps) < 3
+    assert np.max(np.abs(dtf - dto) / dto) < REL_TOL_DT
+    assert g < REL_TOL_U
+    assert c < 10.0 * REL_TOL_U
+    return g, c
+
+
+def test_cone20_to_the_end_against_the_oracle(oracle, product):
+    """cone20 for its whole 5 ms (833 steps, cone20-test.rb): the throughput build stays within 1e-10 of the oracle."""
+    _full_length(cases.cone20, oracle, product, 833, flux_calculator="ausmdv")
+    _full_length(cases.cone20, oracle, product, 833, flux_calculator="adaptive_hanel_ausmdv")
+
+
+def test_simple_ramp_3d_to_the_end_against_the_oracle(oracle, product):
+    """The 3D simple-ramp job for all its 862 steps (ramp-test.rb), default adaptive flux calculator."""
+    _full_length(cases.ramp3d, oracle, product, 862)
+
+
+def test_block_of_the_benchmark_shape(oracle, product):
+    """One 128^3 block -- the benchmark's block size: whole 32 x 16 tiles, the k-chunking of a full-size block, TMA
+    staging -- three predictor-corrector steps against the oracle."""
+    _compare(cases.box3d, oracle, product, 3, n=128, nb=1)
+
+
 def test_simple_ramp_3d_first_steps(oracle, product):
     """examples/eilmer/3D/simple-ramp/sg: clustered general-metric 3D blocks, Euler update, default adaptive flux."""
     _compare(cases.ramp3d, oracle, product, 150)
@@ -149,9 +190,16 @@ def test_ffs_2d_three_blocks(oracle, product):
     _compare(cases.ffs, oracle, product, 40, nx=120, ny=40)
 
 
-@pytest.mark.parametrize("scheme", ["euler", "midpoint", "classic-rk3", "tvd-rk3"])
+@pytest.mark.parametrize("scheme", ["euler", "midpoint", "classic-rk3", "tvd-rk3", "denman-rk3", "classic-rk4"])
 def test_update_schemes(oracle, product, scheme):
+    """Gamma tables of simcore_gasdynamic_step.d:1235-1395; Denman's scheme continues from the U of the stage before,
+    classic_rk4 has four stages.  Both fused kernels for uniform blocks (32^3: whole tiles of the cell-centred one) and
+    the general-metric path."""
     _compare(cases.box3d, oracle, product, 5, n=12, nb=1, gasdynamic_update_scheme=scheme)
+    if scheme in ("denman-rk3", "classic-rk4"):
+        _compare(cases.box3d, oracle, product, 4, n=32, nb=1, gasdynamic_update_scheme=scheme)
+        _compare(cases.box3d, oracle, product, 4, n=12, nb=2, sheared=True, gasdynamic_update_scheme=scheme)
+        _compare(cases.ffs, oracle, product, 12, nx=60, ny=20, gasdynamic_update_scheme=scheme)
 
 
 def test_first_order_and_no_limiter(oracle, product):
@@ -235,7 +283,7 @@ def test_tma_and_cp_async_staging_agree(product, case, strict):
         assert max_rel_diff(U3, U2) < 1.0e-10
 
 
-@pytest.mark.parametrize("case", ["box3d", "box3d_sheared", "ffs", "sod3d", "tpg"])
+@pytest.mark.parametrize("case", ["box3d", "box3d_sheared", "ffs", "sod3d", "tpg", "sod3d_adaptive", "box3d_adaptive", "ffs_adaptive"])
 def test_pushed_and_copied_ghost_cells_agree(product, case):
     """Ghost cells behind same-GPU block connections are written by the flux kernel itself (push) or by the
     ghost-cell kernel (no_push): the same values either way, also across a failed step and a fresh upload."""
@@ -243,7 +291,11 @@ def test_pushed_and_copied_ghost_cells_agree(product, case):
                       "box3d_sheared": (cases.box3d, dict(n=16, nb=2, sheared=True), 6),
                       "ffs": (cases.ffs, dict(nx=120, ny=40), 30),
                       "sod3d": (cases.sod, dict(dims=3, ncells=48, nj=4, nk=4, nblocks=3), 20),
-                      "tpg": (cases.tpg_box3d, dict(n=12, nb=2), 4)}[case]
+                      "tpg": (cases.tpg_box3d, dict(n=12, nb=2), 4),
+                      # the shock detector's FlowState.S travels with the pushed FlowStates
+                      "sod3d_adaptive": (cases.sod, dict(dims=3, ncells=48, nj=4, nk=4, nblocks=3, flux_calculator="adaptive_hanel_ausmdv"), 30),
+                      "box3d_adaptive": (cases.box3d, dict(n=32, nb=2, flux_calculator="adaptive_hanel_ausmdv"), 8),
+                      "ffs_adaptive": (cases.ffs, dict(nx=120, ny=40, flux_calculator="adaptive_hanel_ausmdv"), 40)}[case]
     s1, U1, P1 = run_case(factory, product, n, strict=True, **kw)
     s2, U2, P2 = run_case(factory, product, n, strict=True, no_push=True, **kw)
     assert identical(U1, U2) and identical(P1, P2)
@@ -263,6 +315,36 @@ def test_thermally_perfect_five_species(oracle, product, flux, sheared):
     solves at both sides of every face and in every decode.  Not bit-comparable (CUDA's log() and
     glibc's differ in the last place), so both builds are held to the 1e-10 tolerance."""
     _compare(cases.tpg_box3d, oracle, product, 5, expect_bitwise=False, n=12, nb=2, flux_calculator=flux, sheared=sheared)
+
+
+@pytest.mark.parametrize("case", ["box24", "box40", "ffs", "rk3"])
+def test_thermally_perfect_tuned_and_generic_kernels_agree(product, case):
+    """The cell-centred kernel for thermally perfect mixtures (flux_kernel_tp.cuh) against the generic kernel:
+    the same operations in the FMA-free build (identical bits, ragged tiles and several k-chunks included),
+    within the tolerance in the throughput build (Newton from per-cell species tables, early exit)."""
+    factory, kw, n = {"box24": (cases.tpg_box3d, dict(n=24, nb=2), 4),
+                      "box40": (cases.tpg_box3d, dict(n=40, nb=1), 3),
+                      "ffs": (cases.tpg_ffs, dict(nx=120, ny=40), 20),
+                      "rk3": (cases.tpg_box3d, dict(n=16, nb=1, gasdynamic_update_scheme="tvd-rk3"), 3)}[case]
+    s1, U1, _ = run_case(factory, product, n, strict=True, **kw)
+    s2, U2, _ = run_case(factory, product, n, strict=True, force_generic_kernel=True, **kw)
+    assert identical(U1, U2)
+    assert s1.dt_history == s2.dt_history
+    s3, U3, _ = run_case(factory, product, n, strict=False, **kw)
+    assert max_rel_diff(U3, U2) < REL_TOL_U
+
+
+def test_thermally_perfect_2d(oracle, product):
+    """Thermally perfect air in two dimensions: the forward-facing step on uniform blocks (cell-centred kernel) and
+    cone20's axisymmetric general-metric blocks (generic kernel)."""
+    _compare(cases.tpg_ffs, oracle, product, 25, expect_bitwise=False, nx=90, ny=30)
+    _compare(cases.tpg_cone20, oracle, product, 40, expect_bitwise=False)
+
+
+def test_thermally_perfect_whole_tiles(oracle, product):
+    """A block of 64^3 (whole 32 x 8 tiles, several k-chunks) against the oracle, adaptive flux calculator included."""
+    _compare(cases.tpg_box3d, oracle, product, 3, expect_bitwise=False, n=64, nb=1)
+    _compare(cases.tpg_box3d, oracle, product, 3, expect_bitwise=False, n=32, nb=1, flux_calculator="adaptive_hanel_ausmdv")
 
 
 ADAPTIVE = ["adaptive_hanel_ausmdv", "adaptive_hanel_ausm_plus_up", "adaptive_ldfss0_ldfss2", "adaptive"]   # "adaptive" = adaptive_efm_ausmdv

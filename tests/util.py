@@ -47,3 +47,20 @@ def max_rel_diff(A, B):
 
 def identical(A, B):
     return all(np.array_equal(a, b) for bid in B for a, b in zip(A[bid], B[bid]))
+
+
+def cellwise_rel_diff(A, B):
+    """Largest |a-b| / |b| cell by cell over the positive-definite conserved quantities (mass, total energy and
+    species densities above 1e-12 of the mixture); the momentum components have no cell-wise scale of their own
+    (they pass through zero) and are measured by max_rel_diff."""
+    worst = 0.0
+    for bid in B:
+        n = len(B[bid])
+        dims = 3 if n in (5, 10) else 2
+        rho = np.abs(B[bid][0])
+        for q in [0, 1 + dims] + list(range(2 + dims, n)):
+            a, b = A[bid][q], B[bid][q]
+            keep = np.abs(b) > 1.0e-12 * rho if q > 1 + dims else np.ones_like(b, dtype=bool)
+            if keep.any():
+                worst = max(worst, float(np.max(np.abs(a - b)[keep] / np.abs(b)[keep])))
+    return worst
