@@ -138,8 +138,10 @@ def build_case(spec):
 
 def kernel_name(spec):
     """Which fused flux+update kernel the library picks for this workload (same rule as gdtk_b200/csrc/flux_inst.cu)."""
-    if spec["kernel"] == "generic" or spec["workload"] == "tpg":
+    if spec["kernel"] == "generic":
         return "flux_update_kernel (generic)"
+    if spec["workload"] == "tpg":
+        return "flux_update_kernel_tp (cell-centred, thermally perfect mixture, uniform Cartesian)"
     if spec["workload"] == "box3d" and spec["sheared"]:
         return "flux_update_kernel_v2 (face-centred, general metric)"
     return "flux_update_kernel_v2 (face-centred)" if spec["kernel"] == "v2" else "flux_update_kernel_v3 (cell-centred, uniform Cartesian)"

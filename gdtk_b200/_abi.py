@@ -43,6 +43,8 @@ BC_OUTFLOW_SIMPLE_FLUX = 3
 BC_EXCHANGE_FULL_FACE = 4
 BC_OUTFLOW_FIXED_P = 5
 BC_OUTFLOW_FIXED_PT = 6
+BC_WALL_WITH_SLIP1 = 7
+BC_GHOST_PROFILE = 8
 
 
 class Species(C.Structure):

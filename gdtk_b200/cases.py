@@ -67,6 +67,64 @@ def cone20(flux_calculator="ausmdv", nx0=10, nx1=30, ny=40, fbarray=False, gmode
     return cfg, gm, [blk0, blk1]
 
 
+def vortex_flow(gm):
+    """The inviscid compressible vortex of udf-vortex-flow.lua:7-46 as a function of position -> FlowState
+    (the file's own constants: R = 287 J/kg/K and gamma = 1.4 define p and T, the gas model turns them into a state)."""
+    Rgas, g = 287.0, 1.4
+    r_i, p_i, M_i, rho_i = 1.0, 100.0e3, 2.25, 1.0
+    T_i = p_i / (Rgas * rho_i)
+    a_i = np.sqrt(g * Rgas * T_i)
+    u_i = M_i * a_i
+
+    def state(x, y, z=0.0):
+        r = np.sqrt(x * x + y * y)
+        theta = np.arctan2(y, x)
+        u = u_i * r_i / r
+        t1 = r_i / r
+        t2 = 1.0 + 0.5 * (g - 1.0) * M_i * M_i * (1.0 - t1 * t1)
+        rho = rho_i * t2 ** (1.0 / (g - 1.0))
+        p = p_i * (rho / rho_i) ** g
+        T = p / (rho * Rgas)
+        return FlowState(gm, p=float(p), T=float(T), velx=float(np.sin(theta) * u), vely=float(-np.cos(theta) * u))
+    return state
+
+
+def vortex(gfactor=4, nib=4, flux_calculator="adaptive_hanel_ausmdv", **cfg_kw):
+    """examples/eilmer/2D/vortex-supersonic/vtx.lua: supersonic vortex in a 90-degree bend, inner and outer walls
+    WallBC_WithSlip1 (no ghost cells: one-sided reconstruction and the wall flux), the exact vortex in the ghost
+    cells of the inflow plane (UserDefinedBC), OutFlowBC_Simple at the exit; 4 blocks (FBArray nib = 4), the default
+    flux calculator, 20 ms.  vtx-test.rb expects 2761 +- 3 steps and, against the exact solution, L2(p) = 800 +- 100 Pa
+    and L2(T) = 0.405 +- 0.10 K (volume-weighted, flowsolution.d:306-346)."""
+    from .sim import UserDefinedBC, WallBC_WithSlip1
+    gm = ideal_air()
+    cfg = Config(dimensions=2, flux_calculator=flux_calculator, max_time=20.0e-3, max_step=6000, dt_init=1.0e-6, cfl_value=0.5)
+    for k, v in cfg_kw.items():
+        setattr(cfg, k, v)
+    initial = FlowState(gm, p=1000.0, T=348.43, velx=0.0, vely=0.0)
+    R_inner, R_outer = 1.0, 1.384
+    nx, ny = int(20 * gfactor), int(10 * gfactor)
+    # makePatch{north=Arc c->e, east=Line d->e, south=Arc b->d, west=Line b->c}: with arcs about the origin and
+    # radial lines the Coons patch is the polar map (r along i: angle from 90 degrees down to 0, s along j: radius)
+    r = (np.arange(nx + 1) / nx)[None, :]
+    sv = (np.arange(ny + 1) / ny)[:, None]
+    theta = 0.5 * np.pi * (1.0 - r)
+    rad = R_inner + (R_outer - R_inner) * sv
+    grid = (rad * np.cos(theta), rad * np.sin(theta))
+    exact = vortex_flow(gm)
+    blocks = []
+    for ib, jb, kb, sub in split_grid(grid, nib, 1):
+        blk = FluidBlock(sub, initial, id=len(blocks))
+        blk.bcList["north"] = WallBC_WithSlip1()
+        blk.bcList["south"] = WallBC_WithSlip1()
+        if ib == 0:
+            blk.bcList["west"] = UserDefinedBC(exact)
+        if ib == nib - 1:
+            blk.bcList["east"] = OutFlowBC_Simple()
+        blocks.append(blk)
+    identify_block_connections(blocks, 2)
+    return cfg, gm, blocks
+
+
 def ramp3d(flux_calculator="adaptive_hanel_ausmdv", **cfg_kw):
     """Mach 1.5 flow over a 10-degree ramp, 3D, two blocks (examples/eilmer/3D/simple-ramp/sg/ramp.lua):
     10x4x40 cells ahead of the ramp, 30x4x40 over it, k-lines clustered towards the wedge surface with
@@ -160,7 +218,7 @@ class PerturbedState:
 
 
 def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True, seed=1234,
-          gmodel=None, inflow=None, **cfg_kw):
+          gmodel=None, inflow=None, wall_bc=None, perturb=True, **cfg_kw):
     """3D ideal-air box (C3/C4): unit cube, n^3 cells in nb^3 blocks; inflow west, simple
     outflow east, slip walls elsewhere; initial state = inflow + smooth perturbation.
     sheared=True tilts the k-lines by 10 degrees (general-metric path, cf.
@@ -178,6 +236,7 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
     blocks = {}
     bid = 0
     shared = None
+    amp = {} if perturb else {"amplitude": 0.0, "noise": 0.0}      # perturb=False: the uniform stream
     for ib in range(nb):
         for jb in range(nb):
             for kb in range(nb):
@@ -187,12 +246,12 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
                     if sheared:
                         X = X + math.tan(math.radians(10.0)) * Z
                     geom = geometry_3d(X, Y, Z)
-                    init = PerturbedState(inflow, seed + bid)
+                    init = PerturbedState(inflow, seed + bid, **amp)
                 else:
                     if shared is None:
                         shared = uniform_box_geometry(3, m, m, m, h, h, h)
                     geom = shared
-                    init = PerturbedState(inflow, seed + bid, origin=(x0, y0, z0), spacing=(h, h, h))
+                    init = PerturbedState(inflow, seed + bid, origin=(x0, y0, z0), spacing=(h, h, h), **amp)
                 blk = FluidBlock(geom, init, id=bid)
                 blocks[(ib, jb, kb)] = blk
                 bid += 1
@@ -202,16 +261,46 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
             blk.bcList["west"] = InFlowBC_Supersonic(inflow)
         if ib == nb - 1:
             blk.bcList["east"] = OutFlowBC_Simple()
+        if wall_bc is not None:          # the four side walls with another wall class (WallBC_WithSlip1: no ghost cells)
+            for name, at_wall in (("south", jb == 0), ("north", jb == nb - 1), ("bottom", kb == 0), ("top", kb == nb - 1)):
+                if at_wall:
+                    blk.bcList[name] = wall_bc()
     cfg.block_index = {blk.id: key for key, blk in blocks.items()}
     return cfg, gm, list(blocks.values())
 
 
-def tpg_box3d(n=32, nb=2, gas_file=None, **kw):
-    """C5: thermally-perfect 5-species air (N2, O2, NO, N, O), frozen chemistry, T = 3000 K."""
-    gas_file = gas_file or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                                        "tests", "golden", "gas", "therm-perf-5-species-air.json")
-    gm = set_gas_model(gas_file)
-    massf = {"N2": 0.767 * 0.99, "O2": 0.233 * 0.99, "NO": 0.004, "N": 0.003, "O": 0.003}
+def tpg_subset_model(species):
+    """A thermally perfect mixture of some of the species of the 5-species air file (the same CEA curves), as a
+    gas model plus free-stream mass fractions: lets the tests run other species counts than five."""
+    import json
+    import tempfile
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "gas")
+    with open(os.path.join(root, "therm-perf-5-species-air.json")) as f:
+        d = json.load(f)
+    d["species"] = list(species)
+    d["db"] = {k: d["db"][k] for k in species}
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(d, f)
+        path = f.name
+    try:
+        gm = set_gas_model(path)
+    finally:
+        os.unlink(path)
+    air = {"N2": 0.767 * 0.99, "O2": 0.233 * 0.99, "NO": 0.004, "N": 0.003, "O": 0.003}
+    tot = sum(air[k] for k in species)
+    return gm, {k: air[k] / tot for k in species}
+
+
+def tpg_box3d(n=32, nb=2, gas_file=None, species=None, **kw):
+    """C5: thermally-perfect 5-species air (N2, O2, NO, N, O), frozen chemistry, T = 3000 K.
+    species: a subset of those five (other species counts)."""
+    if species is not None:
+        gm, massf = tpg_subset_model(species)
+    else:
+        gas_file = gas_file or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                            "tests", "golden", "gas", "therm-perf-5-species-air.json")
+        gm = set_gas_model(gas_file)
+        massf = {"N2": 0.767 * 0.99, "O2": 0.233 * 0.99, "NO": 0.004, "N": 0.003, "O": 0.003}
     inflow = FlowState(gm, p=95.84e3, T=3000.0, velx=3000.0, massf=massf)
     return box3d(n=n, nb=nb, gmodel=gm, inflow=inflow, **kw)
 

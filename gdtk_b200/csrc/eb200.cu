@@ -558,7 +558,7 @@ int enqueue_step(Sim* s, double dt)
             if (!s->peers.empty()) CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
             for (Block* b : s->local) {
                 MODE_CALL(s, launch_detect_shocks, s->P, s->hdesc[b->local_index], s->A, prim_in, s->stream);
-                s->launches += s->P.strict_shock ? 2 : 1;
+                s->launches += s->P.strict_shock ? 1 : 0;
             }
         }
         EbStageArgs S;
@@ -633,8 +633,17 @@ int eb200_init(const eb200_config* cfg)
     if (cfg->dimensions != 2 && cfg->dimensions != 3) { set_err("dimensions must be 2 or 3"); return -1; }
     if (cfg->n_species < 1 || cfg->n_species > EB_MAXSP) { set_err("bad n_species"); return -1; }
     if (cfg->gas_model == EB200_GAS_IDEAL && cfg->n_species != 1) { set_err("ideal gas has one species"); return -1; }
-    if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT && cfg->n_species != 5) {
-        set_err("thermally perfect gas: kernels are built for 5 species (got %d)", cfg->n_species); return -1;
+    if (cfg->gas_model == EB200_GAS_THERMALLY_PERFECT) {
+        bool built = false;
+        std::string list;
+#define EB_CHK_NSP(N) { if (cfg->n_species == N) built = true; list += (list.empty() ? "" : ", "); list += #N; }
+        EB_TPG_NSP_LIST(EB_CHK_NSP)
+#undef EB_CHK_NSP
+        if (!built) {
+            set_err("thermally perfect gas: this library is built for %s species (got %d); rebuild with make TPG_NSP=\"... %d\"",
+                    list.c_str(), cfg->n_species, cfg->n_species);
+            return -1;
+        }
     }
     if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_HLLE2) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
     if ((cfg->flux_calculator == EB200_FLUX_ROE || cfg->flux_calculator == EB200_FLUX_HLLC || cfg->flux_calculator == EB200_FLUX_HLLE2) && cfg->n_species > 1) {
@@ -801,11 +810,22 @@ int eb200_block_set_bc(int sim, int blk_id, int face, int kind, const double* pa
     Block* b = get_blk(s, blk_id); if (!b) return -1;
     if (s->committed) { set_err("set_bc after commit"); return -1; }
     if (face < 0 || face >= s->nfaces) { set_err("bad face %d", face); return -1; }
-    if (kind < 0 || kind > EB200_BC_OUTFLOW_FIXED_PT) { set_err("unknown bc kind %d", kind); return -1; }
+    if (kind < 0 || kind > EB200_BC_GHOST_PROFILE) { set_err("unknown bc kind %d", kind); return -1; }
+    if (kind == EB200_BC_WALL_WITH_SLIP1) {
+        const int nd = (face / 2 == 0) ? b->nic : ((face / 2 == 1) ? b->njc : b->nkc);
+        if (nd < 4) { set_err("block %d: a boundary without ghost-cell data needs at least 4 cells along its normal (got %d)", blk_id, nd); return -1; }
+    }
     BC& bc = b->bc[face];
     bc.kind = kind; bc.other_blk = other_blk; bc.other_face = other_face; bc.orientation = orientation;
     if (kind == EB200_BC_INFLOW_SUPERSONIC) {
         if (nparams != s->P.nprim || !params) { set_err("inflow FlowState needs %d values", s->P.nprim); return -1; }
+        bc.params.assign(params, params + nparams);
+    }
+    if (kind == EB200_BC_GHOST_PROFILE) {
+        const int d = face / 2;
+        const int nn[3] = { b->nic, b->njc, b->nkc };
+        const long long need = (long long)EB_NG * nn[(d + 1) % 3] * nn[(d + 2) % 3] * s->P.nprim;
+        if (nparams != need || !params) { set_err("ghost profile of block %d face %d needs %lld values (got %d)", blk_id, face, need, nparams); return -1; }
         bc.params.assign(params, params + nparams);
     }
     if (kind == EB200_BC_OUTFLOW_FIXED_P || kind == EB200_BC_OUTFLOW_FIXED_PT) {
@@ -880,9 +900,11 @@ int eb200_commit(int sim)
         D.nic = b->nic; D.njc = b->njc; D.nkc = b->nkc; D.NI = b->NI; D.NJ = b->NJ; D.NK = b->NK; D.kg = b->kg;
         D.cell0 = b->cell0; for (int d = 0; d < 3; ++d) D.stride[d] = b->stride[d];
         D.outflow_flux_faces = 0;
+        D.noghost_faces = 0;
         for (int f = 0; f < 6; ++f) {
             D.bc_kind[f] = b->bc[f].kind;
             if (b->bc[f].kind == EB200_BC_OUTFLOW_SIMPLE_FLUX) D.outflow_flux_faces |= (1 << f);
+            if (f < s->nfaces && b->bc[f].kind == EB200_BC_WALL_WITH_SLIP1) D.noghost_faces |= (1 << f);
         }
         D.push_mask = 0;
         for (int f = 0; f < 6; ++f) D.push_off[f] = 0;
@@ -898,12 +920,17 @@ int eb200_commit(int sim)
         (b->cartesian ? any_cart : any_general) = true;
         cells_total += (long long)b->nic * b->njc * b->nkc;
     }
-    s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (s->cfg.reserved_i[1] == 1 ? 4 : 0) | (s->cfg.reserved_i[1] == 2 ? 8 : 0);
+    // a boundary without ghost-cell data anywhere in the job (any rank: every rank must pick the same kernels for the
+    // multi-GPU result to equal the single-GPU one): the generic kernel, which knows the one-sided stencils
+    bool one_sided = false;
+    for (auto& b : s->blocks) for (int f = 0; f < s->nfaces; ++f) if (b->bc[f].kind == EB200_BC_WALL_WITH_SLIP1) one_sided = true;
+    const bool force_generic = s->cfg.reserved_i[1] == 1 || one_sided;
+    s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (force_generic ? 4 : 0) | (s->cfg.reserved_i[1] == 2 ? 8 : 0);
     // Which fused kernel runs a block decides its tiling.  The cell-centred kernel (flux_kernel_v3.cuh) takes the
     // uniform-Cartesian blocks of the reference's default configuration (same conditions as in flux_inst.cu) when
     // their tiles can be staged by TMA.
     const bool tma_ok = tma_available(s);
-    const bool v3_config = tma_ok && s->cfg.reserved_i[1] == 0 && s->cfg.gas_model == EB200_GAS_IDEAL &&
+    const bool v3_config = tma_ok && s->cfg.reserved_i[1] == 0 && !one_sided && s->cfg.gas_model == EB200_GAS_IDEAL &&
                            s->P.interpolation_order == 2 && s->P.apply_limiter != 0 && s->P.thermo_interp == EB200_INTERP_RHOU;
     for (size_t n = 0; n < s->local.size(); ++n) s->hdesc[n].v3 = (v3_config && s->hdesc[n].cartesian) ? 1 : 0;
     {
@@ -1032,6 +1059,8 @@ int eb200_commit(int sim)
                     recv_sets[ot->owner].push_back({ { b->id, f }, recv_list });
                     send_sets[ot->owner].push_back({ { ot->id, bc.other_face }, send_list });
                 }
+            } else if (bc.kind == EB200_BC_WALL_WITH_SLIP1) {
+                // no ghost-cell data: nothing fills these cells and nothing reads them
             } else if (bc.kind == EB200_BC_WALL_WITH_SLIP) {
                 for_face_ghosts(s, b, f, [&](int, int, int, long long cf, long long ghost, long long mirror, long long) {
                     refl.push_back({ (int)(b->cell0 + ghost), (int)(b->cell0 + mirror), (int)(b->cell0 + cf), b->local_index * 4 + d });
@@ -1041,6 +1070,14 @@ int eb200_commit(int sim)
                 params.insert(params.end(), bc.params.begin(), bc.params.end());
                 for_face_ghosts(s, b, f, [&](int, int, int, long long, long long ghost, long long, long long) {
                     fill.push_back({ (int)(b->cell0 + ghost), bc.param_index });
+                });
+            } else if (bc.kind == EB200_BC_GHOST_PROFILE) {
+                // one row of the parameter table per ghost cell, in the enumeration order of for_face_ghosts
+                bc.param_index = (int)(params.size() / nprim);
+                params.insert(params.end(), bc.params.begin(), bc.params.end());
+                int row = bc.param_index;
+                for_face_ghosts(s, b, f, [&](int, int, int, long long, long long ghost, long long, long long) {
+                    fill.push_back({ (int)(b->cell0 + ghost), row++ });
                 });
             } else if (bc.kind == EB200_BC_OUTFLOW_FIXED_P || bc.kind == EB200_BC_OUTFLOW_FIXED_PT) {
                 bc.param_index = (int)(params.size() / nprim);

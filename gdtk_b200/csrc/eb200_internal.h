@@ -63,6 +63,7 @@ struct EbBlockDesc {
     // (van Albada's epsilon is rescaled by 1/c^2 so that the limiter value is the same number)
     double uq[3][5];
     int outflow_flux_faces;   // bit f set: face f has EB200_BC_OUTFLOW_SIMPLE_FLUX
+    int noghost_faces;        // bit f set: face f has no ghost-cell data (EB200_BC_WALL_WITH_SLIP1): one-sided stencils, wall flux
     // Same-GPU full-face neighbours behind opposite, equally sized faces get their ghost cells written by
     // the kernel that produces the FlowStates ("push"): a cell within two layers of face f is also stored
     // at arena index c + push_off[f], the ghost cell of the neighbour that mirrors it (full_face_copy.d
@@ -128,6 +129,11 @@ struct EbStageArgs {
 // ghost-cell work lists (indices into the arena)
 struct EbCopyItem { int dst, src; };
 struct EbReflectItem { int dst, src, fidx, meta; };   // meta = blk*4 + dir
+// Species counts for which the thermally-perfect-gas kernels are instantiated: a build-time list
+// (make TPG_NSP="2 3 5 7"); eb200_init refuses other counts with a message that says so.
+#ifndef EB_TPG_NSP_LIST
+#define EB_TPG_NSP_LIST(X) X(3) X(5)
+#endif
 #define EB_P2P_MAXPEERS 64                    /* flags per slot in the region the halo peers of one rank share */
 struct EbFillItem { int dst, param; };
 

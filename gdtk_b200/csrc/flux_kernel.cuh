@@ -61,6 +61,235 @@ __device__ __forceinline__ void outflow_flux(const Prim<NSP>& fs, int outsign, d
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Faces next to a boundary WITHOUT ghost-cell data (EB200_BC_WALL_WITH_SLIP1, bc.lua:783-806): the wall face has no
+// cells on one side, the next face in has one (sfluidblock.d:455-530, 548-611).  onedinterp.d:117-273 picks the
+// stencil from those counts: l0r2 / l2r0 (linear extrapolation, or the cell copy when extrema_clipping is on,
+// :1451-1456), l1r2 / l2r1 (:386-454); the wall face takes compute_flux_at_left_wall / _right_wall
+// (fluxcalc.d:41-51, 187-385).  Few faces: out of line, written for clarity, the reference's order of operations.
+enum { EB_ST_L2R2 = 0, EB_ST_L2R1 = 1, EB_ST_L1R2 = 2, EB_ST_L2R0 = 3, EB_ST_L0R2 = 4 };
+
+struct EbOneSided {
+    int mode;
+    bool limiter, clip;
+    double eps;
+    EbWeights w;
+    double w0, w1;
+    __device__ double weight(double q0, double q1) const      // onedinterp.d:477-485 weight_scalar
+    {
+        double q = q0 * w0 + q1 * w1;
+        if (clip) q = clip_to_limits(q, q0, q1);
+        return q;
+    }
+    // one variable; a side the stencil does not produce keeps its value
+    __device__ void scalar(double qL1, double qL0, double qR0, double qR1, double& qL, double& qR) const
+    {
+        if (mode == EB_ST_L2R2) { interp_scalar(w, limiter, clip, eps, qL1, qL0, qR0, qR1, qL, qR); return; }
+        if (mode == EB_ST_L2R1) {           // :398-419
+            const double delLminus = (qL0 - qL1) * w.two_over_L0L1;
+            const double del = (qR0 - qL0) * w.two_over_R0L0;
+            double sL = 1.0;
+            if (limiter) sL = eb_div(delLminus * del + fabs(delLminus * del) + eps, delLminus * delLminus + del * del + eps);
+            qL = qL0 + sL * w.aL0 * (del * w.two_L0_plus_L1 + delLminus * w.lenR0);
+            if (limiter && (delLminus * del < 0.0)) qR = qR0; else qR = weight(qL0, qR0);
+            if (clip) qL = clip_to_limits(qL, qL0, qR0);
+        } else if (mode == EB_ST_L1R2) {    // :434-454
+            const double del = (qR0 - qL0) * w.two_over_R0L0;
+            const double delRplus = (qR1 - qR0) * w.two_over_R1R0;
+            double sR = 1.0;
+            if (limiter) sR = eb_div(del * delRplus + fabs(del * delRplus) + eps, del * del + delRplus * delRplus + eps);
+            qR = qR0 - sR * w.aR0 * (delRplus * w.lenL0 + del * w.two_R0_plus_R1);
+            if (limiter && (delRplus * del < 0.0)) qL = qL0; else qL = weight(qL0, qR0);
+            if (clip) qR = clip_to_limits(qR, qL0, qR0);
+        } else if (mode == EB_ST_L2R0) qL = weight(qL0, qL1);
+        else qR = weight(qR0, qR1);
+    }
+};
+
+// gamma = Cp / Cv of a state (gas_model.d:205)
+template <int GASM, int NSP>
+__device__ double gas_gamma(const EbGas* __restrict__ g, const Prim<NSP>& Q)
+{
+    if (GASM == EB200_GAS_IDEAL) return g->gamma_CpCv;
+    double Cp = 0.0, Cv = 0.0;
+    double cps[NSP];
+    for (int i = 0; i < NSP; ++i) { cea_Cp(g->curves[i], Q.T, cps[i]); Cp += Q.massf[i] * cps[i]; }
+    for (int i = 0; i < NSP; ++i) Cv += Q.massf[i] * (cps[i] - g->Rsp[i]);
+    return Cp / Cv;
+}
+
+// fluxcalc.d:187-385 for a state already in the face frame, gvel = 0.  side 0: gas on the right of the face.
+template <int DIM, int GASM, int NSP>
+__device__ void wall_flux_local(const EbGas* __restrict__ gas, const Prim<NSP>& fs, int side, double* F)
+{
+    typedef Layout<DIM, NSP> Lay;
+    const double vstar = 0.0;
+    const double a = fs.a, v = fs.vx;
+    const double gm = gas_gamma<GASM, NSP>(gas, fs);
+    const double rho = fs.rho, p = fs.p;
+    double tmp;
+    if (side == 0) {
+        const double Jminus = v - 2.0 * a / (gm - 1.0);
+        tmp = (vstar - Jminus) * (gm - 1.0) / (2.0 * sqrt(gm)) * sqrt(rho / pow(p, 1.0 / gm));
+    } else {
+        const double Jplus = v + 2.0 * a / (gm - 1.0);
+        tmp = (Jplus - vstar) * (gm - 1.0) / (2.0 * sqrt(gm)) * sqrt(rho / pow(p, 1.0 / gm));
+    }
+    const double ptiny = 0.1;            // flowstate_limits.min_pressure, globalconfig.d:85
+    double pstar = (tmp > 0.0) ? pow(tmp, 2.0 * gm / (gm - 1.0)) : ptiny;
+    if (pstar > 1.1 * p) {
+        int count = 0;
+        double incr_pstar;
+        do {
+            double fv[2];
+            const double dp = 0.001 * pstar;
+            for (int n = 0; n < 2; ++n) {
+                const double ps = (n == 0) ? pstar : pstar + dp;
+                const double xi = ps / p;
+                const double M1sq = 1.0 + (gm + 1.0) / 2.0 / gm * (xi - 1.0);
+                const double v1 = sqrt(M1sq) * a;
+                const double v2 = v1 * ((gm - 1.0) * M1sq + 2.0) / ((gm + 1.0) * M1sq);
+                fv[n] = (side == 0) ? (vstar - v1 + v2 - v) : (vstar + v1 - v2 - v);
+            }
+            incr_pstar = -fv[0] * dp / (fv[1] - fv[0]);
+            pstar += incr_pstar;
+            count += 1;
+        } while (fabs(incr_pstar) / pstar > 0.01 && count < 10);
+    }
+    pstar = fmin(pstar, p * 10.0);
+#pragma unroll
+    for (int q = 0; q < Lay::NCQ; ++q) F[q] = 0.0;
+    F[Lay::iXMom] = pstar;
+    F[Lay::iEnergy] = pstar * vstar;
+}
+
+template <int DIM, int FLUX, int GASM, int NSP, bool CART>
+__device__ __noinline__ bool face_flux_one_sided(const EbParams& P, const EbGas* __restrict__ gas, const EbBlockDesc& D,
+                                                 const EbArena& A, const double* __restrict__ prim,
+                                                 long long c, long long st, int d, int nL, int nR, double* F)
+{
+    typedef Layout<DIM, NSP> Lay;
+    const long long total = P.total;
+    Frame fr;
+    if (!CART) load_frame<DIM>(fr, A.face[d], total, c);
+    auto loc = [&](double& x, double& y, double& z) { if (CART) axis_to_local(D.fr[d], x, y, z); else to_local<DIM>(fr, x, y, z); };
+    auto glob = [&](double& x, double& y, double& z) { if (CART) axis_to_global(D.fr[d], x, y, z); else to_global<DIM>(fr, x, y, z); };
+    int mode;
+    if (nL == 0 && nR >= 2) mode = EB_ST_L0R2;
+    else if (nL == 1 && nR >= 2) mode = EB_ST_L1R2;
+    else if (nL >= 2 && nR == 1) mode = EB_ST_L2R1;
+    else if (nL >= 2 && nR == 0) mode = EB_ST_L2R0;
+    else if (nL >= 2 && nR >= 2) mode = EB_ST_L2R2;
+    else return false;                      // "Stencils not suitable for standard interpolation."
+    const bool has[4] = { nL >= 2, nL >= 1, nR >= 1, nR >= 2 };
+    const long long cc[4] = { c - 2 * st, c - st, c, c + st };
+    Prim<NSP> X[4];                         // L1, L0, R0, R1
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (has[m]) { load_prim<NSP>(X[m], prim, total, cc[m]); if (DIM == 2) X[m].vz = 0.0; }
+    }
+    if (!has[1]) X[1] = X[2];               // onedinterp.d:120-121
+    if (!has[2]) X[2] = X[1];
+    if (!has[0]) X[0] = X[1];               // never used by the stencil: defined values only
+    if (!has[3]) X[3] = X[2];
+    Prim<NSP> L = X[1], R = X[2];
+    bool ok = true;
+    const bool doL = (mode != EB_ST_L0R2), doR = (mode != EB_ST_L2R0);
+    const bool extrap_copy = (mode == EB_ST_L2R0 || mode == EB_ST_L0R2) && P.extrema_clipping;
+    if (P.interpolation_order > 1 && !extrap_copy) {
+        const bool local_frame = (P.local_frame != 0);
+        if (local_frame) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) loc(X[m].vx, X[m].vy, X[m].vz);
+        }
+        double len[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) len[m] = CART ? D.w[d].lenL0 : (has[m] ? ldg(A.len[d] + cc[m]) : 0.0);
+        if (mode == EB_ST_L2R0 && !CART) { len[0] = ldg(A.len[0] + cc[0]); len[1] = ldg(A.len[0] + cc[1]); }   // :236 passes iLength
+        EbOneSided I;
+        I.mode = mode; I.limiter = P.apply_limiter != 0; I.clip = P.extrema_clipping != 0; I.eps = P.eps_va;
+        I.w0 = 0.0; I.w1 = 0.0;
+        const double lenL1 = len[0], lenL0 = len[1], lenR0 = len[2], lenR1 = len[3];
+        if (mode == EB_ST_L2R2) l2r2_prepare(I.w, lenL1, lenL0, lenR0, lenR1);
+        else if (mode == EB_ST_L2R1) {
+            I.w.lenL0 = lenL0; I.w.lenR0 = lenR0;
+            I.w.aL0 = eb_div(0.5 * lenL0, (lenL1 + 2.0 * lenL0 + lenR0));
+            I.w.two_over_L0L1 = eb_div(2.0, (lenL0 + lenL1));
+            I.w.two_over_R0L0 = eb_div(2.0, (lenR0 + lenL0));
+            I.w.two_L0_plus_L1 = (2.0 * lenL0 + lenL1);
+            I.w0 = eb_div(lenR0, (lenL0 + lenR0)); I.w1 = eb_div(lenL0, (lenL0 + lenR0));
+        } else if (mode == EB_ST_L1R2) {
+            I.w.lenL0 = lenL0; I.w.lenR0 = lenR0;
+            I.w.aR0 = eb_div(0.5 * lenR0, (lenL0 + 2.0 * lenR0 + lenR1));
+            I.w.two_over_R0L0 = eb_div(2.0, (lenR0 + lenL0));
+            I.w.two_over_R1R0 = eb_div(2.0, (lenR1 + lenR0));
+            I.w.two_R0_plus_R1 = (2.0 * lenR0 + lenR1);
+            I.w0 = eb_div(lenR0, (lenL0 + lenR0)); I.w1 = eb_div(lenL0, (lenL0 + lenR0));
+        } else if (mode == EB_ST_L2R0) {
+            I.w0 = eb_div((2.0 * lenL0 + lenL1), (lenL0 + lenL1)); I.w1 = eb_div(-lenL0, (lenL0 + lenL1));
+        } else {
+            I.w0 = eb_div((2.0 * lenR0 + lenR1), (lenR0 + lenR1)); I.w1 = eb_div(-lenR0, (lenR0 + lenR1));
+        }
+        I.scalar(X[0].vx, X[1].vx, X[2].vx, X[3].vx, L.vx, R.vx);
+        I.scalar(X[0].vy, X[1].vy, X[2].vy, X[3].vy, L.vy, R.vy);
+        I.scalar(X[0].vz, X[1].vz, X[2].vz, X[3].vz, L.vz, R.vz);
+        if (NSP > 1) {
+            for (int i = 0; i < NSP; ++i) I.scalar(X[0].rho_s[i], X[1].rho_s[i], X[2].rho_s[i], X[3].rho_s[i], L.rho_s[i], R.rho_s[i]);
+        }
+        const int ti = P.thermo_interp;
+        bool okL = true, okR = true;
+        if (ti == EB200_INTERP_PT) {
+            I.scalar(X[0].p, X[1].p, X[2].p, X[3].p, L.p, R.p);
+            I.scalar(X[0].T, X[1].T, X[2].T, X[3].T, L.T, R.T);
+            if (doL) okL = thermo_from_pT<GASM, NSP>(gas, L);
+            if (doR) okR = thermo_from_pT<GASM, NSP>(gas, R);
+        } else {
+            if (NSP > 1) {
+                double rho_L = 0.0, rho_R = 0.0;
+                for (int i = 0; i < NSP; ++i) { rho_L += L.rho_s[i]; rho_R += R.rho_s[i]; }
+                if (doL) { L.rho = rho_L; for (int i = 0; i < NSP; ++i) L.massf[i] = L.rho_s[i] / L.rho; ok &= scale_mass_fractions<NSP>(L.massf); }
+                if (doR) { R.rho = rho_R; for (int i = 0; i < NSP; ++i) R.massf[i] = R.rho_s[i] / R.rho; ok &= scale_mass_fractions<NSP>(R.massf); }
+            } else I.scalar(X[0].rho, X[1].rho, X[2].rho, X[3].rho, L.rho, R.rho);
+            if (ti == EB200_INTERP_RHOP) {
+                I.scalar(X[0].p, X[1].p, X[2].p, X[3].p, L.p, R.p);
+                if (doL) okL = thermo_from_rhop<GASM, NSP>(gas, L);
+                if (doR) okR = thermo_from_rhop<GASM, NSP>(gas, R);
+            } else if (ti == EB200_INTERP_RHOT) {
+                I.scalar(X[0].T, X[1].T, X[2].T, X[3].T, L.T, R.T);
+                if (doL) okL = thermo_from_rhoT<GASM, NSP>(gas, L);
+                if (doR) okR = thermo_from_rhoT<GASM, NSP>(gas, R);
+            } else {
+                I.scalar(X[0].u, X[1].u, X[2].u, X[3].u, L.u, R.u);
+                if (doL) okL = thermo_from_rhou<GASM, NSP>(gas, L);
+                if (doR) okR = thermo_from_rhou<GASM, NSP>(gas, R);
+            }
+        }
+        if (!okL) L = X[1];                 // the cell's state, velocity in the frame the cells are in now
+        if (!okR) R = X[2];
+        if (ti == EB200_INTERP_PT && NSP > 1) {
+            if (doL) { for (int i = 0; i < NSP; ++i) L.massf[i] = L.rho_s[i] / L.rho; ok &= scale_mass_fractions<NSP>(L.massf); }
+            if (doR) { for (int i = 0; i < NSP; ++i) R.massf[i] = R.rho_s[i] / R.rho; ok &= scale_mass_fractions<NSP>(R.massf); }
+        }
+        if (local_frame) {                  // back to the global frame (the side that was not produced never left it)
+            if (doL) glob(L.vx, L.vy, L.vz);
+            if (doR) glob(R.vx, R.vy, R.vz);
+        }
+    }
+    // into the face frame (fluxcalc.d:61-66, 192-193, 294-295)
+    loc(L.vx, L.vy, L.vz); loc(R.vx, R.vy, R.vz);
+    if (nL == 0) wall_flux_local<DIM, GASM, NSP>(gas, R, 0, F);
+    else if (nR == 0) wall_flux_local<DIM, GASM, NSP>(gas, L, 1, F);
+    else {
+        const double alpha = (FluxPair<FLUX>::adaptive && A.Sf[d]) ? A.Sf[d][c] : 0.0;
+        flux_in_face_frame<DIM, NSP, GASM, FLUX>(P, gas, L, R, alpha, F);
+    }
+    double fx = F[Lay::iXMom], fy = F[Lay::iYMom], fz = (DIM == 3) ? F[Lay::iZMom] : 0.0;
+    glob(fx, fy, fz);
+    F[Lay::iXMom] = fx; F[Lay::iYMom] = fy;
+    if (DIM == 3) F[Lay::iZMom] = fz;
+    return ok;
+}
+
 // One interface: reconstruction (onedinterp.d:751-988) + flux (fluxcalc.d:54-184).
 // c = arena index of the cell on the plus side (right_cells[0]); st = stride along d.
 // bcf = boundary face id if the interface lies on a block boundary, else -1.
@@ -68,10 +297,16 @@ __device__ __forceinline__ void outflow_flux(const Prim<NSP>& fs, int outsign, d
 template <int DIM, int FLUX, int GASM, int NSP, bool CART>
 __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __restrict__ gas, const EbBlockDesc& D,
                                           const EbArena& A, const double* __restrict__ prim,
-                                          long long c, long long st, int d, int bcf, double* F)
+                                          long long c, long long st, int d, int bcf, double* F, int idx = 0, int nd = 0)
 {
     typedef Layout<DIM, NSP> Lay;
     const long long total = P.total;
+    if (D.noghost_faces) {                   // idx = index of the face along d, nd = cells of the block along d
+        int nL = 2, nR = 2;
+        if ((D.noghost_faces >> (2 * d)) & 1) nL = min(idx, 2);
+        if ((D.noghost_faces >> (2 * d + 1)) & 1) nR = min(nd - idx, 2);
+        if (nL < 2 || nR < 2) return face_flux_one_sided<DIM, FLUX, GASM, NSP, CART>(P, gas, D, A, prim, c, st, d, nL, nR, F);
+    }
     Frame fr;
     if (!CART) load_frame<DIM>(fr, A.face[d], total, c);
 
@@ -360,24 +595,25 @@ flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBloc
 #pragma unroll 1
         for (int job = 0; job < 4; ++job) {
             bool active; long long cf, st; int d, bcf = -1; int row = 0, col = 0;
+            int fidx, fn;               // index of the face along its direction, cells of the block along it
             if (job == 0) {             // west face of my cell
-                active = plane_has_cells && faceW_ok; cf = c; st = 1; d = 0;
+                active = plane_has_cells && faceW_ok; cf = c; st = 1; d = 0; fidx = i; fn = nic;
                 if (i == 0) bcf = EB200_WEST; else if (i == nic) bcf = EB200_EAST;
             } else if (job == 1) {      // south face
-                active = plane_has_cells && faceS_ok; cf = c; st = sj; d = 1;
+                active = plane_has_cells && faceS_ok; cf = c; st = sj; d = 1; fidx = j; fn = njc;
                 if (j == 0) bcf = EB200_SOUTH; else if (j == njc) bcf = EB200_NORTH;
             } else if (job == 2) {      // bottom face (3D)
                 if (DIM != 3) continue;
-                active = cell_ok; cf = c; st = sk; d = 2;
+                active = cell_ok; cf = c; st = sk; d = 2; fidx = k; fn = nkc;
                 if (k == 0) bcf = EB200_BOTTOM; else if (k == nkc) bcf = EB200_TOP;
             } else {                    // tile-edge faces
                 if (wy > 1) continue;
                 if (wy == 0) {
-                    active = plane_has_cells && extraE_ok; row = lane; d = 0; st = 1;
+                    active = plane_has_cells && extraE_ok; row = lane; d = 0; st = 1; fidx = i0 + 32; fn = nic;
                     cf = D.cell0 + ((long long)(k + D.kg) * D.NJ + (j0 + lane + EB_NG)) * D.NI + (i0 + 32 + EB_NG);
                     if (i0 + 32 == nic) bcf = EB200_EAST;
                 } else {
-                    active = plane_has_cells && extraN_ok; col = lane; d = 1; st = sj;
+                    active = plane_has_cells && extraN_ok; col = lane; d = 1; st = sj; fidx = j0 + TY; fn = njc;
                     cf = D.cell0 + ((long long)(k + D.kg) * D.NJ + (j0 + TY + EB_NG)) * D.NI + (i + EB_NG);
                     if (j0 + TY == njc) bcf = EB200_NORTH;
                 }
@@ -386,7 +622,7 @@ flux_update_kernel(const EbParams P, const EbGas* __restrict__ gas, const EbBloc
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) F[q] = 0.0;
             if (active) {
-                bool ok = face_flux<DIM, FLUX, GASM, NSP, CART>(P, gas, D, A, S.prim_in, cf, st, d, bcf, F);
+                bool ok = face_flux<DIM, FLUX, GASM, NSP, CART>(P, gas, D, A, S.prim_in, cf, st, d, bcf, F, fidx, fn);
                 fail |= !ok;
             }
             if (job == 0) {
@@ -519,7 +755,9 @@ void launch_face_debug_impl(const EbParams& P, int gas_model, const EbGas* gas, 
     if (gas_model == EB200_GAS_IDEAL) { if (P.dims == 3) EB_DBG(3, EB200_GAS_IDEAL, 1); else EB_DBG(2, EB200_GAS_IDEAL, 1); }
     else {
 #if EB_FLUX_HAS_TPG
-        if (P.nsp == 5) { if (P.dims == 3) EB_DBG(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_DBG(2, EB200_GAS_THERMALLY_PERFECT, 5); }
+#define EB_DBG_NSP(N) if (P.nsp == N) { if (P.dims == 3) EB_DBG(3, EB200_GAS_THERMALLY_PERFECT, N); else EB_DBG(2, EB200_GAS_THERMALLY_PERFECT, N); }
+        EB_TPG_NSP_LIST(EB_DBG_NSP)
+#undef EB_DBG_NSP
 #endif
     }
 #undef EB_DBG
@@ -541,7 +779,9 @@ void launch_flux_update_impl(const EbParams& P, int gas_model, const EbGas* gas,
     } else {
 #if EB_FLUX_HAS_TPG
 #ifndef EB_TP_DEV3D
-        if (P.nsp == 5) { if (P.dims == 3) EB_LAUNCH(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_LAUNCH(2, EB200_GAS_THERMALLY_PERFECT, 5); }
+#define EB_LAUNCH_NSP(N) if (P.nsp == N) { if (P.dims == 3) EB_LAUNCH(3, EB200_GAS_THERMALLY_PERFECT, N); else EB_LAUNCH(2, EB200_GAS_THERMALLY_PERFECT, N); }
+        EB_TPG_NSP_LIST(EB_LAUNCH_NSP)
+#undef EB_LAUNCH_NSP
 #endif
 #endif
     }

@@ -273,11 +273,13 @@ __device__ __forceinline__ void tp_make_state(const TpGasS<NSP>& G, const EbGas*
     X.a = a0;
 }
 
-// both sides of cell c along direction d (stride st): M at its minus face, Pl at its plus face
+// both sides of cell c along direction d (stride st): the state at its plus face goes straight to where its reader
+// will look for it (dstP, field stride strideP: shared memory), the state at its minus face comes back in M -- one
+// state in registers at a time
 template <int DIM, int NSP>
 __device__ __forceinline__ void tp_cell_states(const EbBlockDesc& D, const TpGasS<NSP>& G, const EbGas* __restrict__ gas, int d, double eps,
                                                bool clip, const double* __restrict__ prim, long long total, long long c, long long st,
-                                               bool wantM, bool wantP, Prim<NSP>& M, Prim<NSP>& Pl, bool& fail, Prim<NSP>& rare)
+                                               bool wantM, bool wantP, double* dstP, int strideP, Prim<NSP>& M, bool& fail, Prim<NSP>& rare)
 {
     constexpr int NV = TpCfg<DIM, NSP>::NV;
     double qM[NV], qP[NV];
@@ -297,8 +299,12 @@ __device__ __forceinline__ void tp_cell_states(const EbBlockDesc& D, const TpGas
     const double T0 = ldg(prim + 3 * total + c), a0 = ldg(prim + 4 * total + c);
     TpCellTable<NSP> tb;
     tp_table<NSP>(G, T0, tb);
+    if (wantP) {
+        Prim<NSP> X;
+        tp_make_state<DIM, NSP>(G, gas, prim, total, c, qP, a0, tb, X, fail, rare);
+        tp_put<NSP>(dstP, strideP, X);
+    }
     if (wantM) tp_make_state<DIM, NSP>(G, gas, prim, total, c, qM, a0, tb, M, fail, rare);
-    if (wantP) tp_make_state<DIM, NSP>(G, gas, prim, total, c, qP, a0, tb, Pl, fail, rare);
 }
 
 // flux of a face along direction dir from complete states; F in conserved-quantity order, momentum in (x, y, z)
@@ -493,16 +499,22 @@ struct TpSmem {
     static constexpr int O_PJ = 0;                                    // [TY + 1][NS][32]: slot r = plus state (along j) of row r - 1
     static constexpr int O_FS = O_PJ + (TY + 1) * NS * 32;            // [TY + 1][NCQ][32]: south-face fluxes, row TY = north edge
     static constexpr int O_PIW = O_FS + (TY + 1) * NCQ * 32;          // [2][NS][TY]: plus state (along i) of the cell west of the tile, by plane parity
-    static constexpr int O_PIE = O_PIW + 2 * NS * TY;                 // [NS][TY]: plus state (along i) of lane 31
-    static constexpr int O_FE = O_PIE + NS * TY;                      // [NCQ][TY]: east-edge fluxes
-    static constexpr int O_K = O_FE + NCQ * TY;                       // [NS][NTM]: plus state along k of the cell one plane below
-    static constexpr int O_ACC = O_K + ((DIM == 3) ? NS * NTM : 0);   // [NACC][NTM]: partial surface integral
+    static constexpr int O_PI = O_PIW + 2 * NS * TY;                  // [TY][NS][32]: plus state (along i) of every cell of the tile
+    static constexpr int O_MJ = O_PI + TY * NS * 32;                  // [TY][NS][32]: minus state (along j), parked across the barrier
+    static constexpr int O_FE = O_MJ + TY * NS * 32;                  // [NCQ][TY]: east-edge fluxes
+    static constexpr int O_K = O_FE + NCQ * TY;                       // [2][NS][NTM]: plus state along k of the cell one plane below, by plane parity
+    static constexpr int O_ACC = O_K + ((DIM == 3) ? 2 * NS * NTM : 0);   // [NACC][NTM]: partial surface integral
     static constexpr int O_DESC = O_ACC + NACC * NTM;
     static constexpr size_t BYTES = sizeof(double) * O_DESC + sizeof(EbBlockDesc);
 };
 
 template <int DIM, int FLUX, int NSP, int TY>
-__global__ void __launch_bounds__(32 * (TY + 2), EB_TP_MIN_CTAS)
+__global__ void
+#ifdef EB_TP_MAXNREG
+__maxnreg__(EB_TP_MAXNREG)
+#else
+__launch_bounds__(32 * (TY + 2), EB_TP_MIN_CTAS)
+#endif
 flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbBlockDesc* __restrict__ descs, int nblocks,
                       const EbArena A, const EbStageArgs S)
 {
@@ -514,7 +526,8 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
     double* const sPj = smem + SM::O_PJ;
     double* const sFS = smem + SM::O_FS;
     double* const sPiW = smem + SM::O_PIW;
-    double* const sPiE = smem + SM::O_PIE;
+    double* const sPi = smem + SM::O_PI;
+    double* const sMj = smem + SM::O_MJ;
     double* const sFE = smem + SM::O_FE;
     double* const sK = smem + SM::O_K;
     double* const sAcc = smem + SM::O_ACC;
@@ -570,7 +583,7 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
     bool fail = false;
     int n_invalid = 0;
     Prim<NSP> rare;                                   // scratch of the out-of-line reference route (see tp_thermo)
-    const int kfirst = (DIM == 3) ? k0 - 1 : 0;       // 3D: the plane below the chunk only gives the first k states
+    const int kfirst = k0 - 1;       // a lead-in pass: the first states along k (3D) and the west halo of the first plane
     const int kend = (DIM == 3) ? k1 : 0;
 
     // =============================== helper warps ==============================================================
@@ -583,29 +596,25 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
         const bool colOk = (lane < TY) && (j0 + lane < njc) && (h0 || (i0 + 32 <= nic));
         Prim<NSP> Y, Z;
         for (int k = kfirst; k <= kend; ++k) {
-            const bool pre = (DIM == 3) && (k < k0);
-            const bool has_cells = !pre && ((DIM == 3) ? (k < k1) : true);
+            const bool pre = (k < k0);
+            const bool has_cells = !pre && (k < k1);
             if (!pre && !has_cells) break;
             const int par = (k - k0) & 1;
 #pragma unroll 1
             for (int jb = 0; jb < 2; ++jb) {
                 // jb 0: the row (along j);  jb 1: the column (along i; the west column belongs to the next plane)
                 const int d = (jb == 0) ? 1 : 0;
-                const int kk = (h0 && jb == 1 && DIM == 3) ? k + 1 : k;
+                const int kk = (h0 && jb == 1) ? k + 1 : k;
                 bool act = (jb == 0) ? (rowOk && !pre) : colOk;
-                if (jb == 1 && h0 && DIM == 3 && kk >= k1) act = false;
+                if (jb == 1 && h0 && kk >= k1) act = false;
                 if (jb == 1 && !h0 && pre) act = false;
-                if (DIM == 2 && jb == 1 && h0) act = colOk;
                 const long long cc = (jb == 0) ? cell_at(i, h0 ? j0 - 1 : j0 + TY, kk) : cell_at(h0 ? i0 - 1 : i0 + 32, j0 + lane, kk);
-                Prim<NSP> M, Pl;
+                Prim<NSP> M;
                 if (act) {
-                    tp_cell_states<DIM, NSP>(D, G, gas, d, eps_of(d), clip, prim, total, cc, (d == 0) ? 1 : sj, !h0, h0, M, Pl, fail, rare);
-                    if (h0) {
-                        if (jb == 0) tp_put<NSP>(sPj + lane, 32, Pl);
-                        else tp_put<NSP>(sPiW + ((((DIM == 3) ? (par ^ 1) : 0) * NS) * TY) + lane, TY, Pl);
-                    } else {
-                        if (jb == 0) Y = M; else Z = M;
-                    }
+                    double* dstP = (jb == 0) ? sPj + lane : sPiW + (((par ^ 1) * NS) * TY) + lane;
+                    tp_cell_states<DIM, NSP>(D, G, gas, d, eps_of(d), clip, prim, total, cc, (d == 0) ? 1 : sj, !h0, h0,
+                                             dstP, (jb == 0) ? 32 : TY, M, fail, rare);
+                    if (!h0) { if (jb == 0) Y = M; else Z = M; }
                 }
             }
             __syncthreads();
@@ -620,7 +629,8 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
                     double F[NCQ];
                     if (!tp_outflow_override<DIM, NSP>(P, D, prim, d, (jb == 0) ? j0 + TY : i0 + 32, (jb == 0) ? njc : nic, cf, (jb == 0) ? sj : 1, F)) {
                         Prim<NSP> L;
-                        if (jb == 0) tp_get<NSP>(sPj + (TY * NS) * 32 + lane, 32, L); else tp_get<NSP>(sPiE + lane, TY, L);
+                        if (jb == 0) tp_get<NSP>(sPj + (TY * NS) * 32 + lane, 32, L);
+                        else tp_get<NSP>(sPi + (lane * NS) * 32 + 31, 32, L);          // the plus state of lane 31 in row `lane`
                         tp_face_flux<DIM, NSP, FLUX>(P, gas, d, L, (jb == 0) ? Y : Z, alpha_at(d, cf), F);
                     }
                     if (jb == 0) {
@@ -643,17 +653,18 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
     const bool cell_ok = (i < nic) && (j < njc);
     const bool doI = (i <= nic) && (j < njc);
     const bool doJ = (i < nic) && (j <= njc);
-    double* const myK = sK + tid;             // field f at stride NTM
+    double* const myK = sK + tid;             // field f at stride NTM, buffer b at b * NS * NTM
     double* const myAcc = sAcc + tid;
+    double* const myPi = sPi + (wy * NS) * 32 + lane;
+    double* const myMj = sMj + (wy * NS) * 32 + lane;
     const double aI = D.area[0], aJ = D.area[1], aK = D.area[2];
 
     for (int k = kfirst; k <= kend; ++k) {
-        const bool pre = (DIM == 3) && (k < k0);
-        const bool has_cells = !pre && ((DIM == 3) ? (k < k1) : true);
+        const bool pre = (k < k0);
+        const bool has_cells = !pre && (k < k1);
         const int par = (k - k0) & 1;
-        const long long c = cell_at(i, j, k);
-        Prim<NSP> Mj;
-        const int nd = (DIM == 3) ? (has_cells ? 3 : 1) : 2;
+        const long long c = cell_at(i, j, (DIM == 3) ? k : 0);
+        const int nd = (DIM == 3) ? (has_cells ? 3 : 1) : (pre ? 0 : 2);
 #pragma unroll 1
         for (int dd = 0; dd < nd; ++dd) {
             // 3D: along k first (the bottom face of this plane is the top face of the cell one plane below, which is then
@@ -663,32 +674,30 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
             const bool wM = !pre;
             const bool wP = (d == 2) ? (pre || has_cells) : cell_ok;
             const long long st = (d == 0) ? 1 : ((d == 1) ? sj : sk);
-            Prim<NSP> M, L;
-            if (act) tp_cell_states<DIM, NSP>(D, G, gas, d, eps_of(d), clip, prim, total, c, st, wM, wP, M, L, fail, rare);      // L: the plus state for now
-            bool dofl = false;
-            if (d == 2) {
-                if (cell_ok) {
-                    Prim<NSP> Pl = L;
-                    if (!pre) { tp_get<NSP>(myK, NTM, L); dofl = true; }
-                    if (wP) tp_put<NSP>(myK, NTM, Pl);
-                }
-            } else if (d == 0) {
-                if (lane == 31 && cell_ok) tp_put<NSP>(sPiE + wy, TY, L);
-                tp_shfl_up<NSP>(L);
-                if (lane == 0 && doI) tp_get<NSP>(sPiW + ((((DIM == 3) ? par : 0) * NS) * TY) + wy, TY, L);
-                dofl = doI;
-            } else {
-                if (cell_ok) tp_put<NSP>(sPj + ((wy + 1) * NS) * 32 + lane, 32, L);
-                Mj = M;
+            // where the plus state goes: along k into the other buffer of the thread's slot (this plane still needs the
+            // one below), along i into the row buffer (read by the next lane), along j into the slot of the row above
+            double* dstP = (d == 2) ? myK + ((par ^ 1) * NS) * NTM : ((d == 0) ? myPi : sPj + ((wy + 1) * NS) * 32 + lane);
+            const int strideP = (d == 2) ? NTM : 32;
+            Prim<NSP> M;
+            if (act) tp_cell_states<DIM, NSP>(D, G, gas, d, eps_of(d), clip, prim, total, c, st, wM, wP, dstP, strideP, M, fail, rare);
+            if (d == 1) {
+                if (doJ) tp_put<NSP>(myMj, 32, M);
+                continue;
             }
-            if (d == 1) continue;
+            if (d == 0) __syncwarp();
             double F[NCQ];
 #pragma unroll
             for (int q = 0; q < NCQ; ++q) F[q] = 0.0;
+            const bool dofl = (d == 2) ? (cell_ok && !pre) : doI;
             if (dofl) {
                 const int idx = (d == 0) ? i : k, n = (d == 0) ? nic : nkc;
-                if (!tp_outflow_override<DIM, NSP>(P, D, prim, d, idx, n, c, st, F))
+                if (!tp_outflow_override<DIM, NSP>(P, D, prim, d, idx, n, c, st, F)) {
+                    Prim<NSP> L;
+                    if (d == 2) tp_get<NSP>(myK + (par * NS) * NTM, NTM, L);
+                    else if (lane == 0) tp_get<NSP>(sPiW + ((par * NS) * TY) + wy, TY, L);
+                    else tp_get<NSP>(myPi - 1, 32, L);
                     tp_face_flux<DIM, NSP, FLUX>(P, gas, d, L, M, alpha_at(d, c), F);
+                }
             }
             if (d == 2) {
                 if (cell_ok && !pre) {
@@ -737,8 +746,9 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
             for (int q = 0; q < NCQ; ++q) FS_[q] = 0.0;
             if (doJ) {
                 if (!tp_outflow_override<DIM, NSP>(P, D, prim, 1, j, njc, c, sj, FS_)) {
-                    Prim<NSP> L;
+                    Prim<NSP> L, Mj;
                     tp_get<NSP>(sPj + (wy * NS) * 32 + lane, 32, L);
+                    tp_get<NSP>(myMj, 32, Mj);
                     tp_face_flux<DIM, NSP, FLUX>(P, gas, 1, L, Mj, alpha_at(1, c), FS_);
                 }
             }
@@ -815,11 +825,9 @@ bool launch_flux_update_tp_impl(const EbParams& P, const EbGas* gas, const EbBlo
                                 long long ncta, const EbArena& A, const EbStageArgs& S, cudaStream_t st)
 {
 #define EB_TP(DIM, NSP) launch_one_tp<DIM, FLUX, NSP>(P, gas, desc, nblocks, ncta, A, S, st)
-#ifdef EB_TP_DEV3D
-    if (P.nsp == 5 && P.dims == 3) { EB_TP(3, 5); return true; }
-#else
-    if (P.nsp == 5) { if (P.dims == 3) EB_TP(3, 5); else EB_TP(2, 5); return true; }
-#endif
+#define EB_TP_NSP(N) if (P.nsp == N) { if (P.dims == 3) EB_TP(3, N); else EB_TP(2, N); return true; }
+    EB_TPG_NSP_LIST(EB_TP_NSP)
+#undef EB_TP_NSP
 #undef EB_TP
     return false;
 }

@@ -127,7 +127,9 @@ void launch_decode(const EbParams& P, int gas_model, const EbGas* gas, const EbB
 #define EB_DEC(DIM, GASM, NSP) decode_kernel<DIM, GASM, NSP><<<blocks, threads, 0, st>>>(P, gas, hdesc, prim_in, prim_out, U, do_encode, status)
     if (gas_model == EB200_GAS_IDEAL) { if (P.dims == 3) EB_DEC(3, EB200_GAS_IDEAL, 1); else EB_DEC(2, EB200_GAS_IDEAL, 1); }
 #ifndef EB_NO_TPG
-    else if (P.nsp == 5) { if (P.dims == 3) EB_DEC(3, EB200_GAS_THERMALLY_PERFECT, 5); else EB_DEC(2, EB200_GAS_THERMALLY_PERFECT, 5); }
+#define EB_DEC_NSP(N) else if (P.nsp == N) { if (P.dims == 3) EB_DEC(3, EB200_GAS_THERMALLY_PERFECT, N); else EB_DEC(2, EB200_GAS_THERMALLY_PERFECT, N); }
+    EB_TPG_NSP_LIST(EB_DEC_NSP)
+#undef EB_DEC_NSP
 #endif
 #undef EB_DEC
 }
@@ -404,11 +406,78 @@ void launch_unpack(const EbParams& P, double* prim, double* S, const int* idx, l
 
 // ---------------------------------------------------------------------------------------
 // detect_shocks (simcore_gasdynamic_step.d:3197-3224) with shock_detector_smoothing = 0, one block:
-//   pass 0  detect_shock_points  (fluidblock.d:479-520): PJ_ShockDetector (shockdetectors.d:22-93) on every face
-//   pass 1  shock_faces_to_cells (:573-583)
-//   pass 2  enforce_strict_shock_detector (:585-605); ghost-cell S is what the last ghost fill copied.
+//   detect_shock_points  (fluidblock.d:479-520): PJ_ShockDetector (shockdetectors.d:22-93) on every face
+//   shock_faces_to_cells (:573-583)
+//   enforce_strict_shock_detector (:585-605); ghost-cell S is what the last ghost fill copied.
 // One thread per position of the block extended by one cell on the plus side of every direction.
 
+// PJ_ShockDetector (shockdetectors.d:22-93) for the face between cells cL and cR = cL + st along direction d
+// side: 0 = the face has a cell on both sides; 1 = only the left cell exists (a wall without ghost-cell data on the
+// right), 2 = only the right cell: shockdetectors.d:48-84, the gas velocity relative to the wall (gvel = 0)
+template <int DIM>
+__device__ __forceinline__ double pj_detector(const EbParams& P, const EbBlockDesc& D, const EbArena& A, const double* __restrict__ prim,
+                                              int d, long long cR, long long st, int side = 0)
+{
+    const long long total = P.total, c = cR;
+    if (side != 0) {
+        const long long cc = (side == 1) ? c - st : c;
+        const double vx = ldg(prim + 5 * total + cc), vy = ldg(prim + 6 * total + cc);
+        const double vz = (DIM == 3) ? ldg(prim + 7 * total + cc) : 0.0;
+        const double a = ldg(prim + 4 * total + cc);
+        double n_[3], t1[3], t2[3];
+        if (D.cartesian) {
+            for (int m = 0; m < 3; ++m) { n_[m] = 0.0; t1[m] = 0.0; t2[m] = 0.0; }
+            n_[D.fr[d].perm[0]] = D.fr[d].neg[0] ? -1.0 : 1.0;
+            t1[D.fr[d].perm[1]] = D.fr[d].neg[1] ? -1.0 : 1.0;
+            t2[D.fr[d].perm[2]] = D.fr[d].neg[2] ? -1.0 : 1.0;
+        } else {
+            for (int m = 0; m < 3; ++m) {
+                n_[m] = ldg(A.face[d] + m * total + c); t1[m] = ldg(A.face[d] + (3 + m) * total + c);
+                t2[m] = ldg(A.face[d] + (6 + m) * total + c);
+            }
+        }
+        const double u = vx * n_[0] + vy * n_[1] + vz * n_[2];
+        const double comp = (side == 1) ? ((-u) / a) : (u / a);
+        const double v = vx * t1[0] + vy * t1[1] + vz * t1[2];
+        const double w = vx * t2[0] + vy * t2[1] + vz * t2[2];
+        const double shear = fmax(fabs(v) / a, fabs(w) / a);
+        return ((shear < P.shear_tol) && (comp < P.comp_tol)) ? 1.0 : 0.0;
+    }
+    const double vLx = ldg(prim + 5 * total + c - st), vLy = ldg(prim + 6 * total + c - st);
+    const double vLz = (DIM == 3) ? ldg(prim + 7 * total + c - st) : 0.0;
+    const double vRx = ldg(prim + 5 * total + c), vRy = ldg(prim + 6 * total + c);
+    const double vRz = (DIM == 3) ? ldg(prim + 7 * total + c) : 0.0;
+    const double aL = ldg(prim + 4 * total + c - st), aR = ldg(prim + 4 * total + c);
+    double n_[3], t1[3], t2[3];
+    if (D.cartesian) {
+        // reconstruct the exact +-1/0 frame of this direction from the descriptor
+        for (int m = 0; m < 3; ++m) { n_[m] = 0.0; t1[m] = 0.0; t2[m] = 0.0; }
+        n_[D.fr[d].perm[0]] = D.fr[d].neg[0] ? -1.0 : 1.0;
+        t1[D.fr[d].perm[1]] = D.fr[d].neg[1] ? -1.0 : 1.0;
+        t2[D.fr[d].perm[2]] = D.fr[d].neg[2] ? -1.0 : 1.0;
+    } else {
+        for (int m = 0; m < 3; ++m) {
+            n_[m] = ldg(A.face[d] + m * total + c); t1[m] = ldg(A.face[d] + (3 + m) * total + c);
+            t2[m] = ldg(A.face[d] + (6 + m) * total + c);
+        }
+    }
+    const double uL = vLx * n_[0] + vLy * n_[1] + vLz * n_[2];
+    const double uR = vRx * n_[0] + vRy * n_[1] + vRz * n_[2];
+    const double a_min = (aL < aR) ? aL : aR;
+    const double comp = ((uR - uL) / a_min);
+    const double vL = vLx * t1[0] + vLy * t1[1] + vLz * t1[2], vR = vRx * t1[0] + vRy * t1[1] + vRz * t1[2];
+    const double wL = vLx * t2[0] + vLy * t2[1] + vLz * t2[2], wR = vRx * t2[0] + vRy * t2[1] + vRz * t2[2];
+    const double sound_speed = 0.5 * (aL + aR);
+    const double shear_y = fabs(vL - vR) / sound_speed;
+    const double shear_z = fabs(wL - wR) / sound_speed;
+    const double shear = fmax(shear_y, shear_z);
+    return ((shear < P.shear_tol) && (comp < P.comp_tol)) ? 1.0 : 0.0;
+}
+
+// pass 0: the detector on the minus-side faces of every position AND, in the same launch, shock_faces_to_cells for
+// interior cells: the detector of a cell's plus-side faces is evaluated a second time by the cell itself (a pure
+// function of the same FlowStates: the same value the owner of that face stores), which saves a pass over the block.
+// pass 2: enforce_strict_shock_detector.
 template <int DIM>
 __global__ void shock_kernel(const EbParams P, const EbBlockDesc D, const EbArena A, const double* __restrict__ prim, int pass)
 {
@@ -418,59 +487,32 @@ __global__ void shock_kernel(const EbParams P, const EbBlockDesc D, const EbAren
     if (t >= n) return;
     const int i = (int)(t % ei), j = (int)((t / ei) % ej), k = (int)(t / ((long long)ei * ej));
     const long long c = D.cell0 + ((long long)(k + D.kg) * D.NJ + (j + EB_NG)) * D.NI + (i + EB_NG);
-    const long long total = P.total;
     const bool in_i = i < D.nic, in_j = j < D.njc, in_k = (DIM == 3) ? (k < D.nkc) : true;
-    if (pass == 1) {
-        if (!(in_i && in_j && in_k)) return;
-        double S = 0.0;                                    // iface order W,E,S,N,B,T
-        S = fmax(S, A.Sf[0][c]); S = fmax(S, A.Sf[0][c + 1]);
-        S = fmax(S, A.Sf[1][c]); S = fmax(S, A.Sf[1][c + D.stride[1]]);
-        if (DIM == 3) { S = fmax(S, A.Sf[2][c]); S = fmax(S, A.Sf[2][c + D.stride[2]]); }
-        A.S[c] = S;
-        return;
-    }
+    double Smax = 0.0;                                     // iface order W,E,S,N,B,T; max is order-independent
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
         // the face on the minus-d side of this position exists if the other two indices are interior
         const bool face_ok = (d == 0) ? (in_j && in_k) : ((d == 1) ? (in_i && in_k) : (in_i && in_j));
         if (!face_ok) continue;
         const long long st = D.stride[d];
+        // faces on a boundary without ghost-cell data have a cell on one side only
+        const int idx = (d == 0) ? i : ((d == 1) ? j : k), nd = (d == 0) ? D.nic : ((d == 1) ? D.njc : D.nkc);
+        const bool wallL = (D.noghost_faces >> (2 * d)) & 1, wallR = (D.noghost_faces >> (2 * d + 1)) & 1;
+        const int side = (wallL && idx == 0) ? 2 : ((wallR && idx == nd) ? 1 : 0);
         if (pass == 0) {
-            const double vLx = ldg(prim + 5 * total + c - st), vLy = ldg(prim + 6 * total + c - st);
-            const double vLz = (DIM == 3) ? ldg(prim + 7 * total + c - st) : 0.0;
-            const double vRx = ldg(prim + 5 * total + c), vRy = ldg(prim + 6 * total + c);
-            const double vRz = (DIM == 3) ? ldg(prim + 7 * total + c) : 0.0;
-            const double aL = ldg(prim + 4 * total + c - st), aR = ldg(prim + 4 * total + c);
-            double n_[3], t1[3], t2[3];
-            if (D.cartesian) {
-                // reconstruct the exact +-1/0 frame of this direction from the descriptor
-                for (int m = 0; m < 3; ++m) { n_[m] = 0.0; t1[m] = 0.0; t2[m] = 0.0; }
-                n_[D.fr[d].perm[0]] = D.fr[d].neg[0] ? -1.0 : 1.0;
-                t1[D.fr[d].perm[1]] = D.fr[d].neg[1] ? -1.0 : 1.0;
-                t2[D.fr[d].perm[2]] = D.fr[d].neg[2] ? -1.0 : 1.0;
-            } else {
-                for (int m = 0; m < 3; ++m) {
-                    n_[m] = ldg(A.face[d] + m * total + c); t1[m] = ldg(A.face[d] + (3 + m) * total + c);
-                    t2[m] = ldg(A.face[d] + (6 + m) * total + c);
-                }
+            const double Sf = pj_detector<DIM>(P, D, A, prim, d, c, st, side);
+            A.Sf[d][c] = Sf;
+            if (in_i && in_j && in_k) {
+                Smax = fmax(Smax, Sf);
+                Smax = fmax(Smax, pj_detector<DIM>(P, D, A, prim, d, c + st, st, (wallR && idx + 1 == nd) ? 1 : 0));
             }
-            const double uL = vLx * n_[0] + vLy * n_[1] + vLz * n_[2];
-            const double uR = vRx * n_[0] + vRy * n_[1] + vRz * n_[2];
-            const double a_min = (aL < aR) ? aL : aR;
-            const double comp = ((uR - uL) / a_min);
-            const double vL = vLx * t1[0] + vLy * t1[1] + vLz * t1[2], vR = vRx * t1[0] + vRy * t1[1] + vRz * t1[2];
-            const double wL = vLx * t2[0] + vLy * t2[1] + vLz * t2[2], wR = vRx * t2[0] + vRy * t2[1] + vRz * t2[2];
-            const double sound_speed = 0.5 * (aL + aR);
-            const double shear_y = fabs(vL - vR) / sound_speed;
-            const double shear_z = fabs(wL - wR) / sound_speed;
-            const double shear = fmax(shear_y, shear_z);
-            A.Sf[d][c] = ((shear < P.shear_tol) && (comp < P.comp_tol)) ? 1.0 : 0.0;
         } else {
             double Sf = A.Sf[d][c];
-            if (Sf > 0.0 || A.S[c - st] > 0.0 || A.S[c] > 0.0) Sf = 1.0;
+            if (Sf > 0.0 || (side != 2 && A.S[c - st] > 0.0) || (side != 1 && A.S[c] > 0.0)) Sf = 1.0;     // fluidblock.d:585-605: cells that exist
             A.Sf[d][c] = Sf;
         }
     }
+    if (pass == 0 && in_i && in_j && in_k) A.S[c] = Smax;
 }
 
 void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A, const double* prim, cudaStream_t st)
@@ -478,8 +520,7 @@ void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbA
     const long long n = (long long)(hdesc.nic + 1) * (hdesc.njc + 1) * ((P.dims == 3) ? hdesc.nkc + 1 : 1);
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    const int npass = P.strict_shock ? 3 : 2;
-    for (int pass = 0; pass < npass; ++pass) {
+    for (int pass = 0; pass <= (P.strict_shock ? 2 : 0); pass += 2) {
         if (P.dims == 3) shock_kernel<3><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, pass);
         else shock_kernel<2><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, pass);
     }

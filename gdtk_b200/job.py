@@ -19,7 +19,7 @@ import os
 from . import io
 from .gas import FlowState, set_gas_model
 from .sim import (Config, ExchangeBC_FullFace, FluidBlock, InFlowBC_Supersonic, OutFlowBC_FixedP, OutFlowBC_FixedPT,
-                  OutFlowBC_SimpleExtrapolate, OutFlowBC_SimpleFlux, WallBC_WithSlip)
+                  OutFlowBC_SimpleExtrapolate, OutFlowBC_SimpleFlux, WallBC_WithSlip, WallBC_WithSlip1)
 
 FACES = ["west", "east", "south", "north", "bottom", "top"]          # _abi face order
 
@@ -50,8 +50,12 @@ def _bc_from_json(gm, face, b):
     pre = b.get("pre_recon_action", [])
     post = b.get("post_conv_flux_action", [])
     types = [e["type"] for e in pre]
-    if b.get("is_wall_with_viscous_effects") or not b.get("ghost_cell_data_available", True):
-        raise ValueError(f"boundary {face}: viscous walls and no-ghost-cell boundaries are not on this path")
+    if b.get("is_wall_with_viscous_effects"):
+        raise ValueError(f"boundary {face}: viscous walls are not on this path")
+    if not b.get("ghost_cell_data_available", True):
+        if not types and not post:
+            return WallBC_WithSlip1()            # bc.lua:783-806
+        raise ValueError(f"boundary {face}: a boundary without ghost-cell data and with effects {types} + {[e['type'] for e in post]} is not on this path")
     if types == ["internal_copy_then_reflect"] and not post:
         return WallBC_WithSlip()
     if types == ["flowstate_copy"] and not post:
@@ -76,7 +80,10 @@ def _bc_from_json(gm, face, b):
 
 def _bc_to_json(bc, nsp):
     pre, post, kind = [], [], "wall_with_slip"
-    if isinstance(bc, WallBC_WithSlip):
+    ghost = True
+    if isinstance(bc, WallBC_WithSlip1):
+        ghost = False
+    elif isinstance(bc, WallBC_WithSlip):
         pre = [{"type": "internal_copy_then_reflect"}]
     elif isinstance(bc, InFlowBC_Supersonic):
         kind = "inflow_supersonic"
@@ -101,7 +108,7 @@ def _bc_to_json(bc, nsp):
                 "Rmatrix": [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]}]
     else:
         raise ValueError(f"cannot write boundary condition {type(bc).__name__}")
-    return {"label": "", "type": kind, "group": "", "is_wall_with_viscous_effects": False, "ghost_cell_data_available": True,
+    return {"label": "", "type": kind, "group": "", "is_wall_with_viscous_effects": False, "ghost_cell_data_available": ghost,
             "convective_flux_computed_in_bc": bool(post), "is_design_surface": False, "num_cntrl_pts": 0,
             "pre_recon_action": pre, "post_conv_flux_action": post, "pre_spatial_deriv_action_at_bndry_faces": [],
             "pre_spatial_deriv_action_at_bndry_cells": [], "post_diff_flux_action": []}

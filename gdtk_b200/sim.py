@@ -172,6 +172,44 @@ class WallBC_WithSlip(BoundaryCondition):
     kind = _abi.BC_WALL_WITH_SLIP
 
 
+class WallBC_WithSlip1(BoundaryCondition):
+    """bc.lua:783-806: a slip wall WITHOUT ghost-cell data (ghost_cell_data_available = false, no preReconAction).
+    The faces next to it are reconstructed from one-sided stencils (onedinterp.d:117-273: l0r2 / l1r2 / l2r1 / l2r0)
+    and the wall face takes the one-sided wall flux (fluxcalc.d:187-385)."""
+    kind = _abi.BC_WALL_WITH_SLIP1
+
+
+class UserDefinedBC(BoundaryCondition):
+    """bc.lua UserDefinedBC whose ``ghostCells`` function depends on the position of the ghost cell only (the vortex
+    inflow of examples/eilmer/2D/vortex-supersonic/udf-vortex-flow.lua): ``ghost_state(x, y, z) -> FlowState``.
+    bc/user_defined_effects.d:237-310 calls the Lua function with the ghost-cell centres every stage; a function of
+    position gives the same FlowStates every time, so it is evaluated once, at set-up, at the centres the reference
+    gives its ghost cells (sfluidblock.d:897-1086: linear extrapolation from the two cells inside)."""
+    kind = _abi.BC_GHOST_PROFILE
+
+    def __init__(self, ghost_state):
+        self.ghost_state = ghost_state
+
+    def params_for(self, geom, face):
+        d, hi = face // 2, face & 1
+        n = (geom.nic, geom.njc, geom.nkc)
+        off = (NG, NG, geom.kg)
+        d1, d2 = (d + 1) % 3, (d + 2) % 3
+        out = []
+        for a2 in range(n[d2]):
+            for a1 in range(n[d1]):
+                def centre(m):                      # interior cell m layers in from the face
+                    idx = [0, 0, 0]
+                    idx[d], idx[d1], idx[d2] = (n[d] - 1 - m if hi else m), a1, a2
+                    return geom.pos[:, idx[2] + off[2], idx[1] + off[1], idx[0] + off[0]]
+                c1, c2 = centre(0), centre(1)
+                g0 = 2.0 * c1 - c2                  # extrap(ghost, cell_1, cell_2)
+                g1 = 2.0 * g0 - c1
+                for pos in (g0, g1):
+                    out += self.ghost_state(float(pos[0]), float(pos[1]), float(pos[2])).as_prims()
+        return out
+
+
 class InFlowBC_Supersonic(BoundaryCondition):
     kind = _abi.BC_INFLOW_SUPERSONIC
 
@@ -503,7 +541,7 @@ class Simulation:
                 arr(g.len[2]) if self.dims == 3 else None, faces), "block_set_geometry")
             for f in range(nfaces):
                 bc = b.bcList.get(_abi.FACE_NAMES[f]) or WallBC_WithSlip()
-                p = bc.params()
+                p = bc.params_for(g, f) if hasattr(bc, "params_for") else bc.params()
                 pa = (C.c_double * max(1, len(p)))(*p)
                 if isinstance(bc, ExchangeBC_FullFace):
                     lib.check(lib.block_set_bc(h, b.id, f, bc.kind, pa, 0, bc.otherBlock, bc.otherFace,
@@ -516,6 +554,14 @@ class Simulation:
             m = np.ascontiguousarray(bc.cell_map, dtype=np.int32)
             lib.check(lib.block_set_face_map(h, blk.id, f, m.ctypes.data_as(C.POINTER(C.c_int)), m.size // 3), "block_set_face_map")
         local_ids = {b.id for b in local}
+        # a wall without ghost-cell data anywhere in the job moves every block to the kernel that knows the one-sided
+        # stencils: every process has to hear of it, whoever owns the block
+        for b in self.blocks:
+            if b.id in local_ids:
+                continue
+            for f in range(nfaces):
+                if isinstance(b.bcList.get(_abi.FACE_NAMES[f]), WallBC_WithSlip1):
+                    lib.check(lib.block_set_bc(h, b.id, f, _abi.BC_WALL_WITH_SLIP1, (C.c_double * 1)(), 0, -1, -1, 0), "block_set_bc")
         for b in self.blocks:
             if b.id not in needed:
                 continue

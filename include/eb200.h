@@ -119,7 +119,19 @@ enum eb200_bc_kind {
     EB200_BC_OUTFLOW_FIXED_P = 5,
     /* OutFlowBC_FixedPT (bc.lua:1649-1670), GhostCellFixedPT (fixed_pt.d): also T = T_outside;
      * params = { p_outside, T_outside } */
-    EB200_BC_OUTFLOW_FIXED_PT = 6
+    EB200_BC_OUTFLOW_FIXED_PT = 6,
+    /* WallBC_WithSlip1 (bc.lua:783-806): ghost_cell_data_available = false, no ghost-cell effect.  The wall face has
+     * no left (or right) cells and takes compute_flux_at_left_wall / _right_wall (fluxcalc.d:41-51, 187-385); it and
+     * the next face in are reconstructed from the one-sided stencils l0r2 / l2r0 and l1r2 / l2r1
+     * (onedinterp.d:117-273, 386-485, 991-1838).  Not combined with the adaptive flux calculators on this path. */
+    EB200_BC_WALL_WITH_SLIP1 = 7,
+    /* UserDefinedBC (bc.lua) whose ghostCells() function does not depend on time or on the flow
+     * (bc/user_defined_effects.d:237-310 evaluates it at the ghost-cell centres every stage and gets the same
+     * FlowStates every time): the caller evaluates it once.  params = one FlowState (nprim doubles, the order of
+     * upload_flow) per ghost cell, nparams = 2 * n1 * n2 * nprim with the ghost cell of layer l (0 = next to the
+     * face) behind the face cell (a1, a2) at ((a2 * n1 + a1) * 2 + l) * nprim; a1 runs along direction (d + 1) % 3,
+     * a2 along (d + 2) % 3, d = direction of the face normal (0 = i). */
+    EB200_BC_GHOST_PROFILE = 8
 };
 
 /* Order of the primitive (FlowState) variables in upload/download and in the

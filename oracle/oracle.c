@@ -66,6 +66,7 @@ typedef struct {
     int* map;                /* orc_block_set_face_map: (i,j,k) of the source cell of every ghost cell, or NULL */
     FS fstate;               /* for FlowStateCopy */
     double p_outside, T_outside;   /* FixedP / FixedPT */
+    double* profile;         /* EB200_BC_GHOST_PROFILE: one FlowState (nprim doubles) per ghost cell of the face */
 } BC;
 
 typedef struct {
@@ -499,6 +500,7 @@ typedef struct {
     double aL0, aR0, lenL0_, lenR0_;
     double two_over_lenL0_plus_lenL1, two_over_lenR0_plus_lenL0, two_over_lenR1_plus_lenR0;
     double two_lenL0_plus_lenL1, two_lenR0_plus_lenR1;
+    double w0, w1;                 /* linear interpolation / extrapolation weights of the one-sided stencils */
 } L2R2;
 
 /* onedinterp.d:338-354 l2r2_prepare */
@@ -544,19 +546,115 @@ static void interp_l2r2_scalar(const Sim* s, const L2R2* w, double qL1, double q
     }
 }
 
-/* onedinterp.d:117-123,240-262 interp() general symmetric branch + :751-988 interp_l2r2,
- * thermo_interpolator = rhou.  cells[] = {L1, L0, R0, R1} flow states (copies).
+/* One-sided stencils next to a boundary without ghost-cell data (WallBC_WithSlip1, bc.lua:783-806):
+ * onedinterp.d:386-454 l2r1 / l1r2 scalars, :456-485 linear extrapolation weights and weight_scalar. */
+enum { ST_L2R2 = 0, ST_L2R1 = 1, ST_L1R2 = 2, ST_L2R0 = 3, ST_L0R2 = 4 };
+
+/* onedinterp.d:386-396 l2r1_prepare, :421-431 l1r2_prepare (both end with linear_interp_prepare(lenL0, lenR0), :467-475),
+ * :458-465 linear_extrap_prepare */
+static void stencil_prepare(L2R2* w, int mode, const double len[4])
+{
+    const double lenL1 = len[0], lenL0 = len[1], lenR0 = len[2], lenR1 = len[3];
+    if (mode == ST_L2R2) { l2r2_prepare(w, lenL1, lenL0, lenR0, lenR1); return; }
+    if (mode == ST_L2R1) {
+        w->lenL0_ = lenL0; w->lenR0_ = lenR0;
+        w->aL0 = 0.5 * lenL0 / (lenL1 + 2.0 * lenL0 + lenR0);
+        w->two_over_lenL0_plus_lenL1 = 2.0 / (lenL0 + lenL1);
+        w->two_over_lenR0_plus_lenL0 = 2.0 / (lenR0 + lenL0);
+        w->two_lenL0_plus_lenL1 = (2.0 * lenL0 + lenL1);
+        w->w0 = lenR0 / (lenL0 + lenR0); w->w1 = lenL0 / (lenL0 + lenR0);
+    } else if (mode == ST_L1R2) {
+        w->lenL0_ = lenL0; w->lenR0_ = lenR0;
+        w->aR0 = 0.5 * lenR0 / (lenL0 + 2.0 * lenR0 + lenR1);
+        w->two_over_lenR0_plus_lenL0 = 2.0 / (lenR0 + lenL0);
+        w->two_over_lenR1_plus_lenR0 = 2.0 / (lenR1 + lenR0);
+        w->two_lenR0_plus_lenR1 = (2.0 * lenR0 + lenR1);
+        w->w0 = lenR0 / (lenL0 + lenR0); w->w1 = lenL0 / (lenL0 + lenR0);
+    } else if (mode == ST_L2R0) {        /* linear_extrap_prepare(cL0Length, cL1Length), :1463 */
+        w->w0 = (2.0 * lenL0 + lenL1) / (lenL0 + lenL1); w->w1 = -lenL0 / (lenL0 + lenL1);
+    } else {                             /* linear_extrap_prepare(cR0Length, cR1Length), :1661 */
+        w->w0 = (2.0 * lenR0 + lenR1) / (lenR0 + lenR1); w->w1 = -lenR0 / (lenR0 + lenR1);
+    }
+}
+
+/* onedinterp.d:477-485 weight_scalar */
+static double weight_scalar(const Sim* s, const L2R2* w, double q0, double q1)
+{
+    double q = q0 * w->w0 + q1 * w->w1;
+    if (s->cfg.extrema_clipping) q = clip_to_limits(q, q0, q1);
+    return q;
+}
+
+/* one variable on the stencil `mode`; a side the stencil does not produce keeps its value */
+static void interp_scalar_mode(const Sim* s, const L2R2* w, int mode, double qL1, double qL0, double qR0, double qR1,
+                               double* qL, double* qR, double beta)
+{
+    const double eps = s->cfg.epsilon_van_albada;
+    switch (mode) {
+    case ST_L2R2: interp_l2r2_scalar(s, w, qL1, qL0, qR0, qR1, qL, qR, beta); break;
+    case ST_L2R1: {                      /* :398-419 interp_l2r1_scalar */
+        double delLminus = (qL0 - qL1) * w->two_over_lenL0_plus_lenL1;
+        double del = (qR0 - qL0) * w->two_over_lenR0_plus_lenL0;
+        double sL = 1.0;
+        if (s->cfg.apply_limiter)
+            sL = (delLminus * del + fabs(delLminus * del) + eps) / (delLminus * delLminus + del * del + eps);
+        *qL = qL0 + beta * sL * w->aL0 * (del * w->two_lenL0_plus_lenL1 + delLminus * w->lenR0_);
+        if (s->cfg.apply_limiter && (delLminus * del < 0.0)) *qR = qR0;
+        else *qR = weight_scalar(s, w, qL0, qR0);
+        if (s->cfg.extrema_clipping) *qL = clip_to_limits(*qL, qL0, qR0);
+        break; }
+    case ST_L1R2: {                      /* :434-454 interp_l1r2_scalar */
+        double del = (qR0 - qL0) * w->two_over_lenR0_plus_lenL0;
+        double delRplus = (qR1 - qR0) * w->two_over_lenR1_plus_lenR0;
+        double sR = 1.0;
+        if (s->cfg.apply_limiter)
+            sR = (del * delRplus + fabs(del * delRplus) + eps) / (del * del + delRplus * delRplus + eps);
+        *qR = qR0 - beta * sR * w->aR0 * (delRplus * w->lenL0_ + del * w->two_lenR0_plus_lenR1);
+        if (s->cfg.apply_limiter && (delRplus * del < 0.0)) *qL = qL0;
+        else *qL = weight_scalar(s, w, qL0, qR0);
+        if (s->cfg.extrema_clipping) *qR = clip_to_limits(*qR, qL0, qR0);
+        break; }
+    case ST_L2R0: *qL = weight_scalar(s, w, qL0, qL1); break;      /* :1464-1466 */
+    default: *qR = weight_scalar(s, w, qR0, qR1); break;           /* :1662-1664 */
+    }
+}
+
+/* onedinterp.d:117-273 interp(): the stencil by the number of cells the face has on each side
+ * (nL, nR = 0, 1 or 2 with two ghost layers), in the order of the reference's if-chain.  -1: no suitable stencil. */
+static int stencil_mode(int nL, int nR)
+{
+    if (nL == 0 && nR >= 2) return ST_L0R2;
+    if (nL == 1 && nR >= 2) return ST_L1R2;
+    if (nL >= 2 && nR == 1) return ST_L2R1;
+    if (nL >= 2 && nR == 0) return ST_L2R0;
+    if (nL >= 2 && nR >= 2) return ST_L2R2;
+    return -1;
+}
+
+/* onedinterp.d:117-123,240-262 interp() + :751-988 interp_l2r2 (and its one-sided siblings :991-1838, which differ
+ * in the scalar function and in which cells and sides they touch).  cells[] = {L1, L0, R0, R1} flow states
+ * (copies; a cell the stencil does not have is not read -- for ST_L2R0 cells[2] must hold a copy of L0 and for
+ * ST_L0R2 cells[1] a copy of R0, the reference's choice of cL0 / cR0 at :120-121).
  * Returns 0, or -1 when scale_mass_fractions throws (not caught in the reference). */
-static int interp_l2r2(const Sim* s, FS cells[4], const double len[4], const FaceGeo* g, FS* Lft, FS* Rght)
+static int interp_stencil(const Sim* s, int mode, FS cells[4], const double len[4], const FaceGeo* g, FS* Lft, FS* Rght)
 {
     const double beta = 1.0; /* apply_heuristic_pressure_based_limiting is off */
     FS *cL1 = &cells[0], *cL0 = &cells[1], *cR0 = &cells[2], *cR1 = &cells[3];
+    const int hasL1 = (mode == ST_L2R2 || mode == ST_L2R1 || mode == ST_L2R0);
+    const int hasL0 = (mode != ST_L0R2), hasR0 = (mode != ST_L2R0);
+    const int hasR1 = (mode == ST_L2R2 || mode == ST_L1R2 || mode == ST_L0R2);
+    const int doL = (mode != ST_L0R2), doR = (mode != ST_L2R0);
     *Lft = *cL0; *Rght = *cR0;                        /* :120-123 */
+    /* l2r0 / l0r2 with extrema clipping: "Let the copy, made by the caller, stand." (:1451-1456, :1649-1654) */
+    if ((mode == ST_L2R0 || mode == ST_L0R2) && s->cfg.extrema_clipping) return 0;
     if (s->cfg.interpolate_in_local_frame) {          /* :761-770 */
-        to_local(&cL1->vx, &cL1->vy, &cL1->vz, g); to_local(&cL0->vx, &cL0->vy, &cL0->vz, g);
-        to_local(&cR0->vx, &cR0->vy, &cR0->vz, g); to_local(&cR1->vx, &cR1->vy, &cR1->vz, g);
+        if (hasL1) to_local(&cL1->vx, &cL1->vy, &cL1->vz, g);
+        if (hasL0) to_local(&cL0->vx, &cL0->vy, &cL0->vz, g);
+        if (hasR0) to_local(&cR0->vx, &cR0->vy, &cR0->vz, g);
+        if (hasR1) to_local(&cR1->vx, &cR1->vy, &cR1->vz, g);
     }
-    L2R2 w; l2r2_prepare(&w, len[0], len[1], len[2], len[3]);
+    L2R2 w; stencil_prepare(&w, mode, len);
+#define interp_l2r2_scalar(s_, w_, a_, b_, c_, d_, ql_, qr_, beta_) interp_scalar_mode(s_, w_, mode, a_, b_, c_, d_, ql_, qr_, beta_)
     interp_l2r2_scalar(s, &w, cL1->vx, cL0->vx, cR0->vx, cR1->vx, &Lft->vx, &Rght->vx, beta);
     interp_l2r2_scalar(s, &w, cL1->vy, cL0->vy, cR0->vy, cR1->vy, &Lft->vy, &Rght->vy, beta);
     interp_l2r2_scalar(s, &w, cL1->vz, cL0->vz, cR0->vz, cR1->vz, &Lft->vz, &Rght->vz, beta);
@@ -570,54 +668,64 @@ static int interp_l2r2(const Sim* s, FS cells[4], const double len[4], const Fac
     if (ti == EB200_INTERP_PT) {                      /* case InterpolateOption.pt :820-850 */
         interp_l2r2_scalar(s, &w, cL1->gas.p, cL0->gas.p, cR0->gas.p, cR1->gas.p, &Lft->gas.p, &Rght->gas.p, beta);
         interp_l2r2_scalar(s, &w, cL1->gas.T, cL0->gas.T, cR0->gas.T, cR1->gas.T, &Lft->gas.T, &Rght->gas.T, beta);
-        if (gas_update_thermo_from_pT(s, &Lft->gas)) *Lft = *cL0;
-        if (gas_update_thermo_from_pT(s, &Rght->gas)) *Rght = *cR0;
+        if (doL && gas_update_thermo_from_pT(s, &Lft->gas)) *Lft = *cL0;
+        if (doR && gas_update_thermo_from_pT(s, &Rght->gas)) *Rght = *cR0;
         if (nsp > 1) {
             for (int i = 0; i < nsp; ++i) {
-                Lft->gas.massf[i] = Lft->gas.rho_s[i] / Lft->gas.rho;
-                Rght->gas.massf[i] = Rght->gas.rho_s[i] / Rght->gas.rho;
+                if (doL) Lft->gas.massf[i] = Lft->gas.rho_s[i] / Lft->gas.rho;
+                if (doR) Rght->gas.massf[i] = Rght->gas.rho_s[i] / Rght->gas.rho;
             }
-            if (scale_mass_fractions(nsp, Lft->gas.massf)) return -1;
-            if (scale_mass_fractions(nsp, Rght->gas.massf)) return -1;
-        } else { Lft->gas.massf[0] = 1.0; Rght->gas.massf[0] = 1.0; }
+            if (doL && scale_mass_fractions(nsp, Lft->gas.massf)) return -1;
+            if (doR && scale_mass_fractions(nsp, Rght->gas.massf)) return -1;
+        } else { if (doL) Lft->gas.massf[0] = 1.0; if (doR) Rght->gas.massf[0] = 1.0; }
         goto back_to_global;
     }
     /* cases rhou :854-896, rhop :896-940, rhot :940-978 share the density part */
     if (nsp > 1) {
         double rho_L = 0.0, rho_R = 0.0;
         for (int i = 0; i < nsp; ++i) { rho_L += Lft->gas.rho_s[i]; rho_R += Rght->gas.rho_s[i]; }
-        Lft->gas.rho = rho_L; Rght->gas.rho = rho_R;
+        if (doL) Lft->gas.rho = rho_L;
+        if (doR) Rght->gas.rho = rho_R;
         for (int i = 0; i < nsp; ++i) {
-            Lft->gas.massf[i] = Lft->gas.rho_s[i] / Lft->gas.rho;
-            Rght->gas.massf[i] = Rght->gas.rho_s[i] / Rght->gas.rho;
+            if (doL) Lft->gas.massf[i] = Lft->gas.rho_s[i] / Lft->gas.rho;
+            if (doR) Rght->gas.massf[i] = Rght->gas.rho_s[i] / Rght->gas.rho;
         }
         /* scale_species_after_reconstruction (default true) */
-        if (scale_mass_fractions(nsp, Lft->gas.massf)) return -1;
-        if (scale_mass_fractions(nsp, Rght->gas.massf)) return -1;
+        if (doL && scale_mass_fractions(nsp, Lft->gas.massf)) return -1;
+        if (doR && scale_mass_fractions(nsp, Rght->gas.massf)) return -1;
     } else {
         interp_l2r2_scalar(s, &w, cL1->gas.rho, cL0->gas.rho, cR0->gas.rho, cR1->gas.rho, &Lft->gas.rho, &Rght->gas.rho, beta);
     }
     if (ti == EB200_INTERP_RHOP) {
         interp_l2r2_scalar(s, &w, cL1->gas.p, cL0->gas.p, cR0->gas.p, cR1->gas.p, &Lft->gas.p, &Rght->gas.p, beta);
-        if (gas_update_thermo_from_rhop(s, &Lft->gas)) *Lft = *cL0;
-        if (gas_update_thermo_from_rhop(s, &Rght->gas)) *Rght = *cR0;
+        if (doL && gas_update_thermo_from_rhop(s, &Lft->gas)) *Lft = *cL0;
+        if (doR && gas_update_thermo_from_rhop(s, &Rght->gas)) *Rght = *cR0;
     } else if (ti == EB200_INTERP_RHOT) {
         interp_l2r2_scalar(s, &w, cL1->gas.T, cL0->gas.T, cR0->gas.T, cR1->gas.T, &Lft->gas.T, &Rght->gas.T, beta);
-        if (gas_update_thermo_from_rhoT(s, &Lft->gas)) *Lft = *cL0;
-        if (gas_update_thermo_from_rhoT(s, &Rght->gas)) *Rght = *cR0;
+        if (doL && gas_update_thermo_from_rhoT(s, &Lft->gas)) *Lft = *cL0;
+        if (doR && gas_update_thermo_from_rhoT(s, &Rght->gas)) *Rght = *cR0;
     } else {
         interp_l2r2_scalar(s, &w, cL1->gas.u, cL0->gas.u, cR0->gas.u, cR1->gas.u, &Lft->gas.u, &Rght->gas.u, beta);
         /* mixin(codeForThermoUpdateBoth("rhou")) :45-74: on exception copy the whole cell state */
-        if (gas_update_thermo_from_rhou(s, &Lft->gas)) *Lft = *cL0;
-        if (gas_update_thermo_from_rhou(s, &Rght->gas)) *Rght = *cR0;
+        if (doL && gas_update_thermo_from_rhou(s, &Lft->gas)) *Lft = *cL0;
+        if (doR && gas_update_thermo_from_rhou(s, &Rght->gas)) *Rght = *cR0;
     }
 back_to_global:
+#undef interp_l2r2_scalar
     if (s->cfg.interpolate_in_local_frame) {          /* :979-987 */
-        to_global(&Lft->vx, &Lft->vy, &Lft->vz, g); to_global(&Rght->vx, &Rght->vy, &Rght->vz, g);
-        to_global(&cL1->vx, &cL1->vy, &cL1->vz, g); to_global(&cL0->vx, &cL0->vy, &cL0->vz, g);
-        to_global(&cR0->vx, &cR0->vy, &cR0->vz, g); to_global(&cR1->vx, &cR1->vy, &cR1->vz, g);
+        if (doL) to_global(&Lft->vx, &Lft->vy, &Lft->vz, g);
+        if (doR) to_global(&Rght->vx, &Rght->vy, &Rght->vz, g);
+        if (hasL1) to_global(&cL1->vx, &cL1->vy, &cL1->vz, g);
+        if (hasL0) to_global(&cL0->vx, &cL0->vy, &cL0->vz, g);
+        if (hasR0) to_global(&cR0->vx, &cR0->vy, &cR0->vz, g);
+        if (hasR1) to_global(&cR1->vx, &cR1->vy, &cR1->vz, g);
     }
     return 0;
+}
+
+static int interp_l2r2(const Sim* s, FS cells[4], const double len[4], const FaceGeo* g, FS* Lft, FS* Rght)
+{
+    return interp_stencil(s, ST_L2R2, cells, len, g, Lft, Rght);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1200,6 +1308,64 @@ static void compute_outflow_flux(const Sim* s, const FS* fs, int outsign, const 
     }
 }
 
+/* fluxcalc.d:187-286 compute_flux_at_left_wall (side = 0: the gas is on the right of the face) and :289-385
+ * compute_flux_at_right_wall (side = 1: the gas is on the left), gvel = 0: the pressure behind the wave that brings
+ * the gas to rest at the wall (isentropic, or a shock when pstar > 1.1 p).  F is ASSIGNED, in the reference too. */
+#define EB_MIN_PRESSURE 0.1      /* flowstate_limits.min_pressure, globalconfig.d:85 (not a config field of this path) */
+static void compute_flux_at_wall(const Sim* s, FS* fs, int side, const FaceGeo* g, double* F)
+{
+    double gvx = 0.0, gvy = 0.0, gvz = 0.0;
+    to_local(&gvx, &gvy, &gvz, g);
+    to_local(&fs->vx, &fs->vy, &fs->vz, g);
+    const double vstar = gvx;
+    const double a = fs->gas.a, v = fs->vx;
+    const double gm = gas_gamma(s, &fs->gas);
+    const double rho = fs->gas.rho, p = fs->gas.p;
+    double tmp;
+    if (side == 0) {
+        const double Jminus = v - 2.0 * a / (gm - 1.0);
+        tmp = (vstar - Jminus) * (gm - 1.0) / (2.0 * sqrt(gm)) * sqrt(rho / pow(p, 1.0 / gm));
+    } else {
+        const double Jplus = v + 2.0 * a / (gm - 1.0);
+        tmp = (Jplus - vstar) * (gm - 1.0) / (2.0 * sqrt(gm)) * sqrt(rho / pow(p, 1.0 / gm));
+    }
+    const double ptiny = EB_MIN_PRESSURE;
+    double pstar = (tmp > 0.0) ? pow(tmp, 2.0 * gm / (gm - 1.0)) : ptiny;
+    if (pstar > 1.1 * p) {
+        int count = 0;
+        double incr_pstar;
+        do {
+            double fv[2];
+            const double dp = 0.001 * pstar;
+            for (int n = 0; n < 2; ++n) {
+                const double ps = (n == 0) ? pstar : pstar + dp;
+                const double xi = ps / p;
+                const double M1sq = 1.0 + (gm + 1.0) / 2.0 / gm * (xi - 1.0);
+                const double v1 = sqrt(M1sq) * a;
+                const double v2 = v1 * ((gm - 1.0) * M1sq + 2.0) / ((gm + 1.0) * M1sq);
+                fv[n] = (side == 0) ? (vstar - v1 + v2 - v) : (vstar + v1 - v2 - v);
+            }
+            incr_pstar = -fv[0] * dp / (fv[1] - fv[0]);
+            pstar += incr_pstar;
+            count += 1;
+        } while (fabs(incr_pstar) / pstar > 0.01 && count < 10);
+    }
+    pstar = fmin(pstar, p * 10.0);
+    F[s->iMass] = 0.0;
+    F[s->iXMom] = pstar;
+    F[s->iYMom] = 0.0;
+    if (s->threeD) F[s->iZMom] = 0.0;
+    F[s->iEnergy] = pstar * vstar;
+    if (s->nsp > 1) for (int i = 0; i < s->nsp; ++i) F[s->iSpecies + i] = 0.0;
+    if (s->threeD) {
+        F[s->iZMom] += gvz * F[s->iMass];
+        to_global(&F[s->iXMom], &F[s->iYMom], &F[s->iZMom], g);
+    } else {
+        double zDummy = 0.0;
+        to_global(&F[s->iXMom], &F[s->iYMom], &zDummy, g);
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* Block-level phases                                                         */
 
@@ -1226,19 +1392,32 @@ static int flux_sweep(const Sim* s, Blk* b, int d)
         double Fl[MAXCQ]; for (int q = 0; q < ncq; ++q) Fl[q] = 0.0;  /* clear_fluxes_of_conserved_quantities */
         FS cells[4], Lft, Rght;
         long cc[4] = { c - 2 * st, c - st, c, c + st };
-        for (int m = 0; m < 4; ++m) load_fs(s, b, cc[m], &cells[m]);
+        /* cells on each side of the face (sfluidblock.d:455-530, 548-611): a boundary without ghost-cell data leaves
+         * its own face with none and the next face in with one */
+        int nL = 2, nR = 2;
+        if (b->bc[lo_face].kind == EB200_BC_WALL_WITH_SLIP1) nL = (idx[d] < 2) ? idx[d] : 2;
+        if (b->bc[hi_face].kind == EB200_BC_WALL_WITH_SLIP1) nR = (n[d] - idx[d] < 2) ? n[d] - idx[d] : 2;
+        const int has[4] = { nL >= 2, nL >= 1, nR >= 1, nR >= 2 };
+        for (int m = 0; m < 4; ++m) if (has[m]) load_fs(s, b, cc[m], &cells[m]);
+        if (!has[1]) cells[1] = cells[2];       /* onedinterp.d:120-121: cL0 = right_cells[0] when there is no left cell */
+        if (!has[2]) cells[2] = cells[1];
         if (s->cfg.interpolation_order > 1) {
-            double len[4];
-            for (int m = 0; m < 4; ++m) len[m] = b->len[d][cc[m]];
-            if (interp_l2r2(s, cells, len, &g, &Lft, &Rght)) { failed = 1; continue; }
+            double len[4] = { 0.0, 0.0, 0.0, 0.0 };
+            for (int m = 0; m < 4; ++m) if (has[m]) len[m] = b->len[d][cc[m]];
+            const int mode = stencil_mode(nL, nR);
+            if (mode < 0) { failed = 1; continue; }
+            if (mode == ST_L2R0) { len[0] = b->len[0][cc[0]]; len[1] = b->len[0][cc[1]]; }   /* :236 passes iLength whatever f.idir is */
+            if (interp_stencil(s, mode, cells, len, &g, &Lft, &Rght)) { failed = 1; continue; }
             if (s->mutate_cell_vel) {
-                for (int m = 0; m < 4; ++m) { PR(s, b, 5)[cc[m]] = cells[m].vx; PR(s, b, 6)[cc[m]] = cells[m].vy; PR(s, b, 7)[cc[m]] = cells[m].vz; }
+                for (int m = 0; m < 4; ++m) if (has[m]) { PR(s, b, 5)[cc[m]] = cells[m].vx; PR(s, b, 6)[cc[m]] = cells[m].vy; PR(s, b, 7)[cc[m]] = cells[m].vz; }
             }
         } else {
             Lft = cells[1]; Rght = cells[2];
         }
         int bcf = on_lo ? lo_face : (on_hi ? hi_face : -1);
-        if (bcf >= 0 && b->bc[bcf].kind == EB200_BC_OUTFLOW_SIMPLE_FLUX) {
+        if (nL == 0) compute_flux_at_wall(s, &Rght, 0, &g, Fl);               /* fluxcalc.d:41-51 */
+        else if (nR == 0) compute_flux_at_wall(s, &Lft, 1, &g, Fl);
+        else if (bcf >= 0 && b->bc[bcf].kind == EB200_BC_OUTFLOW_SIMPLE_FLUX) {
             /* convective_flux_computed_in_bc: phase0 skips, applyPostConvFluxAction fills */
             int outsign = on_hi ? 1 : -1;
             FS inner; load_fs(s, b, on_hi ? c - st : c, &inner);
@@ -1261,6 +1440,8 @@ static void reflect_normal_velocity(FS* fs, const FaceGeo* g)
 
 /* applyPreReconAction for the physical boundaries of one block:
  * internal_copy_then_reflect.d:111-134, flow_state_copy.d:92-107, extrapolate_copy.d:124-145 */
+static void fs_from_params(const Sim* s, const double* p, FS* fs);
+
 static void apply_pre_recon_bcs(const Sim* s, Blk* b)
 {
     int n[3] = { b->nic, b->njc, b->nkc };
@@ -1287,6 +1468,8 @@ static void apply_pre_recon_bcs(const Sim* s, Blk* b)
                     load_fs(s, b, src, &fs); reflect_normal_velocity(&fs, &g); Sval = b->S[src]; break;
                 case EB200_BC_INFLOW_SUPERSONIC:
                     fs = bc->fstate; Sval = 0.0; break;
+                case EB200_BC_GHOST_PROFILE:
+                    fs_from_params(s, bc->profile + (((long)a2 * n[d1] + a1) * NG + layer) * s->nprim, &fs); Sval = 0.0; break;
                 case EB200_BC_OUTFLOW_SIMPLE_EXTRAPOLATE:
                 case EB200_BC_OUTFLOW_SIMPLE_FLUX:
                     load_fs(s, b, hi ? cf - st : cf, &fs); Sval = b->S[hi ? cf - st : cf]; break;
@@ -1623,6 +1806,22 @@ static int check_data(const Sim* s, const FS* fs)
 
 /* shockdetectors.d:22-93 PJ_ShockDetector, two-cell branch (every face on this path has a cell,
  * ghost or interior, on both sides; gvel = 0) */
+/* shockdetectors.d:48-84: a face with a cell on one side only (a wall without ghost-cell data; gvel = 0):
+ * the gas velocity relative to the wall.  side 1: the left cell exists, side 2: the right cell. */
+static double PJ_ShockDetector_wall(const FS* c, int side, const FaceGeo* g, double comp_tol, double shear_tol)
+{
+    double u = c->vx * g->n[0] + c->vy * g->n[1] + c->vz * g->n[2];
+    double a = c->gas.a;
+    double comp = (side == 1) ? ((-u) / a) : (u / a);
+    double v = c->vx * g->t1[0] + c->vy * g->t1[1] + c->vz * g->t1[2];
+    double w = c->vx * g->t2[0] + c->vy * g->t2[1] + c->vz * g->t2[2];
+    double shear_y = fabs(v) / a;
+    double shear_z = fabs(w) / a;
+    double shear = fmax(shear_y, shear_z);
+    if ((shear < shear_tol) && (comp < comp_tol)) return 1.0;
+    return 0.0;
+}
+
 static double PJ_ShockDetector(const FS* cL, const FS* cR, const FaceGeo* g, double comp_tol, double shear_tol)
 {
     double uL = cL->vx * g->n[0] + cL->vy * g->n[1] + cL->vz * g->n[2];
@@ -1656,8 +1855,15 @@ static void detect_shocks_block(const Sim* s, Blk* b)
         for (int kk = 0; kk < ext[2]; ++kk) for (int jj = 0; jj < ext[1]; ++jj) for (int ii = 0; ii < ext[0]; ++ii) {
             long c = cidx(b, ii + off[0], jj + off[1], kk + off[2]);
             FaceGeo g; load_face(b, d, c, &g);
-            FS cL, cR; load_fs(s, b, c - st, &cL); load_fs(s, b, c, &cR);
-            b->Sf[d][c] = PJ_ShockDetector(&cL, &cR, &g, s->cfg.compression_tolerance, s->cfg.shear_tolerance);
+            int idx[3] = { ii, jj, kk };
+            const int noL = (idx[d] == 0) && b->bc[2 * d].kind == EB200_BC_WALL_WITH_SLIP1;
+            const int noR = (idx[d] == n[d]) && b->bc[2 * d + 1].kind == EB200_BC_WALL_WITH_SLIP1;
+            FS cL, cR;
+            if (!noL) load_fs(s, b, c - st, &cL);
+            if (!noR) load_fs(s, b, c, &cR);
+            if (noL) b->Sf[d][c] = PJ_ShockDetector_wall(&cR, 2, &g, s->cfg.compression_tolerance, s->cfg.shear_tolerance);
+            else if (noR) b->Sf[d][c] = PJ_ShockDetector_wall(&cL, 1, &g, s->cfg.compression_tolerance, s->cfg.shear_tolerance);
+            else b->Sf[d][c] = PJ_ShockDetector(&cL, &cR, &g, s->cfg.compression_tolerance, s->cfg.shear_tolerance);
         }
     }
     for (int k = b->kg; k < b->kg + b->nkc; ++k) for (int j = NG; j < NG + b->njc; ++j) for (int i = NG; i < NG + b->nic; ++i) {
@@ -1675,9 +1881,12 @@ static void detect_shocks_block(const Sim* s, Blk* b)
             long st = b->stride[d];
             for (int kk = 0; kk < ext[2]; ++kk) for (int jj = 0; jj < ext[1]; ++jj) for (int ii = 0; ii < ext[0]; ++ii) {
                 long c = cidx(b, ii + off[0], jj + off[1], kk + off[2]);
+                int idx[3] = { ii, jj, kk };
+                const int noL = (idx[d] == 0) && b->bc[2 * d].kind == EB200_BC_WALL_WITH_SLIP1;      /* fluidblock.d:593-604: */
+                const int noR = (idx[d] == n[d]) && b->bc[2 * d + 1].kind == EB200_BC_WALL_WITH_SLIP1;  /* only cells that exist */
                 if (b->Sf[d][c] > 0.0) { b->Sf[d][c] = 1.0; continue; }
-                if (b->S[c - st] > 0.0) { b->Sf[d][c] = 1.0; continue; }
-                if (b->S[c] > 0.0) { b->Sf[d][c] = 1.0; continue; }
+                if (!noL && b->S[c - st] > 0.0) { b->Sf[d][c] = 1.0; continue; }
+                if (!noR && b->S[c] > 0.0) { b->Sf[d][c] = 1.0; continue; }
             }
         }
     }
@@ -1831,7 +2040,9 @@ static void free_blk(Blk* b)
     free(b->vol); free(b->areaxy); for (int d = 0; d < 3; ++d) { free(b->len[d]); free(b->fgeo[d]); free(b->F[d]); }
     free(b->prim); for (int l = 0; l <= MAXLEVELS; ++l) free(b->U[l]);
     for (int l = 0; l < MAXLEVELS; ++l) free(b->dUdt[l]);
-    free(b->bad); free(b->S); for (int d = 0; d < 3; ++d) free(b->Sf[d]); free(b);
+    free(b->bad); free(b->S); for (int d = 0; d < 3; ++d) free(b->Sf[d]);
+    for (int f = 0; f < 6; ++f) free(b->bc[f].profile);
+    free(b);
 }
 
 int orc_finalize(int sim)
@@ -1928,6 +2139,15 @@ int orc_block_set_bc(int sim, int blk_id, int face, int kind, const double* para
         const int need = (kind == EB200_BC_OUTFLOW_FIXED_P) ? 1 : 2;
         if (nparams != need || !params) { set_err("bc kind %d needs %d parameter(s)", kind, need); return -1; }
         bc->p_outside = params[0]; bc->T_outside = (need == 2) ? params[1] : 0.0;
+    }
+    if (kind == EB200_BC_GHOST_PROFILE) {
+        const int d = face / 2;
+        const int nn[3] = { b->nic, b->njc, b->nkc };
+        const long need = (long)NG * nn[(d + 1) % 3] * nn[(d + 2) % 3] * s->nprim;
+        if (nparams != need || !params) { set_err("ghost profile of block %d face %d needs %ld values", blk_id, face, need); return -1; }
+        free(bc->profile);
+        bc->profile = (double*)malloc(sizeof(double) * need);
+        memcpy(bc->profile, params, sizeof(double) * need);
     }
     if (kind == EB200_BC_EXCHANGE_FULL_FACE && s->threeD && orientation != 0) { set_err("only orientation 0 supported in 3D"); return -1; }
     return 0;

@@ -210,3 +210,19 @@ def test_step_status_is_decided_collectively():
     sim.reduce_step_status = lambda rc: -2
     with pytest.raises(RuntimeError, match="another rank"):
         sim.gasdynamic_step()
+
+
+def test_wall_without_ghost_cells_in_the_job_file():
+    """bc.lua:783-806 writes WallBC_WithSlip1 as type wall_with_slip with ghost_cell_data_available = false and no
+    effects; the job reader maps that (and only that) to the one-sided path."""
+    from gdtk_b200 import job
+    from gdtk_b200.sim import WallBC_WithSlip, WallBC_WithSlip1
+    j = job._bc_to_json(WallBC_WithSlip1(), 1)
+    assert j["type"] == "wall_with_slip" and j["ghost_cell_data_available"] is False and j["pre_recon_action"] == []
+    assert isinstance(job._bc_from_json(None, "north", j), WallBC_WithSlip1)
+    j2 = job._bc_to_json(WallBC_WithSlip(), 1)
+    assert j2["ghost_cell_data_available"] is True
+    assert type(job._bc_from_json(None, "north", j2)) is WallBC_WithSlip
+    j["pre_recon_action"] = [{"type": "internal_copy_then_reflect"}]
+    with pytest.raises(ValueError):
+        job._bc_from_json(None, "north", j)

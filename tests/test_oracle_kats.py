@@ -8,6 +8,10 @@ CPU oracle.  fluxcalc.d / onedinterp.d / fvcell.d have no function-level vectors
    (833 +- 3 steps to 5 ms; free-stream probe; cone-surface pressure 95.84e3 + 0.387 q_inf +- 1 kPa).
    Run here with flux_calculator='ausmdv' and a Coons patch for the second block (see
    gdtk_b200/cases.py), hence the slightly wider step-count window.
+ * supersonic vortex: examples/eilmer/2D/vortex-supersonic/vtx-test.rb:33,50,65 (2761 +- 3 steps to 20 ms; L2 error
+   norms against the exact vortex: p 800 +- 100 Pa, T 0.405 +- 0.10 K).  The job's walls are WallBC_WithSlip1 (no
+   ghost cells): this is the known answer behind the one-sided stencils of onedinterp.d:386-485 and the wall fluxes
+   of fluxcalc.d:187-385.
 """
 import math
 
@@ -290,4 +294,50 @@ def test_hll_family_consistency_and_sod(oracle, flux):
     v = probe(sim, blocks, 0.78, 0.025)
     for k, r in {"rho": 0.2647, "p": 30.2e3, "T": 398.0, "velx": 293.0}.items():
         assert abs(v[k] - r) / r < 2.0e-2, (k, v[k], r)
+    sim.close()
+
+
+def test_supersonic_vortex_with_walls_without_ghost_cells(oracle):
+    """vtx-test.rb: step count and the volume-weighted L2 norms of flowsolution.d:306-346 against udf-vortex-flow.lua's
+    refSoln (the same function that fills the ghost cells of the inflow plane)."""
+    cfg, gm, blocks = cases.vortex()
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    steps = sim.run()
+    assert abs(steps - 2761) < 3
+    exact = cases.vortex_flow(gm)
+    sum_p = sum_T = vol = 0.0
+    for b in blocks:
+        g = b.geom
+        P = sim.download_flow(b.id)
+        p, T = sim.interior(b.id, P[2]), sim.interior(b.id, P[3])
+        V, X, Y = (sim.interior(b.id, a) for a in (g.vol, g.pos[0], g.pos[1]))
+        for idx in np.ndindex(p.shape):
+            e = exact(X[idx], Y[idx])
+            sum_p += V[idx] * (p[idx] - e.gas.p) ** 2
+            sum_T += V[idx] * (T[idx] - e.gas.T) ** 2
+            vol += V[idx]
+    L2p, L2T = math.sqrt(sum_p / vol), math.sqrt(sum_T / vol)
+    print(f"vortex: {steps} steps, L2(p) = {L2p:.1f} Pa, L2(T) = {L2T:.4f} K  (vtx-test.rb: 2761, 800, 0.405)")
+    assert abs(L2p - 800.0) < 100.0
+    assert abs(L2T - 0.405) < 0.10
+    sim.close()
+
+
+def test_one_sided_stencils_reduce_to_the_symmetric_one_on_linear_data(oracle):
+    """On a linear profile with uniform cells every stencil of onedinterp.d:117-273 that interpolates (l2r2, l2r1, l1r2)
+    returns the face value exactly on the side it reconstructs with the limited parabola; the walls' own faces keep
+    the cell value when extrema clipping is on (:1451-1456).  Run as a job: a uniform stream along a straight channel
+    with WallBC_WithSlip1 walls stays uniform to rounding (the wall flux returns p* = p for zero normal velocity up
+    to pow's last place)."""
+    from gdtk_b200.sim import WallBC_WithSlip1
+    cfg, gm, blocks = cases.box3d(n=8, nb=1, wall_bc=WallBC_WithSlip1, perturb=False)
+    sim = Simulation(cfg, gm, blocks, lib=oracle)
+    sim.run(max_step=5)
+    for b in blocks:
+        P = sim.download_flow(b.id)
+        for v, name in ((0, "rho"), (2, "p"), (5, "velx")):
+            a = sim.interior(b.id, P[v])
+            assert np.max(np.abs(a - a.flat[0])) <= 1.0e-12 * abs(a.flat[0]), name
+        for v in (6, 7):
+            assert np.max(np.abs(sim.interior(b.id, P[v]))) < 1.0e-9
     sim.close()
