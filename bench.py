@@ -242,7 +242,7 @@ def run_gpu_workload(args, spec, rank, world, local_rank, with_e2e=False, with_r
                 "note": "instructions per cell from the ncu capture in profiles/ (DFMA+DMUL+DADD+DSETP); peak measured with profiles/micro/fp64_peak.cu"}
     result = {
         "name": name, "value": value, "ms": ms, "steps": steps, "ncells": ncells, "dt": dt, "launches": launches,
-        "setup_s": t_setup, "clocks": clocks,
+        "setup_s": t_setup, "clocks": clocks, "halo": getattr(sim, "halo_transport", None),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
                      "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per cell (256^3 capture, profiles/r2_traffic.json) x cells per launch; "
@@ -336,11 +336,13 @@ def run_e2e(args, sim, dt, ncells, world):
             raise RuntimeError(f"e2e step returned {rc}: {lib.error()}")
         for bid, (_, _, _, _, down_ptrs, ndown) in host.items():
             if short:
-                lib.check(lib.download_conserved(h, bid, down_ptrs, ndown), "download_conserved")
+                # asynchronous: these device -> host copies run beside the next step's host -> device copies
+                lib.check(lib.download_conserved_async(h, bid, down_ptrs, ndown), "download_conserved_async")
             else:
                 lib.check(lib.download_flow(h, bid, down_ptrs, ndown), "download_flow")
 
     one_step()          # warm
+    lib.check(lib.wait_downloads(h), "wait_downloads")
     torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
@@ -348,6 +350,7 @@ def run_e2e(args, sim, dt, ncells, world):
     t0 = time.perf_counter()
     for _ in range(nsteps):
         one_step()
+    lib.check(lib.wait_downloads(h), "wait_downloads")        # the last step's results are in host memory
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
     if world > 1:
@@ -362,7 +365,7 @@ def run_e2e(args, sim, dt, ncells, world):
         h2d, d2h = int(h2d_t[0]), int(h2d_t[1])
     return {"value": ncells * nsteps / el, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": nsteps,
-            "note": ("eb200_upload_flow (rho, u, velocity) + eb200_step + eb200_download_conserved" if short else
+            "note": ("eb200_upload_flow (rho, u, velocity) + eb200_step + eb200_download_conserved_async (+ eb200_wait_downloads after the last step; the downloads of a step overlap the uploads of the next)" if short else
                      "eb200_upload_flow + eb200_step + eb200_download_flow") + " per step, pinned host buffers (bytes summed over ranks)"}
 
 
@@ -519,7 +522,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "v2"],
                     help="A/B testing: force the generic fused kernel, or the face-centred tuned kernel (v2) where the "
                          "cell-centred one (v3) would run")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=128)
     ap.add_argument("--cpu-nb", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -610,7 +613,8 @@ def main():
             "ms_per_step": main_res["ms"] / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": main_res["name"], "cells": main_res["ncells"], "dt": main_res["dt"],
-                       "parallelism": f"blocks over {world} GPU(s), halo exchange per stage" if world > 1 else "single GPU",
+                       "parallelism": (f"blocks over {world} GPU(s), halo exchange per stage: {main_res.get('halo') or 'exchange callback (NCCL send/recv)'}"
+                                       if world > 1 else "single GPU"),
                        "timed_region": "eb200_run_steps: fixed dt, no host synchronisation between steps; "
                                        "`real_loop` is the same steps with eb200_compute_dt every 10 steps and eb200_step's status read-back",
                        "l2_policy": "state arrays (tens of GB) far exceed the 126 MB L2; no flush needed",

@@ -114,6 +114,8 @@ SIGNATURES = {
     "upload_flow": (C.c_int, [C.c_int, C.c_int, DPP, C.c_int]),
     "download_flow": (C.c_int, [C.c_int, C.c_int, DPP, C.c_int]),
     "download_conserved": (C.c_int, [C.c_int, C.c_int, DPP, C.c_int]),
+    "download_conserved_async": (C.c_int, [C.c_int, C.c_int, DPP, C.c_int]),
+    "wait_downloads": (C.c_int, [C.c_int]),
     "probe_cells": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), DP, C.c_int]),
     "compute_dt": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, DP]),
     "step": (C.c_int, [C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int)]),

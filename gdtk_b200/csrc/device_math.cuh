@@ -838,9 +838,21 @@ __device__ __forceinline__ void flux_ausm_plus_up(const Prim<NSP>& L, const Prim
     }
 }
 
-// fluxcalc.d:1929-2120 (single species; gamma(Q) = Cp/Cv as gas_model.d:205)
+// gamma = Cp / Cv of a state (gas_model.d:205)
+template <int GASM, int NSP>
+__device__ double gas_gamma(const EbGas* __restrict__ g, const Prim<NSP>& Q)
+{
+    if (GASM == EB200_GAS_IDEAL) return g->gamma_CpCv;
+    double Cp = 0.0, Cv = 0.0;
+    double cps[NSP];
+    for (int i = 0; i < NSP; ++i) { cea_Cp(g->curves[i], Q.T, cps[i]); Cp += Q.massf[i] * cps[i]; }
+    for (int i = 0; i < NSP; ++i) Cv += Q.massf[i] * (cps[i] - g->Rsp[i]);
+    return Cp / Cv;
+}
+
+// fluxcalc.d:1929-2120 (gamma(Q) = Cp/Cv as gas_model.d:205; the species terms :2055-2107 when NSP > 1)
 template <int DIM, int NSP>
-__device__ __forceinline__ void flux_roe(const Prim<NSP>& L, const Prim<NSP>& R, double gL, double gR, double* F)
+__device__ __forceinline__ void flux_roe(const EbGas* __restrict__ gas, const Prim<NSP>& L, const Prim<NSP>& R, double gL, double gR, double* F)
 {
     typedef Layout<DIM, NSP> Lay;
     EB_UNPACK_LR
@@ -879,12 +891,37 @@ __device__ __forceinline__ void flux_roe(const Prim<NSP>& L, const Prim<NSP>& R,
         FL = rL * uL * wL; FR = rR * uR * wR;
         F[Lay::iZMom] = 0.5 * (FL + FR - (a0 * (w0 * what + rhat * dw)) - (a1 * w1 * what) - (a2 * w2 * what));
     }
-    const double dtke = 0.0, theta = 0.0;
+    const double dtke = 0.0;
+    double theta = 0.0;
+    if (NSP > 1) {                      // Walters et al. (1992) eq. 33b; internal_energy(Q, isp) = h_i(T) - R_i T (therm_perf_gas.d:443-448)
+        const double That = eb_div((sL * L.T + sR * R.T), sden);
+        const double logTL = log(L.T), logTR = log(R.T);
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) {
+            const double dmassf = R.massf[i] - L.massf[i];
+            double hL, hR;
+            cea_h(gas->curves[i], L.T, logTL, hL); cea_h(gas->curves[i], R.T, logTR, hR);
+            const double eiL = hL - gas->Rsp[i] * L.T;
+            const double eiR = hR - gas->Rsp[i] * R.T;
+            const double eihat = eb_div((sL * eiL + sR * eiR), sden);
+            const double psihat = eb_div(gas->Rsp[i] * That, (ghat - 1.0)) - eihat + kehat;
+            theta += dmassf * psihat;
+        }
+    }
     FL = rL * uL * HL; FR = rR * uR * HR;
     F[Lay::iEnergy] = 0.5 * (FL + FR
                              - (a0 * (w0 * (kehat + tkehat) + rhat * (vhat * dv + what * dw + dtke - theta)))
                              - (a1 * w1 * (Hhat + uhat * ahat))
                              - (a2 * w2 * (Hhat - uhat * ahat)));
+    if (NSP > 1) {                      // :2093-2107
+#pragma unroll
+        for (int i = 0; i < NSP; ++i) {
+            const double massfhat = eb_div((sL * L.massf[i] + sR * R.massf[i]), sden);
+            const double dmassf = R.massf[i] - L.massf[i];
+            FL = rL * uL * L.massf[i]; FR = rR * uR * R.massf[i];
+            F[Lay::iSpecies + i] = 0.5 * (FL + FR - (a0 * (w0 * massfhat + rhat * dmassf)) - (a1 * w1 * massfhat) - (a2 * w2 * massfhat));
+        }
+    }
 }
 
 
@@ -1101,7 +1138,7 @@ __device__ __forceinline__ void basic_flux(const EbParams& P, const EbGas* __res
     else if (BASE == EB200_FLUX_LDFSS0) flux_ldfss<DIM, NSP, 0>(L, R, F);
     else if (BASE == EB200_FLUX_LDFSS2) flux_ldfss<DIM, NSP, 2>(L, R, F);
     else if (BASE == EB200_FLUX_AUSM_PLUS_UP) flux_ausm_plus_up<DIM, NSP>(L, R, P.M_inf, F);
-    else if (BASE == EB200_FLUX_ROE) flux_roe<DIM, NSP>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
+    else if (BASE == EB200_FLUX_ROE) flux_roe<DIM, NSP>(gas, L, R, gas_gamma<GASM, NSP>(gas, L), gas_gamma<GASM, NSP>(gas, R), F);
     else if (BASE == EB200_FLUX_HLLC) flux_hllc<DIM, NSP>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
     else if (BASE == EB200_FLUX_HLLE2) flux_hlle2<DIM, NSP>(L, R, gas->gamma_CpCv, gas->gamma_CpCv, F);
     else flux_efm<DIM, NSP, GASM>(gas, L, R, F);

@@ -53,6 +53,8 @@ struct Block {
     int NI = 0, NJ = 0, NK = 0, kg = 0;
     long long ncp = 0, cell0 = -1, stride[3] = {0, 0, 0};
     int local_index = -1;
+    cudaEvent_t ev_d2h = nullptr;             // last asynchronous download of this block (eb200_download_conserved_async)
+    bool d2h_pending = false;
     bool has_geometry = false, cartesian = false;
     EbBlockDesc cartD;                        // constants of the uniform-Cartesian fast path
     std::vector<double> vol, areaxy, len[3], face[3];
@@ -121,6 +123,9 @@ struct Sim {
     unsigned long long* d_red = nullptr; double* d_last = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;       // halo traffic of other ranks, overlapped with interior tiles
+    cudaStream_t d2h_stream = nullptr;        // asynchronous downloads: device -> host copies run beside the uploads of the next step
+    cudaEvent_t ev_state = nullptr, ev_d2h_all = nullptr;
+    bool d2h_inflight = false;
     cudaStream_t bnd_stream = nullptr;        // boundary tiles: start when the halo is in, run under the interior launch's tail
     cudaEvent_t ev_pack = nullptr, ev_comm = nullptr, ev_ghost = nullptr, ev_bnd = nullptr;
     int* d_tiles_int = nullptr; long long n_tiles_int = 0;   // tiles that read no ghost cell of another rank
@@ -646,8 +651,8 @@ int eb200_init(const eb200_config* cfg)
         }
     }
     if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_HLLE2) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
-    if ((cfg->flux_calculator == EB200_FLUX_ROE || cfg->flux_calculator == EB200_FLUX_HLLC || cfg->flux_calculator == EB200_FLUX_HLLE2) && cfg->n_species > 1) {
-        set_err("roe, hllc and hlle2 with multiple species are not on this path yet"); return -1;
+    if ((cfg->flux_calculator == EB200_FLUX_HLLC || cfg->flux_calculator == EB200_FLUX_HLLE2) && cfg->n_species > 1) {
+        set_err("hllc and hlle2 with multiple species are not on this path yet"); return -1;
     }
     if (!n_stages_for(cfg->update_scheme)) { set_err("unsupported update scheme %d", cfg->update_scheme); return -1; }
     const bool adaptive = (cfg->flux_calculator >= EB200_FLUX_ADAPTIVE_HANEL_AUSMDV && cfg->flux_calculator <= EB200_FLUX_ADAPTIVE_LDFSS0_LDFSS2) ||
@@ -725,6 +730,9 @@ int eb200_init(const eb200_config* cfg)
         CUDA_OK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, hi));
     }
     CUDA_OK(cudaStreamCreateWithFlags(&s->bnd_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&s->d2h_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&s->ev_state, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s->ev_d2h_all, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s->ev_ghost, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s->ev_bnd, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s->ev_pack, cudaEventDisableTiming));
@@ -748,6 +756,8 @@ int eb200_finalize(int sim)
     if (s->h_status) cudaFreeHost(s->h_status);
     if (s->comm_stream) { cudaStreamSynchronize(s->comm_stream); cudaStreamDestroy(s->comm_stream); }
     if (s->bnd_stream) { cudaStreamSynchronize(s->bnd_stream); cudaStreamDestroy(s->bnd_stream); }
+    if (s->d2h_stream) { cudaStreamSynchronize(s->d2h_stream); cudaStreamDestroy(s->d2h_stream); }
+    for (auto& b : s->blocks) if (b->ev_d2h) cudaEventDestroy(b->ev_d2h);
     if (s->ev_ghost) cudaEventDestroy(s->ev_ghost);
     if (s->ev_bnd) cudaEventDestroy(s->ev_bnd);
     if (s->ev_pack) cudaEventDestroy(s->ev_pack);
@@ -924,6 +934,11 @@ int eb200_commit(int sim)
     // multi-GPU result to equal the single-GPU one): the generic kernel, which knows the one-sided stencils
     bool one_sided = false;
     for (auto& b : s->blocks) for (int f = 0; f < s->nfaces; ++f) if (b->bc[f].kind == EB200_BC_WALL_WITH_SLIP1) one_sided = true;
+    if (one_sided && any_cart) {
+        set_err("a job with EB200_BC_WALL_WITH_SLIP1 walls must be initialised with eb200_config.reserved_i[0] = 1: "
+                "the one-sided stencils are served by the general-metric kernel");
+        return -1;
+    }
     const bool force_generic = s->cfg.reserved_i[1] == 1 || one_sided;
     s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (force_generic ? 4 : 0) | (s->cfg.reserved_i[1] == 2 ? 8 : 0);
     // Which fused kernel runs a block decides its tiling.  The cell-centred kernel (flux_kernel_v3.cuh) takes the
@@ -1198,6 +1213,10 @@ int eb200_upload_flow(int sim, int blk_id, const double* const* prims, int nprim
     s->ghosts_stale = true;
     s->undo_cur = -1;
     static const int short_field[EB200_NPRIM_SHORT] = { 0, 1, 5, 6, 7 };
+    if (b->d2h_pending) {      // the block's last asynchronous download reads what this upload rewrites
+        CUDA_OK(cudaStreamWaitEvent(s->stream, b->ev_d2h, 0));
+        b->d2h_pending = false;
+    }
     for (int v = 0; v < nprims; ++v) {
         const int f = short_form ? short_field[v] : v;
         CUDA_OK(cudaMemcpyAsync(prim + (long long)f * s->P.total + b->cell0, prims[v], bytes, cudaMemcpyHostToDevice, s->stream));
@@ -1260,6 +1279,53 @@ int eb200_download_conserved(int sim, int blk_id, double* const* U, int ncq)
     for (int q = 0; q < ncq; ++q)
         CUDA_OK(cudaMemcpyAsync(U[q], Ud + (long long)q * s->P.total + b->cell0, bytes, cudaMemcpyDeviceToHost, s->stream));
     CUDA_OK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// Asynchronous form of eb200_download_conserved: the copies go to a second stream, behind everything enqueued so far,
+// and the call returns at once.  The next eb200_upload_flow of the same block waits (on the device) for them, every
+// other entry point that changes the state waits for all of them; eb200_wait_downloads is the host-side wait.  With
+// page-locked host arrays the device -> host copies of one step then run beside the host -> device copies of the
+// next one (PCIe is full duplex).
+int eb200_download_conserved_async(int sim, int blk_id, double* const* U, int ncq)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    Block* b = get_blk(s, blk_id); if (!b) return -1;
+    if (!s->committed || !b->local) { set_err("download_conserved_async needs a committed local block"); return -1; }
+    if (ncq != s->P.ncq) { set_err("expected %d conserved arrays", s->P.ncq); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (!b->ev_d2h) CUDA_OK(cudaEventCreateWithFlags(&b->ev_d2h, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(s->ev_state, s->stream));
+    CUDA_OK(cudaStreamWaitEvent(s->d2h_stream, s->ev_state, 0));
+    const size_t bytes = (size_t)b->ncp * sizeof(double);
+    const double* Ud = s->A.U[s->Ulev[0]];
+    for (int q = 0; q < ncq; ++q)
+        CUDA_OK(cudaMemcpyAsync(U[q], Ud + (long long)q * s->P.total + b->cell0, bytes, cudaMemcpyDeviceToHost, s->d2h_stream));
+    CUDA_OK(cudaEventRecord(b->ev_d2h, s->d2h_stream));
+    CUDA_OK(cudaEventRecord(s->ev_d2h_all, s->d2h_stream));
+    b->d2h_pending = true;
+    s->d2h_inflight = true;
+    return 0;
+}
+
+int eb200_wait_downloads(int sim)
+{
+    Sim* s = get_sim(sim); if (!s) return -1;
+    if (!s->committed) { set_err("not committed"); return -1; }
+    CUDA_OK(cudaSetDevice(s->cfg.device));
+    CUDA_OK(cudaStreamSynchronize(s->d2h_stream));
+    s->d2h_inflight = false;
+    for (Block* b : s->local) b->d2h_pending = false;
+    return 0;
+}
+
+// the compute stream does not overwrite conserved quantities that an asynchronous download is still reading
+static int order_after_downloads(Sim* s)
+{
+    if (s->d2h_inflight) {
+        CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_d2h_all, 0));
+        s->d2h_inflight = false;
+    }
     return 0;
 }
 
@@ -1330,6 +1396,7 @@ int eb200_step(int sim, double t0, double dt, int* n_bad_cells)
     Sim* s = get_sim(sim); if (!s) return -1;
     if (!s->committed) { set_err("not committed"); return -1; }
     CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (order_after_downloads(s)) return -100;
     CUDA_OK(cudaMemsetAsync(s->d_status, 0, 7 * sizeof(int), s->stream));
     const int cur0 = s->cur;
     int rc = enqueue_step(s, dt);
@@ -1359,6 +1426,7 @@ int eb200_run_steps(int sim, double t0, double dt, int nsteps, int* n_bad_cells)
     if (!s->committed) { set_err("not committed"); return -1; }
     s->undo_cur = -1;
     CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (order_after_downloads(s)) return -100;
     CUDA_OK(cudaMemsetAsync(s->d_status, 0, 7 * sizeof(int), s->stream));
     for (int n = 0; n < nsteps; ++n) {
         int rc = enqueue_step(s, dt);

@@ -6,7 +6,7 @@
 #ifdef EB_NO_TPG
 #define EB_FLUX_HAS_TPG 0
 #else
-#define EB_FLUX_HAS_TPG (EB_FLUX != 5 && EB_FLUX != 7 && EB_FLUX != 8 && EB_FLUX != 10 && EB_FLUX != 11 && EB_FLUX != 12)   /* roe, hllc, hlle2 with several species are not on this path;
+#define EB_FLUX_HAS_TPG (EB_FLUX != 7 && EB_FLUX != 8 && EB_FLUX != 10 && EB_FLUX != 11 && EB_FLUX != 12)   /* hllc, hlle2 with several species are not on this path;
                                                                           of the adaptive ones only the default is built for TPG */
 #endif
 #include "flux_kernel.cuh"

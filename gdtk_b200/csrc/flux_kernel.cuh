@@ -106,18 +106,6 @@ struct EbOneSided {
     }
 };
 
-// gamma = Cp / Cv of a state (gas_model.d:205)
-template <int GASM, int NSP>
-__device__ double gas_gamma(const EbGas* __restrict__ g, const Prim<NSP>& Q)
-{
-    if (GASM == EB200_GAS_IDEAL) return g->gamma_CpCv;
-    double Cp = 0.0, Cv = 0.0;
-    double cps[NSP];
-    for (int i = 0; i < NSP; ++i) { cea_Cp(g->curves[i], Q.T, cps[i]); Cp += Q.massf[i] * cps[i]; }
-    for (int i = 0; i < NSP; ++i) Cv += Q.massf[i] * (cps[i] - g->Rsp[i]);
-    return Cp / Cv;
-}
-
 // fluxcalc.d:187-385 for a state already in the face frame, gvel = 0.  side 0: gas on the right of the face.
 template <int DIM, int GASM, int NSP>
 __device__ void wall_flux_local(const EbGas* __restrict__ gas, const Prim<NSP>& fs, int side, double* F)
@@ -163,7 +151,18 @@ __device__ void wall_flux_local(const EbGas* __restrict__ gas, const Prim<NSP>& 
     F[Lay::iEnergy] = pstar * vstar;
 }
 
-template <int DIM, int FLUX, int GASM, int NSP, bool CART>
+// thermodynamic closure of a reconstructed state by the pair thermo_interpolator names; one copy per gas model
+template <int GASM, int NSP>
+__device__ __noinline__ bool thermo_by_interpolator(const EbGas* __restrict__ gas, int ti, Prim<NSP>* Q)
+{
+    if (ti == EB200_INTERP_PT) return thermo_from_pT<GASM, NSP>(gas, *Q);
+    if (ti == EB200_INTERP_RHOP) return thermo_from_rhop<GASM, NSP>(gas, *Q);
+    if (ti == EB200_INTERP_RHOT) return thermo_from_rhoT<GASM, NSP>(gas, *Q);
+    return thermo_from_rhou<GASM, NSP>(gas, *Q);
+}
+
+// (general-metric blocks only: a job with such a wall is set up without the uniform-Cartesian fast path, eb200.h)
+template <int DIM, int FLUX, int GASM, int NSP>
 __device__ __noinline__ bool face_flux_one_sided(const EbParams& P, const EbGas* __restrict__ gas, const EbBlockDesc& D,
                                                  const EbArena& A, const double* __restrict__ prim,
                                                  long long c, long long st, int d, int nL, int nR, double* F)
@@ -171,9 +170,9 @@ __device__ __noinline__ bool face_flux_one_sided(const EbParams& P, const EbGas*
     typedef Layout<DIM, NSP> Lay;
     const long long total = P.total;
     Frame fr;
-    if (!CART) load_frame<DIM>(fr, A.face[d], total, c);
-    auto loc = [&](double& x, double& y, double& z) { if (CART) axis_to_local(D.fr[d], x, y, z); else to_local<DIM>(fr, x, y, z); };
-    auto glob = [&](double& x, double& y, double& z) { if (CART) axis_to_global(D.fr[d], x, y, z); else to_global<DIM>(fr, x, y, z); };
+    load_frame<DIM>(fr, A.face[d], total, c);
+    auto loc = [&](double& x, double& y, double& z) { to_local<DIM>(fr, x, y, z); };
+    auto glob = [&](double& x, double& y, double& z) { to_global<DIM>(fr, x, y, z); };
     int mode;
     if (nL == 0 && nR >= 2) mode = EB_ST_L0R2;
     else if (nL == 1 && nR >= 2) mode = EB_ST_L1R2;
@@ -204,8 +203,8 @@ __device__ __noinline__ bool face_flux_one_sided(const EbParams& P, const EbGas*
         }
         double len[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) len[m] = CART ? D.w[d].lenL0 : (has[m] ? ldg(A.len[d] + cc[m]) : 0.0);
-        if (mode == EB_ST_L2R0 && !CART) { len[0] = ldg(A.len[0] + cc[0]); len[1] = ldg(A.len[0] + cc[1]); }   // :236 passes iLength
+        for (int m = 0; m < 4; ++m) len[m] = has[m] ? ldg(A.len[d] + cc[m]) : 0.0;
+        if (mode == EB_ST_L2R0) { len[0] = ldg(A.len[0] + cc[0]); len[1] = ldg(A.len[0] + cc[1]); }   // :236 passes iLength
         EbOneSided I;
         I.mode = mode; I.limiter = P.apply_limiter != 0; I.clip = P.extrema_clipping != 0; I.eps = P.eps_va;
         I.w0 = 0.0; I.w1 = 0.0;
@@ -241,8 +240,8 @@ __device__ __noinline__ bool face_flux_one_sided(const EbParams& P, const EbGas*
         if (ti == EB200_INTERP_PT) {
             I.scalar(X[0].p, X[1].p, X[2].p, X[3].p, L.p, R.p);
             I.scalar(X[0].T, X[1].T, X[2].T, X[3].T, L.T, R.T);
-            if (doL) okL = thermo_from_pT<GASM, NSP>(gas, L);
-            if (doR) okR = thermo_from_pT<GASM, NSP>(gas, R);
+            if (doL) okL = thermo_by_interpolator<GASM, NSP>(gas, ti, &L);
+            if (doR) okR = thermo_by_interpolator<GASM, NSP>(gas, ti, &R);
         } else {
             if (NSP > 1) {
                 double rho_L = 0.0, rho_R = 0.0;
@@ -250,19 +249,11 @@ __device__ __noinline__ bool face_flux_one_sided(const EbParams& P, const EbGas*
                 if (doL) { L.rho = rho_L; for (int i = 0; i < NSP; ++i) L.massf[i] = L.rho_s[i] / L.rho; ok &= scale_mass_fractions<NSP>(L.massf); }
                 if (doR) { R.rho = rho_R; for (int i = 0; i < NSP; ++i) R.massf[i] = R.rho_s[i] / R.rho; ok &= scale_mass_fractions<NSP>(R.massf); }
             } else I.scalar(X[0].rho, X[1].rho, X[2].rho, X[3].rho, L.rho, R.rho);
-            if (ti == EB200_INTERP_RHOP) {
-                I.scalar(X[0].p, X[1].p, X[2].p, X[3].p, L.p, R.p);
-                if (doL) okL = thermo_from_rhop<GASM, NSP>(gas, L);
-                if (doR) okR = thermo_from_rhop<GASM, NSP>(gas, R);
-            } else if (ti == EB200_INTERP_RHOT) {
-                I.scalar(X[0].T, X[1].T, X[2].T, X[3].T, L.T, R.T);
-                if (doL) okL = thermo_from_rhoT<GASM, NSP>(gas, L);
-                if (doR) okR = thermo_from_rhoT<GASM, NSP>(gas, R);
-            } else {
-                I.scalar(X[0].u, X[1].u, X[2].u, X[3].u, L.u, R.u);
-                if (doL) okL = thermo_from_rhou<GASM, NSP>(gas, L);
-                if (doR) okR = thermo_from_rhou<GASM, NSP>(gas, R);
-            }
+            if (ti == EB200_INTERP_RHOP) I.scalar(X[0].p, X[1].p, X[2].p, X[3].p, L.p, R.p);
+            else if (ti == EB200_INTERP_RHOT) I.scalar(X[0].T, X[1].T, X[2].T, X[3].T, L.T, R.T);
+            else I.scalar(X[0].u, X[1].u, X[2].u, X[3].u, L.u, R.u);
+            if (doL) okL = thermo_by_interpolator<GASM, NSP>(gas, ti, &L);
+            if (doR) okR = thermo_by_interpolator<GASM, NSP>(gas, ti, &R);
         }
         if (!okL) L = X[1];                 // the cell's state, velocity in the frame the cells are in now
         if (!okR) R = X[2];
@@ -301,11 +292,13 @@ __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __rest
 {
     typedef Layout<DIM, NSP> Lay;
     const long long total = P.total;
-    if (D.noghost_faces) {                   // idx = index of the face along d, nd = cells of the block along d
-        int nL = 2, nR = 2;
-        if ((D.noghost_faces >> (2 * d)) & 1) nL = min(idx, 2);
-        if ((D.noghost_faces >> (2 * d + 1)) & 1) nR = min(nd - idx, 2);
-        if (nL < 2 || nR < 2) return face_flux_one_sided<DIM, FLUX, GASM, NSP, CART>(P, gas, D, A, prim, c, st, d, nL, nR, F);
+    if constexpr (!CART) {
+        if (D.noghost_faces) {               // idx = index of the face along d, nd = cells of the block along d
+            int nL = 2, nR = 2;
+            if ((D.noghost_faces >> (2 * d)) & 1) nL = min(idx, 2);
+            if ((D.noghost_faces >> (2 * d + 1)) & 1) nR = min(nd - idx, 2);
+            if (nL < 2 || nR < 2) return face_flux_one_sided<DIM, FLUX, GASM, NSP>(P, gas, D, A, prim, c, st, d, nL, nR, F);
+        }
     }
     Frame fr;
     if (!CART) load_frame<DIM>(fr, A.face[d], total, c);

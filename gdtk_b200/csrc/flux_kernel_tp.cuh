@@ -279,7 +279,8 @@ __device__ __forceinline__ void tp_make_state(const TpGasS<NSP>& G, const EbGas*
 template <int DIM, int NSP>
 __device__ __forceinline__ void tp_cell_states(const EbBlockDesc& D, const TpGasS<NSP>& G, const EbGas* __restrict__ gas, int d, double eps,
                                                bool clip, const double* __restrict__ prim, long long total, long long c, long long st,
-                                               bool wantM, bool wantP, double* dstP, int strideP, Prim<NSP>& M, bool& fail, Prim<NSP>& rare)
+                                               bool wantM, bool wantP, double* dstP, int strideP, Prim<NSP>& M, bool& fail, Prim<NSP>& rare,
+                                               const TpCellTable<NSP>* cell_table = nullptr)
 {
     constexpr int NV = TpCfg<DIM, NSP>::NV;
     double qM[NV], qP[NV];
@@ -296,9 +297,10 @@ __device__ __forceinline__ void tp_cell_states(const EbBlockDesc& D, const TpGas
             for (int v = 0; v < NV; ++v) recon_cell_scalar<false>(D, d, eps, qm[v], q0[v], qp[v], qM[v], qP[v]);
         }
     }
-    const double T0 = ldg(prim + 3 * total + c), a0 = ldg(prim + 4 * total + c);
+    const double a0 = ldg(prim + 4 * total + c);
     TpCellTable<NSP> tb;
-    tp_table<NSP>(G, T0, tb);
+    if (cell_table) tb = *cell_table;           // the caller made the cell's table once for all directions
+    else tp_table<NSP>(G, ldg(prim + 3 * total + c), tb);
     if (wantP) {
         Prim<NSP> X;
         tp_make_state<DIM, NSP>(G, gas, prim, total, c, qP, a0, tb, X, fail, rare);
@@ -665,6 +667,9 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
         const int par = (k - k0) & 1;
         const long long c = cell_at(i, j, (DIM == 3) ? k : 0);
         const int nd = (DIM == 3) ? (has_cells ? 3 : 1) : (pre ? 0 : 2);
+        // species energies and heat capacities at the cell temperature: once per cell, for all its directions
+        TpCellTable<NSP> tbc;
+        tp_table<NSP>(G, ldg(prim + 3 * total + c), tbc);
 #pragma unroll 1
         for (int dd = 0; dd < nd; ++dd) {
             // 3D: along k first (the bottom face of this plane is the top face of the cell one plane below, which is then
@@ -679,7 +684,7 @@ flux_update_kernel_tp(const EbParams P, const EbGas* __restrict__ gas, const EbB
             double* dstP = (d == 2) ? myK + ((par ^ 1) * NS) * NTM : ((d == 0) ? myPi : sPj + ((wy + 1) * NS) * 32 + lane);
             const int strideP = (d == 2) ? NTM : 32;
             Prim<NSP> M;
-            if (act) tp_cell_states<DIM, NSP>(D, G, gas, d, eps_of(d), clip, prim, total, c, st, wM, wP, dstP, strideP, M, fail, rare);
+            if (act) tp_cell_states<DIM, NSP>(D, G, gas, d, eps_of(d), clip, prim, total, c, st, wM, wP, dstP, strideP, M, fail, rare, &tbc);
             if (d == 1) {
                 if (doJ) tp_put<NSP>(myMj, 32, M);
                 continue;

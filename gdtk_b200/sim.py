@@ -474,6 +474,10 @@ class Simulation:
         self.ncq = (5 if self.dims == 3 else 4) + (self.nsp if self.nsp > 1 else 0)
         self.n_stages = _abi.N_STAGES[_abi.UPDATE_SCHEMES[config.gasdynamic_update_scheme]]
         self._cfg_struct = config.to_struct(gmodel, rank, device)
+        if any(isinstance(bc, WallBC_WithSlip1) for b in self.blocks for bc in b.bcList.values()):
+            # walls without ghost-cell data are served by the general-metric kernel only (include/eb200.h,
+            # EB200_BC_WALL_WITH_SLIP1): every block of the job keeps its metric arrays
+            self._cfg_struct.reserved_i[0] = 1
         self.handle = self.lib.check(self.lib.init(C.byref(self._cfg_struct)), "init")
         self._exchange_cb = None
         self.time = 0.0

@@ -123,7 +123,9 @@ enum eb200_bc_kind {
     /* WallBC_WithSlip1 (bc.lua:783-806): ghost_cell_data_available = false, no ghost-cell effect.  The wall face has
      * no left (or right) cells and takes compute_flux_at_left_wall / _right_wall (fluxcalc.d:41-51, 187-385); it and
      * the next face in are reconstructed from the one-sided stencils l0r2 / l2r0 and l1r2 / l2r1
-     * (onedinterp.d:117-273, 386-485, 991-1838).  Not combined with the adaptive flux calculators on this path. */
+     * (onedinterp.d:117-273, 386-485, 991-1838).  A job with such a wall on any block runs the generic kernel on
+     * every block and must be initialised with eb200_config.reserved_i[0] = 1 (no uniform-Cartesian fast path:
+     * the one-sided code is built for the general-metric kernel only); eb200_commit says so otherwise. */
     EB200_BC_WALL_WITH_SLIP1 = 7,
     /* UserDefinedBC (bc.lua) whose ghostCells() function does not depend on time or on the flow
      * (bc/user_defined_effects.d:237-310 evaluates it at the ghost-cell centres every stage and gets the same
@@ -301,6 +303,15 @@ int eb200_download_flow(int sim, int blk_id, double* const* prims, int nprims);
  * ConservedQuantitiesIndices, conservedquantities.d:67-197:
  * mass, xMom, yMom, [zMom], totEnergy, [species x nsp]). */
 int eb200_download_conserved(int sim, int blk_id, double* const* U, int ncq);
+
+/* The same download without waiting for it: the copies are queued behind everything enqueued so far, on their own
+ * stream, and the call returns.  U must stay valid (and, to overlap, be page-locked) until eb200_wait_downloads
+ * returns.  The next eb200_upload_flow of this block and every step wait for the copies on the device, so a loop
+ * "upload all blocks, step, download all blocks" keeps host -> device and device -> host copies of consecutive
+ * steps in flight together.  (No counterpart in the reference: its FlowStates never leave host memory; this is the
+ * transfer pattern of a D shim that refreshes FVCell.fs every step, simcore.d:1029-1039.) */
+int eb200_download_conserved_async(int sim, int blk_id, double* const* U, int ncq);
+int eb200_wait_downloads(int sim);
 
 /* FlowStates of single cells of local blocks, e.g. the history points of a job
  * (setHistoryPoint; history.d:80-95 writes one line per history cell).

@@ -995,7 +995,6 @@ static void roe(const Sim* s, const FS* Lft, const FS* Rght, double* F)
     double ghat = (sqrt(rL) * gL + sqrt(rR) * gR) / (sqrt(rL) + sqrt(rR));
     double rhat = sqrt(rL * rR);
     double That = (sqrt(rL) * TL + sqrt(rR) * TR) / (sqrt(rL) + sqrt(rR));
-    (void)That;
     double uhat = (sqrt(rL) * uL + sqrt(rR) * uR) / (sqrt(rL) + sqrt(rR));
     double vhat = (sqrt(rL) * vL + sqrt(rR) * vR) / (sqrt(rL) + sqrt(rR));
     double what = (sqrt(rL) * wL + sqrt(rR) * wR) / (sqrt(rL) + sqrt(rR));
@@ -1039,11 +1038,36 @@ static void roe(const Sim* s, const FS* Lft, const FS* Rght, double* F)
                                  - (fabs(lambda[2]) * ((dp - rhat * ahat * du) / (2.0 * ahat2)) * what));
     if (s->threeD) F[s->iZMom] += zMom;
     double theta = 0.0;
+    if (s->nsp > 1) {                   /* fluxcalc.d:2055-2071, Walters et al. (1992) eq. 33b */
+        for (int i = 0; i < s->nsp; ++i) {
+            double dmassf = Rght->gas.massf[i] - Lft->gas.massf[i];
+            double hL, hR;              /* therm_perf_gas.d:443-448 internal_energy(Q, isp) = h_i(T) - R_i T */
+            cea_h(&s->curves[i], Lft->gas.T, &hL); cea_h(&s->curves[i], Rght->gas.T, &hR);
+            double eiL = hL - s->Rsp[i] * Lft->gas.T;
+            double eiR = hR - s->Rsp[i] * Rght->gas.T;
+            double eihat = (sqrt(rL) * eiL + sqrt(rR) * eiR) / (sqrt(rL) + sqrt(rR));
+            double Ri = s->Rsp[i];
+            double psihat = Ri * That / (ghat - 1.0) - eihat + kehat;
+            theta += dmassf * psihat;
+        }
+    }
     FL = rL * uL * HL; FR = rR * uR * HR;
     F[s->iEnergy] += factor * 0.5 * (FL + FR
                                     - (fabs(lambda[0]) * ((dr - dp / ahat2) * (kehat + tkehat) + rhat * (vhat * dv + what * dw + dtke - theta)))
                                     - (fabs(lambda[1]) * ((dp + rhat * ahat * du) / (2.0 * ahat2)) * (Hhat + uhat * ahat))
                                     - (fabs(lambda[2]) * ((dp - rhat * ahat * du) / (2.0 * ahat2)) * (Hhat - uhat * ahat)));
+    if (s->nsp > 1) {                   /* :2093-2107 */
+        for (int i = 0; i < s->nsp; ++i) {
+            double massfhat = (sqrt(rL) * Lft->gas.massf[i] + sqrt(rR) * Rght->gas.massf[i]) / (sqrt(rL) + sqrt(rR));
+            double dmassf = Rght->gas.massf[i] - Lft->gas.massf[i];
+            FL = rL * uL * Lft->gas.massf[i];
+            FR = rR * uR * Rght->gas.massf[i];
+            F[s->iSpecies + i] += factor * 0.5 * (FL + FR
+                                                 - (fabs(lambda[0]) * ((dr - dp / ahat2) * massfhat + rhat * dmassf))
+                                                 - (fabs(lambda[1]) * ((dp + rhat * ahat * du) / (2.0 * ahat2)) * massfhat)
+                                                 - (fabs(lambda[2]) * ((dp - rhat * ahat * du) / (2.0 * ahat2)) * massfhat));
+        }
+    }
 }
 
 /* fluxcalc.d:650-816 hllc: Toro's HLLC solver with Einfeldt's wave speeds (single temperature, no turbulence).
@@ -2005,7 +2029,7 @@ int orc_init(const eb200_config* cfg)
     s->nsp = cfg->n_species;
     if (s->nsp < 1 || s->nsp > MAXSP) { set_err("bad n_species"); return -1; }
     if (cfg->gas_model == EB200_GAS_IDEAL && s->nsp != 1) { set_err("ideal gas has one species"); return -1; }
-    if (cfg->flux_calculator == EB200_FLUX_ROE && s->nsp > 1) { set_err("roe with multiple species is not on this path yet"); return -1; }
+
     /* conservedquantities.d:67-197 */
     s->iMass = 0; s->iXMom = 1; s->iYMom = 2;
     if (s->threeD) { s->iZMom = 3; s->iEnergy = 4; } else { s->iZMom = -1; s->iEnergy = 3; }
@@ -2269,6 +2293,9 @@ int orc_download_conserved(int sim, int blk_id, double* const* U, int ncq)
 }
 
 /* fvcell.d:975-1058 signal_frequency (structured grid, non-stringent, inviscid) */
+int orc_download_conserved_async(int sim, int blk_id, double* const* U, int ncq) { return orc_download_conserved(sim, blk_id, U, ncq); }
+int orc_wait_downloads(int sim) { (void)sim; return 0; }
+
 static double signal_frequency(const Sim* s, const Blk* b, long c)
 {
     FS fs; load_fs(s, b, c, &fs);
