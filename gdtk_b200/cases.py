@@ -218,7 +218,7 @@ class PerturbedState:
 
 
 def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True, seed=1234,
-          gmodel=None, inflow=None, wall_bc=None, perturb=True, **cfg_kw):
+          gmodel=None, inflow=None, wall_bc=None, perturb=True, west_bc=None, **cfg_kw):
     """3D ideal-air box (C3/C4): unit cube, n^3 cells in nb^3 blocks; inflow west, simple
     outflow east, slip walls elsewhere; initial state = inflow + smooth perturbation.
     sheared=True tilts the k-lines by 10 degrees (general-metric path, cf.
@@ -258,7 +258,7 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
     connect_block_array(blocks, 3)
     for (ib, jb, kb), blk in blocks.items():
         if ib == 0:
-            blk.bcList["west"] = InFlowBC_Supersonic(inflow)
+            blk.bcList["west"] = west_bc(gm, inflow) if west_bc is not None else InFlowBC_Supersonic(inflow)
         if ib == nb - 1:
             blk.bcList["east"] = OutFlowBC_Simple()
         if wall_bc is not None:          # the four side walls with another wall class (WallBC_WithSlip1: no ghost cells)
@@ -267,6 +267,17 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
                     blk.bcList[name] = wall_bc()
     cfg.block_index = {blk.id: key for key, blk in blocks.items()}
     return cfg, gm, list(blocks.values())
+
+
+def sheared_inflow_profile(gm, inflow):
+    """A UserDefinedBC for box3d's inflow plane whose ghost-cell FlowStates vary with y and z (a static profile:
+    exercises the per-ghost-cell table and its ordering in 3D)."""
+    from .sim import UserDefinedBC
+    p0, T0, u0 = inflow.gas.p, inflow.gas.T, inflow.vel[0]
+
+    def state(x, y, z):
+        return FlowState(gm, p=p0 * (1.0 + 0.02 * y), T=T0 * (1.0 + 0.01 * z), velx=u0 * (1.0 + 0.03 * y * z), vely=5.0 * z, velz=-3.0 * y)
+    return UserDefinedBC(state)
 
 
 def tpg_subset_model(species):

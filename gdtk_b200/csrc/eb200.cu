@@ -18,6 +18,11 @@
 #include <vector>
 #include "eb200_internal.h"
 
+// one launch of the shock detector for all local blocks (misc_kernels.cu)
+namespace eb_strict { void launch_detect_shocks_all(const EbParams&, const EbBlockDesc*, int, long long, const EbArena&, const double*, cudaStream_t); }
+namespace eb_fast { void launch_detect_shocks_all(const EbParams&, const EbBlockDesc*, int, long long, const EbArena&, const double*, cudaStream_t); }
+
+
 #ifndef EB_TILE_Y
 #define EB_TILE_Y 8
 #endif
@@ -561,10 +566,11 @@ int enqueue_step(Sim* s, double dt)
         if (s->P.shock_detect && stage == 1) {
             // detect_shocks (phase 04) needs every ghost cell: wait for the halo of other ranks first
             if (!s->peers.empty()) CUDA_OK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
-            for (Block* b : s->local) {
-                MODE_CALL(s, launch_detect_shocks, s->P, s->hdesc[b->local_index], s->A, prim_in, s->stream);
-                s->launches += s->P.strict_shock ? 1 : 0;
-            }
+            long long max_pos = 0;
+            for (const EbBlockDesc& D : s->hdesc)
+                max_pos = std::max(max_pos, (long long)(D.nic + 1) * (D.njc + 1) * (s->threeD ? D.nkc + 1 : 1));
+            MODE_CALL(s, launch_detect_shocks_all, s->P, s->d_desc, (int)s->hdesc.size(), max_pos, s->A, prim_in, s->stream);
+            s->launches += s->P.strict_shock ? 1 : 0;
         }
         EbStageArgs S;
         memset(&S, 0, sizeof S);
@@ -649,6 +655,13 @@ int eb200_init(const eb200_config* cfg)
                     list.c_str(), cfg->n_species, cfg->n_species);
             return -1;
         }
+#ifdef EB_TPG_NSP_DEFAULT
+        if (cfg->n_species != 5 && cfg->flux_calculator != EB200_FLUX_AUSMDV) {
+            set_err("thermally perfect gas with %d species: the default build has these kernels for ausmdv only "
+                    "(five species for every flux calculator); rebuild with make TPG_NSP=\"%d 5\"", cfg->n_species, cfg->n_species);
+            return -1;
+        }
+#endif
     }
     if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_HLLE2) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
     if ((cfg->flux_calculator == EB200_FLUX_HLLC || cfg->flux_calculator == EB200_FLUX_HLLE2) && cfg->n_species > 1) {

@@ -130,9 +130,16 @@ struct EbStageArgs {
 struct EbCopyItem { int dst, src; };
 struct EbReflectItem { int dst, src, fidx, meta; };   // meta = blk*4 + dir
 // Species counts for which the thermally-perfect-gas kernels are instantiated: a build-time list
-// (make TPG_NSP="2 3 5 7"); eb200_init refuses other counts with a message that says so.
+// (make TPG_NSP="2 3 5 7", then for every flux calculator); eb200_init refuses other counts with a message that says so.
+// Default: five species for every flux calculator, three as well for ausmdv (each count costs minutes of compile time
+// per flux calculator and arithmetic mode).
 #ifndef EB_TPG_NSP_LIST
+#define EB_TPG_NSP_DEFAULT 1
+#if !defined(EB_FLUX) || EB_FLUX == 0
 #define EB_TPG_NSP_LIST(X) X(3) X(5)
+#else
+#define EB_TPG_NSP_LIST(X) X(5)
+#endif
 #endif
 #define EB_P2P_MAXPEERS 64                    /* flags per slot in the region the halo peers of one rank share */
 struct EbFillItem { int dst, param; };

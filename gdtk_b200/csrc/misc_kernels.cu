@@ -411,84 +411,107 @@ void launch_unpack(const EbParams& P, double* prim, double* S, const int* idx, l
 //   enforce_strict_shock_detector (:585-605); ghost-cell S is what the last ghost fill copied.
 // One thread per position of the block extended by one cell on the plus side of every direction.
 
-// PJ_ShockDetector (shockdetectors.d:22-93) for the face between cells cL and cR = cL + st along direction d
+// PJ_ShockDetector (shockdetectors.d:22-93) on values in registers.
 // side: 0 = the face has a cell on both sides; 1 = only the left cell exists (a wall without ghost-cell data on the
 // right), 2 = only the right cell: shockdetectors.d:48-84, the gas velocity relative to the wall (gvel = 0)
+struct PjCell { double vx, vy, vz, a; };
+struct PjFrame { double n[3], t1[3], t2[3]; };
+
 template <int DIM>
-__device__ __forceinline__ double pj_detector(const EbParams& P, const EbBlockDesc& D, const EbArena& A, const double* __restrict__ prim,
-                                              int d, long long cR, long long st, int side = 0)
+__device__ __forceinline__ PjCell pj_load_cell(const double* __restrict__ prim, long long total, long long c)
 {
-    const long long total = P.total, c = cR;
-    if (side != 0) {
-        const long long cc = (side == 1) ? c - st : c;
-        const double vx = ldg(prim + 5 * total + cc), vy = ldg(prim + 6 * total + cc);
-        const double vz = (DIM == 3) ? ldg(prim + 7 * total + cc) : 0.0;
-        const double a = ldg(prim + 4 * total + cc);
-        double n_[3], t1[3], t2[3];
-        if (D.cartesian) {
-            for (int m = 0; m < 3; ++m) { n_[m] = 0.0; t1[m] = 0.0; t2[m] = 0.0; }
-            n_[D.fr[d].perm[0]] = D.fr[d].neg[0] ? -1.0 : 1.0;
-            t1[D.fr[d].perm[1]] = D.fr[d].neg[1] ? -1.0 : 1.0;
-            t2[D.fr[d].perm[2]] = D.fr[d].neg[2] ? -1.0 : 1.0;
-        } else {
-            for (int m = 0; m < 3; ++m) {
-                n_[m] = ldg(A.face[d] + m * total + c); t1[m] = ldg(A.face[d] + (3 + m) * total + c);
-                t2[m] = ldg(A.face[d] + (6 + m) * total + c);
-            }
-        }
-        const double u = vx * n_[0] + vy * n_[1] + vz * n_[2];
-        const double comp = (side == 1) ? ((-u) / a) : (u / a);
-        const double v = vx * t1[0] + vy * t1[1] + vz * t1[2];
-        const double w = vx * t2[0] + vy * t2[1] + vz * t2[2];
-        const double shear = fmax(fabs(v) / a, fabs(w) / a);
-        return ((shear < P.shear_tol) && (comp < P.comp_tol)) ? 1.0 : 0.0;
-    }
-    const double vLx = ldg(prim + 5 * total + c - st), vLy = ldg(prim + 6 * total + c - st);
-    const double vLz = (DIM == 3) ? ldg(prim + 7 * total + c - st) : 0.0;
-    const double vRx = ldg(prim + 5 * total + c), vRy = ldg(prim + 6 * total + c);
-    const double vRz = (DIM == 3) ? ldg(prim + 7 * total + c) : 0.0;
-    const double aL = ldg(prim + 4 * total + c - st), aR = ldg(prim + 4 * total + c);
-    double n_[3], t1[3], t2[3];
+    PjCell q;
+    q.vx = ldg(prim + 5 * total + c); q.vy = ldg(prim + 6 * total + c);
+    q.vz = (DIM == 3) ? ldg(prim + 7 * total + c) : 0.0;
+    q.a = ldg(prim + 4 * total + c);
+    return q;
+}
+
+// the frame of the face on the minus-d side of cell c: the exact +-1/0 vectors of a uniform-Cartesian block from its
+// descriptor (compares against the loop index: no dynamically indexed local arrays), else the stored (n, t1, t2)
+__device__ __forceinline__ void pj_load_frame(const EbBlockDesc& D, const EbArena& A, long long total, int d, long long c, PjFrame& f)
+{
     if (D.cartesian) {
-        // reconstruct the exact +-1/0 frame of this direction from the descriptor
-        for (int m = 0; m < 3; ++m) { n_[m] = 0.0; t1[m] = 0.0; t2[m] = 0.0; }
-        n_[D.fr[d].perm[0]] = D.fr[d].neg[0] ? -1.0 : 1.0;
-        t1[D.fr[d].perm[1]] = D.fr[d].neg[1] ? -1.0 : 1.0;
-        t2[D.fr[d].perm[2]] = D.fr[d].neg[2] ? -1.0 : 1.0;
+        const int p0 = D.fr[d].perm[0], p1 = D.fr[d].perm[1], p2 = D.fr[d].perm[2];
+        const double s0 = D.fr[d].neg[0] ? -1.0 : 1.0, s1 = D.fr[d].neg[1] ? -1.0 : 1.0, s2 = D.fr[d].neg[2] ? -1.0 : 1.0;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { f.n[m] = (p0 == m) ? s0 : 0.0; f.t1[m] = (p1 == m) ? s1 : 0.0; f.t2[m] = (p2 == m) ? s2 : 0.0; }
     } else {
+#pragma unroll
         for (int m = 0; m < 3; ++m) {
-            n_[m] = ldg(A.face[d] + m * total + c); t1[m] = ldg(A.face[d] + (3 + m) * total + c);
-            t2[m] = ldg(A.face[d] + (6 + m) * total + c);
+            f.n[m] = ldg(A.face[d] + m * total + c); f.t1[m] = ldg(A.face[d] + (3 + m) * total + c);
+            f.t2[m] = ldg(A.face[d] + (6 + m) * total + c);
         }
     }
-    const double uL = vLx * n_[0] + vLy * n_[1] + vLz * n_[2];
-    const double uR = vRx * n_[0] + vRy * n_[1] + vRz * n_[2];
-    const double a_min = (aL < aR) ? aL : aR;
+}
+
+__device__ __forceinline__ double pj_detector(const EbParams& P, const PjCell& cL, const PjCell& cR, const PjFrame& f, int side)
+{
+    if (side != 0) {
+        const PjCell& q = (side == 1) ? cL : cR;
+        const double u = q.vx * f.n[0] + q.vy * f.n[1] + q.vz * f.n[2];
+        const double v = q.vx * f.t1[0] + q.vy * f.t1[1] + q.vz * f.t1[2];
+        const double w = q.vx * f.t2[0] + q.vy * f.t2[1] + q.vz * f.t2[2];
+#ifdef EB_FAST_MATH
+        // sound speeds are positive: compare the numerators with tolerance x denominator, no division
+        const double un = (side == 1) ? -u : u;
+        return ((fmax(fabs(v), fabs(w)) < P.shear_tol * q.a) && (un < P.comp_tol * q.a)) ? 1.0 : 0.0;
+#else
+        const double comp = (side == 1) ? ((-u) / q.a) : (u / q.a);
+        const double shear = fmax(fabs(v) / q.a, fabs(w) / q.a);
+        return ((shear < P.shear_tol) && (comp < P.comp_tol)) ? 1.0 : 0.0;
+#endif
+    }
+    const double uL = cL.vx * f.n[0] + cL.vy * f.n[1] + cL.vz * f.n[2];
+    const double uR = cR.vx * f.n[0] + cR.vy * f.n[1] + cR.vz * f.n[2];
+    const double a_min = (cL.a < cR.a) ? cL.a : cR.a;
+#ifdef EB_FAST_MATH
+    const double comp = 0.0;
+#else
     const double comp = ((uR - uL) / a_min);
-    const double vL = vLx * t1[0] + vLy * t1[1] + vLz * t1[2], vR = vRx * t1[0] + vRy * t1[1] + vRz * t1[2];
-    const double wL = vLx * t2[0] + vLy * t2[1] + vLz * t2[2], wR = vRx * t2[0] + vRy * t2[1] + vRz * t2[2];
-    const double sound_speed = 0.5 * (aL + aR);
+#endif
+    const double vL = cL.vx * f.t1[0] + cL.vy * f.t1[1] + cL.vz * f.t1[2], vR = cR.vx * f.t1[0] + cR.vy * f.t1[1] + cR.vz * f.t1[2];
+    const double wL = cL.vx * f.t2[0] + cL.vy * f.t2[1] + cL.vz * f.t2[2], wR = cR.vx * f.t2[0] + cR.vy * f.t2[1] + cR.vz * f.t2[2];
+    const double sound_speed = 0.5 * (cL.a + cR.a);
+#ifdef EB_FAST_MATH
+    (void)comp;
+    return ((fmax(fabs(vL - vR), fabs(wL - wR)) < P.shear_tol * sound_speed) && ((uR - uL) < P.comp_tol * a_min)) ? 1.0 : 0.0;
+#else
     const double shear_y = fabs(vL - vR) / sound_speed;
     const double shear_z = fabs(wL - wR) / sound_speed;
     const double shear = fmax(shear_y, shear_z);
     return ((shear < P.shear_tol) && (comp < P.comp_tol)) ? 1.0 : 0.0;
+#endif
 }
 
 // pass 0: the detector on the minus-side faces of every position AND, in the same launch, shock_faces_to_cells for
 // interior cells: the detector of a cell's plus-side faces is evaluated a second time by the cell itself (a pure
 // function of the same FlowStates: the same value the owner of that face stores), which saves a pass over the block.
+// A thread loads its own cell once and one neighbour per side and direction.
 // pass 2: enforce_strict_shock_detector.
 template <int DIM>
-__global__ void shock_kernel(const EbParams P, const EbBlockDesc D, const EbArena A, const double* __restrict__ prim, int pass)
+__global__ void shock_kernel(const EbParams P, const EbBlockDesc* __restrict__ descs, const EbArena A, const double* __restrict__ prim, int pass)
 {
+    // blockIdx.y = local block: all blocks of the process in one launch
+    __shared__ EbBlockDesc D;
+    {
+        const int* src = reinterpret_cast<const int*>(&descs[blockIdx.y]);
+        int* dst = reinterpret_cast<int*>(&D);
+        for (int m = threadIdx.x; m < (int)(sizeof(EbBlockDesc) / sizeof(int)); m += blockDim.x) dst[m] = src[m];
+    }
+    __syncthreads();
     const int ei = D.nic + 1, ej = D.njc + 1, ek = (DIM == 3) ? D.nkc + 1 : 1;
     const long long n = (long long)ei * ej * ek;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int i = (int)(t % ei), j = (int)((t / ei) % ej), k = (int)(t / ((long long)ei * ej));
     const long long c = D.cell0 + ((long long)(k + D.kg) * D.NJ + (j + EB_NG)) * D.NI + (i + EB_NG);
+    const long long total = P.total;
     const bool in_i = i < D.nic, in_j = j < D.njc, in_k = (DIM == 3) ? (k < D.nkc) : true;
+    const bool interior = in_i && in_j && in_k;
     double Smax = 0.0;                                     // iface order W,E,S,N,B,T; max is order-independent
+    PjCell own;
+    if (pass == 0) own = pj_load_cell<DIM>(prim, total, c);
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
         // the face on the minus-d side of this position exists if the other two indices are interior
@@ -500,11 +523,19 @@ __global__ void shock_kernel(const EbParams P, const EbBlockDesc D, const EbAren
         const bool wallL = (D.noghost_faces >> (2 * d)) & 1, wallR = (D.noghost_faces >> (2 * d + 1)) & 1;
         const int side = (wallL && idx == 0) ? 2 : ((wallR && idx == nd) ? 1 : 0);
         if (pass == 0) {
-            const double Sf = pj_detector<DIM>(P, D, A, prim, d, c, st, side);
+            PjFrame f;
+            pj_load_frame(D, A, total, d, c, f);
+            PjCell below = own;
+            if (side != 2) below = pj_load_cell<DIM>(prim, total, c - st);
+            const double Sf = pj_detector(P, below, own, f, side);
             A.Sf[d][c] = Sf;
-            if (in_i && in_j && in_k) {
+            if (interior) {
+                const int side1 = (wallR && idx + 1 == nd) ? 1 : 0;
+                PjCell above = own;
+                if (side1 != 1) above = pj_load_cell<DIM>(prim, total, c + st);
+                if (!D.cartesian) pj_load_frame(D, A, total, d, c + st, f);
                 Smax = fmax(Smax, Sf);
-                Smax = fmax(Smax, pj_detector<DIM>(P, D, A, prim, d, c + st, st, (wallR && idx + 1 == nd) ? 1 : 0));
+                Smax = fmax(Smax, pj_detector(P, own, above, f, side1));
             }
         } else {
             double Sf = A.Sf[d][c];
@@ -512,18 +543,24 @@ __global__ void shock_kernel(const EbParams P, const EbBlockDesc D, const EbAren
             A.Sf[d][c] = Sf;
         }
     }
-    if (pass == 0 && in_i && in_j && in_k) A.S[c] = Smax;
+    if (pass == 0 && interior) A.S[c] = Smax;
+}
+
+// (declared here and in eb200.cu)
+void launch_detect_shocks_all(const EbParams& P, const EbBlockDesc* d_desc, int nblocks, long long max_positions, const EbArena& A,
+                              const double* prim, cudaStream_t st)
+{
+    const int threads = 256;
+    const dim3 grid((unsigned)((max_positions + threads - 1) / threads), (unsigned)nblocks);
+    for (int pass = 0; pass <= (P.strict_shock ? 2 : 0); pass += 2) {
+        if (P.dims == 3) shock_kernel<3><<<grid, threads, 0, st>>>(P, d_desc, A, prim, pass);
+        else shock_kernel<2><<<grid, threads, 0, st>>>(P, d_desc, A, prim, pass);
+    }
 }
 
 void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A, const double* prim, cudaStream_t st)
 {
-    const long long n = (long long)(hdesc.nic + 1) * (hdesc.njc + 1) * ((P.dims == 3) ? hdesc.nkc + 1 : 1);
-    const int threads = 256;
-    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    for (int pass = 0; pass <= (P.strict_shock ? 2 : 0); pass += 2) {
-        if (P.dims == 3) shock_kernel<3><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, pass);
-        else shock_kernel<2><<<blocks, threads, 0, st>>>(P, hdesc, A, prim, pass);
-    }
+    (void)P; (void)hdesc; (void)A; (void)prim; (void)st;      // superseded by launch_detect_shocks_all
 }
 
 }  // namespace EB_NS

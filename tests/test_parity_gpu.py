@@ -169,6 +169,14 @@ def test_walls_without_ghost_cells(oracle, product):
              sheared=True, flux_calculator="hanel")
 
 
+def test_user_defined_ghost_profile_3d(oracle, product):
+    """A static UserDefinedBC profile on the inflow plane of the 3D box (FlowStates that vary with y and z, one per
+    ghost cell): the table's ordering on both kinds of block, with the ordinary walls (bit-identical in the FMA-free
+    build)."""
+    _compare(cases.box3d, oracle, product, 6, n=16, nb=2, west_bc=cases.sheared_inflow_profile)
+    _compare(cases.box3d, oracle, product, 4, n=12, nb=1, west_bc=cases.sheared_inflow_profile, sheared=True)
+
+
 def test_block_of_the_benchmark_shape(oracle, product):
     """One 128^3 block -- the benchmark's block size: whole 32 x 16 tiles, the k-chunking of a full-size block, TMA
     staging -- three predictor-corrector steps against the oracle."""
@@ -335,12 +343,13 @@ def test_odd_block_width_uses_cp_async_path(oracle, product):
     _compare(cases.box3d, oracle, product, 6, n=14, nb=2, sheared=True)
 
 
-@pytest.mark.parametrize("flux", ["ausmdv", "hanel", "ldfss2", "ausm_plus_up"])
+@pytest.mark.parametrize("flux", ["ausmdv", "hanel", "ldfss2", "ausm_plus_up", "roe"])
 @pytest.mark.parametrize("sheared", [False, True])
 def test_thermally_perfect_five_species(oracle, product, flux, sheared):
     """C5 at test size: 5-species thermally perfect air, frozen chemistry; Newton temperature
     solves at both sides of every face and in every decode.  Not bit-comparable (CUDA's log() and
-    glibc's differ in the last place), so both builds are held to the 1e-10 tolerance."""
+    glibc's differ in the last place), so both builds are held to the 1e-10 tolerance.  roe: with the species terms of
+    fluxcalc.d:2055-2107 (theta in the energy flux from the species energies h_i(T) - R_i T, species fluxes)."""
     _compare(cases.tpg_box3d, oracle, product, 5, expect_bitwise=False, n=12, nb=2, flux_calculator=flux, sheared=sheared)
 
 
@@ -363,8 +372,9 @@ def test_thermally_perfect_tuned_and_generic_kernels_agree(product, case):
 
 @pytest.mark.parametrize("species", [("N2", "O2", "NO")])
 def test_thermally_perfect_other_species_counts(oracle, product, species):
-    """The thermally-perfect-gas kernels are instantiated for a build-time list of species counts (3 and 5 by
-    default): two and three species, uniform blocks (cell-centred kernel) and sheared ones (generic kernel)."""
+    """The thermally-perfect-gas kernels are instantiated for a build-time list of species counts (by default five
+    for every flux calculator and three for ausmdv): three species, uniform blocks (cell-centred kernel) and sheared
+    ones (generic kernel)."""
     _compare(cases.tpg_box3d, oracle, product, 4, expect_bitwise=False, n=16, nb=2, species=species)
     _compare(cases.tpg_box3d, oracle, product, 4, expect_bitwise=False, n=12, nb=2, species=species, sheared=True)
 
@@ -445,6 +455,45 @@ def test_step_failure_and_retry(product):
     sim.gasdynamic_step()
     assert sim.dt_global < 1.0e-2
     sim.close()
+
+
+def test_asynchronous_downloads_overlap_uploads_without_changing_results(product):
+    """eb200_download_conserved_async + eb200_wait_downloads: the loop 'upload every block, step, download every block'
+    with the downloads on their own stream gives the numbers of the synchronous calls, step after step (the next
+    upload of a block and the next step wait on the device for the copies still in flight)."""
+    import ctypes as C
+    from gdtk_b200 import Simulation
+    from gdtk_b200.sim import _as_dpp
+    cfg, gm, blocks = cases.box3d(n=32, nb=2)
+    sims = [Simulation(cfg, gm, blocks, lib=product) for _ in range(2)]
+    dt = 0.5 * sims[0].compute_dt(False)[0]
+    nbad = C.c_int(0)
+    ids = [b.id for b in sims[0].local_blocks]
+    flows = {bid: [a.copy() for a in sims[0].download_flow(bid)] for bid in ids}
+    g = sims[0].byid[ids[0]].geom
+    bufs = {bid: [np.zeros((g.NK, g.NJ, g.NI)) for _ in range(sims[0].ncq)] for bid in ids}
+    for step in range(3):
+        for sim in sims:
+            for bid in ids:
+                product.check(product.upload_flow(sim.handle, bid, _as_dpp(flows[bid]), len(flows[bid])), "upload_flow")
+            assert product.step(sim.handle, 0.0, dt, C.byref(nbad)) == 0
+        for bid in ids:        # queued, not waited for: the next loop's uploads are enqueued behind them
+            product.check(product.download_conserved_async(sims[0].handle, bid, _as_dpp(bufs[bid]), sims[0].ncq), "download_conserved_async")
+        if step == 2:
+            product.check(product.wait_downloads(sims[0].handle), "wait_downloads")
+    for bid in ids:
+        ref = sims[1].download_conserved(bid)
+        assert all(np.array_equal(a, b) for a, b in zip(bufs[bid], ref))
+    # a step after asynchronous downloads waits for them: the buffers hold the state before that step
+    for bid in ids:
+        product.check(product.download_conserved_async(sims[0].handle, bid, _as_dpp(bufs[bid]), sims[0].ncq), "download_conserved_async")
+    assert product.step(sims[0].handle, 0.0, dt, C.byref(nbad)) == 0
+    product.check(product.wait_downloads(sims[0].handle), "wait_downloads")
+    for bid in ids:
+        ref = sims[1].download_conserved(bid)
+        assert all(np.array_equal(a, b) for a, b in zip(bufs[bid], ref))
+    for sim in sims:
+        sim.close()
 
 
 def test_run_stage_command_line(tmp_path, product):
