@@ -169,6 +169,35 @@ def test_walls_without_ghost_cells(oracle, product):
              sheared=True, flux_calculator="hanel")
 
 
+def test_supersonic_vortex_known_answer_on_the_gpu(product):
+    """vtx-test.rb on the GPU, throughput build, whole job: 2761 +- 3 steps, L2(p) = 800 +- 100 Pa, L2(T) = 0.405 +- 0.10 K
+    against the exact vortex (the oracle gives 2760, 793.5 and 0.4051: tests/test_oracle_kats.py)."""
+    import math
+    from gdtk_b200 import Simulation
+    cfg, gm, blocks = cases.vortex()
+    cfg.strict_fp = False
+    sim = Simulation(cfg, gm, blocks, lib=product)
+    steps = sim.run()
+    exact = cases.vortex_flow(gm)
+    sum_p = sum_T = vol = 0.0
+    for b in blocks:
+        g = b.geom
+        P = sim.download_flow(b.id)
+        p, T = sim.interior(b.id, P[2]), sim.interior(b.id, P[3])
+        V, X, Y = (sim.interior(b.id, a) for a in (g.vol, g.pos[0], g.pos[1]))
+        for idx in np.ndindex(p.shape):
+            e = exact(X[idx], Y[idx])
+            sum_p += V[idx] * (p[idx] - e.gas.p) ** 2
+            sum_T += V[idx] * (T[idx] - e.gas.T) ** 2
+            vol += V[idx]
+    L2p, L2T = math.sqrt(sum_p / vol), math.sqrt(sum_T / vol)
+    print(f"vortex on the GPU: {steps} steps, L2(p) = {L2p:.1f} Pa, L2(T) = {L2T:.4f} K")
+    sim.close()
+    assert abs(steps - 2761) < 3
+    assert abs(L2p - 800.0) < 100.0
+    assert abs(L2T - 0.405) < 0.10
+
+
 def test_user_defined_ghost_profile_3d(oracle, product):
     """A static UserDefinedBC profile on the inflow plane of the 3D box (FlowStates that vary with y and z, one per
     ghost cell): the table's ordering on both kinds of block, with the ordinary walls (bit-identical in the FMA-free
