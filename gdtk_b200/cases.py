@@ -341,11 +341,13 @@ def tpg_cone20(**kw):
     return cone20(gmodel=gm, inflow=inflow, initial=initial, **kw)
 
 
-def ffs(nx=384, ny=128, flux_calculator="ausmdv", uniform_fast=True, gmodel=None, inflow=None, **cfg_kw):
+def ffs(nx=384, ny=128, flux_calculator="ausmdv", uniform_fast=True, gmodel=None, inflow=None, i_step=None, **cfg_kw):
     """Mach-3 forward-facing step (C2): domain [0,3]x[0,1], step at x=0.6, height 0.2
     (examples/eilmer/2D/forward-facing-step/ffs.lua:21-32), three blocks like the example:
     blk0 [0,0.6]x[0,0.2], blk1 [0,0.6]x[0.2,1], blk2 [0.6,3]x[0.2,1].  nx, ny are the cell
-    counts of the bounding grid (4096 x 1024 for the benchmark); dx = 3/nx, dy = 1/ny."""
+    counts of the bounding grid (4096 x 1024 for the benchmark); dx = 3/nx, dy = 1/ny.  i_step: the cell index of
+    the step face (default: the nearest to x = 0.6); the benchmark picks the nearest EVEN index, so that every block
+    has an even padded width and its rows can be staged by TMA (16-byte strides)."""
     gm = gmodel or ideal_air()
     cfg = Config(dimensions=2, flux_calculator=flux_calculator, max_step=10, max_time=1.0,
                  dt_init=1.0e-3, cfl_value=0.5)
@@ -356,7 +358,7 @@ def ffs(nx=384, ny=128, flux_calculator="ausmdv", uniform_fast=True, gmodel=None
         a0 = math.sqrt(gm.gamma * gm.Rgas * T0)
         inflow = FlowState(gm, p=101.325e3, T=T0, velx=3.0 * a0)
     dx, dy = 3.0 / nx, 1.0 / ny
-    i_step, j_step = int(round(0.6 / dx)), int(round(0.2 / dy))
+    i_step, j_step = (int(i_step) if i_step is not None else int(round(0.6 / dx))), int(round(0.2 / dy))
     specs = [(0, i_step, 0, j_step), (0, i_step, j_step, ny), (i_step, nx, j_step, ny)]
     blocks = []
     for bid, (i0, i1, j0, j1) in enumerate(specs):

@@ -18,10 +18,6 @@
 #include <vector>
 #include "eb200_internal.h"
 
-// one launch of the shock detector for all local blocks (misc_kernels.cu)
-namespace eb_strict { void launch_detect_shocks_all(const EbParams&, const EbBlockDesc*, int, long long, const EbArena&, const double*, cudaStream_t); }
-namespace eb_fast { void launch_detect_shocks_all(const EbParams&, const EbBlockDesc*, int, long long, const EbArena&, const double*, cudaStream_t); }
-
 
 #ifndef EB_TILE_Y
 #define EB_TILE_Y 8

@@ -172,8 +172,8 @@ struct EbFillItem { int dst, param; };
                     double* S_dst, const int* src_idx, const int* dst_idx, long long n, cudaStream_t st);  \
     void launch_halo_signal(unsigned long long* const* remote_flags, int npeers, unsigned long long seq, int slot, cudaStream_t st); \
     void launch_halo_wait(const unsigned long long* flags, int npeers, unsigned long long seq, int slot, int* status, cudaStream_t st); \
-    void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A,             \
-                              const double* prim, cudaStream_t st);                                      \
+    void launch_detect_shocks_all(const EbParams& P, const EbBlockDesc* d_desc, int nblocks, long long max_positions,  \
+                                  const EbArena& A, const double* prim, cudaStream_t st);                \
     }
 
 EB_DECLARE_LAUNCHERS(eb_strict)

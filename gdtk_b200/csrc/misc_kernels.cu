@@ -546,7 +546,6 @@ __global__ void shock_kernel(const EbParams P, const EbBlockDesc* __restrict__ d
     if (pass == 0 && interior) A.S[c] = Smax;
 }
 
-// (declared here and in eb200.cu)
 void launch_detect_shocks_all(const EbParams& P, const EbBlockDesc* d_desc, int nblocks, long long max_positions, const EbArena& A,
                               const double* prim, cudaStream_t st)
 {
@@ -556,11 +555,6 @@ void launch_detect_shocks_all(const EbParams& P, const EbBlockDesc* d_desc, int 
         if (P.dims == 3) shock_kernel<3><<<grid, threads, 0, st>>>(P, d_desc, A, prim, pass);
         else shock_kernel<2><<<grid, threads, 0, st>>>(P, d_desc, A, prim, pass);
     }
-}
-
-void launch_detect_shocks(const EbParams& P, const EbBlockDesc& hdesc, const EbArena& A, const double* prim, cudaStream_t st)
-{
-    (void)P; (void)hdesc; (void)A; (void)prim; (void)st;      // superseded by launch_detect_shocks_all
 }
 
 }  // namespace EB_NS
