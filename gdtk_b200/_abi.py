@@ -87,7 +87,8 @@ class Config(C.Structure):
         ("ideal_gamma", C.c_double),
         ("compression_tolerance", C.c_double),
         ("shear_tolerance", C.c_double),
-        ("reserved_d", C.c_double * 4),
+        ("solver_variant", C.c_double),
+        ("reserved_d", C.c_double * 3),
         ("species", Species * MAX_SPECIES),
     ]
 

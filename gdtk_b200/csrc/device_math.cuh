@@ -532,14 +532,21 @@ __device__ __forceinline__ double clip_to_limits(double q, double A, double B)
     return (qc <= upper) ? qc : upper;
 }
 
+// lmr: van Albada's epsilon scaled by the local magnitude and the cell spacing (lmr/onedinterp.d:147-151)
 __device__ __forceinline__ void interp_scalar(const EbWeights& w, bool limiter, bool clip, double eps,
                                               double qL1, double qL0, double qR0, double qR1,
-                                              double& qL, double& qR)
+                                              double& qL, double& qR, bool lmr = false)
 {
     double delLminus = (qL0 - qL1) * w.two_over_L0L1;
     double del = (qR0 - qL0) * w.two_over_R0L0;
     double delRplus = (qR1 - qR0) * w.two_over_R1R0;
     double sL = 1.0, sR = 1.0;
+    if (lmr) {
+        const double qqL = fmax(1e-12, fabs(qL0));
+        const double qqR = fmax(1e-12, fabs(qR0));
+        const double qq = fmax(qqL, qqR);
+        eps = qq * eps * w.two_over_R0L0;
+    }
     if (limiter) {
         sL = eb_div(delLminus * del + fabs(delLminus * del) + eps, delLminus * delLminus + del * del + eps);
         sR = eb_div(del * delRplus + fabs(del * delRplus) + eps, del * del + delRplus * delRplus + eps);
@@ -582,11 +589,17 @@ __device__ __forceinline__ void l2r2_prepare(EbWeights& w, double lenL1, double 
 
 // fluxcalc.d:474-647
 template <int DIM, int NSP>
-__device__ __forceinline__ void flux_ausmdv(const Prim<NSP>& L, const Prim<NSP>& R, bool entropy_fix, double* F)
+__device__ __forceinline__ void flux_ausmdv(const Prim<NSP>& L, const Prim<NSP>& R, bool entropy_fix, double* F, bool smooth_am = false)
 {
     typedef Layout<DIM, NSP> Lay;
     EB_UNPACK_LR
     double am = fmax(aL, aR);
+    if (smooth_am) {            // lmr/fluxcalc.d:553-561: smooth maximum instead of max(aL, aR)
+        const double da = aL - aR;
+        const double scale = 0.5 * (aL + aR);
+        const double eps = 1e-6 * scale + 1e-12;
+        am = 0.5 * (aL + aR) + 0.5 * sqrt(da * da + eps * eps);
+    }
     double duL = 0.5 * (uL + fabs(uL));
     double duR = 0.5 * (uR - fabs(uR));
     double pLplus, uLplus, pRminus, uRminus;
@@ -1133,7 +1146,7 @@ struct FluxPair {
 template <int DIM, int NSP, int GASM, int BASE>
 __device__ __forceinline__ void basic_flux(const EbParams& P, const EbGas* __restrict__ gas, const Prim<NSP>& L, const Prim<NSP>& R, double* F)
 {
-    if (BASE == EB200_FLUX_AUSMDV) flux_ausmdv<DIM, NSP>(L, R, P.entropy_fix != 0, F);
+    if (BASE == EB200_FLUX_AUSMDV) flux_ausmdv<DIM, NSP>(L, R, P.entropy_fix != 0, F, P.lmr != 0);
     else if (BASE == EB200_FLUX_HANEL) flux_hanel<DIM, NSP>(L, R, F);
     else if (BASE == EB200_FLUX_LDFSS0) flux_ldfss<DIM, NSP, 0>(L, R, F);
     else if (BASE == EB200_FLUX_LDFSS2) flux_ldfss<DIM, NSP, 2>(L, R, F);

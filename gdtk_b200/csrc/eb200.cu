@@ -660,6 +660,9 @@ int eb200_init(const eb200_config* cfg)
 #endif
     }
     if (cfg->flux_calculator < 0 || cfg->flux_calculator > EB200_FLUX_HLLE2) { set_err("unknown flux calculator %d", cfg->flux_calculator); return -1; }
+    if (cfg->solver_variant != 0.0 && (cfg->n_species != 1 || !cfg->interpolate_in_local_frame)) {
+        set_err("solver_variant = lmr: single-species gas with interpolate_in_local_frame only (lmr/onedinterp.d:218-227, 270-292)"); return -1;
+    }
     if ((cfg->flux_calculator == EB200_FLUX_HLLC || cfg->flux_calculator == EB200_FLUX_HLLE2) && cfg->n_species > 1) {
         set_err("hllc and hlle2 with multiple species are not on this path yet"); return -1;
     }
@@ -696,7 +699,7 @@ int eb200_init(const eb200_config* cfg)
     if (cfg->thermo_interpolator < EB200_INTERP_RHOU || cfg->thermo_interpolator > EB200_INTERP_RHOT) {
         set_err("unknown thermo_interpolator %d", cfg->thermo_interpolator); return -1;
     }
-    P.thermo_interp = cfg->thermo_interpolator; P.pad_ti = 0;
+    P.thermo_interp = cfg->thermo_interpolator; P.lmr = (cfg->solver_variant != 0.0) ? 1 : 0;
     P.comp_tol = cfg->compression_tolerance; P.shear_tol = cfg->shear_tolerance;
     EbGas& g = s->hgas; memset(&g, 0, sizeof g);
     g.model = cfg->gas_model; g.nsp = cfg->n_species;
@@ -948,13 +951,14 @@ int eb200_commit(int sim)
                 "the one-sided stencils are served by the general-metric kernel");
         return -1;
     }
-    const bool force_generic = s->cfg.reserved_i[1] == 1 || one_sided;
+    if (one_sided && s->P.lmr) { set_err("solver_variant = lmr has no one-sided stencils on this path (lmr/onedinterp.d has l2r2 and l3r3 only)"); return -1; }
+    const bool force_generic = s->cfg.reserved_i[1] == 1 || one_sided || s->P.lmr;     // the variant formulas live in the generic kernel
     s->which = (any_cart ? 1 : 0) | (any_general ? 2 : 0) | (force_generic ? 4 : 0) | (s->cfg.reserved_i[1] == 2 ? 8 : 0);
     // Which fused kernel runs a block decides its tiling.  The cell-centred kernel (flux_kernel_v3.cuh) takes the
     // uniform-Cartesian blocks of the reference's default configuration (same conditions as in flux_inst.cu) when
     // their tiles can be staged by TMA.
     const bool tma_ok = tma_available(s);
-    const bool v3_config = tma_ok && s->cfg.reserved_i[1] == 0 && !one_sided && s->cfg.gas_model == EB200_GAS_IDEAL &&
+    const bool v3_config = tma_ok && s->cfg.reserved_i[1] == 0 && !one_sided && !s->P.lmr && s->cfg.gas_model == EB200_GAS_IDEAL &&
                            s->P.interpolation_order == 2 && s->P.apply_limiter != 0 && s->P.thermo_interp == EB200_INTERP_RHOU;
     for (size_t n = 0; n < s->local.size(); ++n) s->hdesc[n].v3 = (v3_config && s->hdesc[n].cartesian) ? 1 : 0;
     {

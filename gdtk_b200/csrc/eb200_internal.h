@@ -98,7 +98,7 @@ struct EbParams {            // passed by value to kernels (kept small)
     int ignore_low_T;
     int iZMom, iEnergy, iSpecies;
     int shock_detect, strict_shock;       // adaptive flux calculators: PJ shock detector on
-    int thermo_interp, pad_ti;            // eb200_thermo_interpolator
+    int thermo_interp, lmr;               // eb200_thermo_interpolator; lmr != 0: eb200_config.solver_variant = 1 (src/lmr formulas)
     double eps_va, M_inf, max_velocity, max_temp, min_temp, low_T;
     double comp_tol, shear_tol;
     long long total;          // arena length (field stride)

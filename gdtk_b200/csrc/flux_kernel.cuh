@@ -346,11 +346,11 @@ __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __rest
             l2r2_prepare(wl, ldg(ln + cL1), ldg(ln + cL0), ldg(ln + cR0), ldg(ln + cR1));
         }
         const EbWeights& w = CART ? D.w[d] : wl;
-        const bool lim = P.apply_limiter != 0, clip = P.extrema_clipping != 0;
+        const bool lim = P.apply_limiter != 0, clip = P.extrema_clipping != 0, lmr = P.lmr != 0;
         const double eps = P.eps_va;
-        interp_scalar(w, lim, clip, eps, vL1x, vL0x, vR0x, vR1x, L.vx, R.vx);
-        interp_scalar(w, lim, clip, eps, vL1y, vL0y, vR0y, vR1y, L.vy, R.vy);
-        if (DIM == 3) interp_scalar(w, lim, clip, eps, vL1z, vL0z, vR0z, vR1z, L.vz, R.vz);
+        interp_scalar(w, lim, clip, eps, vL1x, vL0x, vR0x, vR1x, L.vx, R.vx, lmr);
+        interp_scalar(w, lim, clip, eps, vL1y, vL0y, vR0y, vR1y, L.vy, R.vy, lmr);
+        if (DIM == 3) interp_scalar(w, lim, clip, eps, vL1z, vL0z, vR0z, vR1z, L.vz, R.vz, lmr);
         else { L.vz = 0.0; R.vz = 0.0; }
         const int ti = P.thermo_interp;
         bool okL, okR;
@@ -358,14 +358,14 @@ __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __rest
 #pragma unroll
             for (int i = 0; i < NSP; ++i) {
                 const double* ps = prim + (8 + NSP + i) * total;
-                interp_scalar(w, lim, clip, eps, ldg(ps + cL1), ldg(ps + cL0), ldg(ps + cR0), ldg(ps + cR1), L.rho_s[i], R.rho_s[i]);
+                interp_scalar(w, lim, clip, eps, ldg(ps + cL1), ldg(ps + cL0), ldg(ps + cR0), ldg(ps + cR1), L.rho_s[i], R.rho_s[i], lmr);
             }
         }
         if (ti == EB200_INTERP_PT) {            // onedinterp.d:820-850: p and T, then the mass fractions
             const double* pp = prim + 2 * total;
             const double* pT = prim + 3 * total;
-            interp_scalar(w, lim, clip, eps, ldg(pp + cL1), ldg(pp + cL0), ldg(pp + cR0), ldg(pp + cR1), L.p, R.p);
-            interp_scalar(w, lim, clip, eps, ldg(pT + cL1), ldg(pT + cL0), ldg(pT + cR0), ldg(pT + cR1), L.T, R.T);
+            interp_scalar(w, lim, clip, eps, ldg(pp + cL1), ldg(pp + cL0), ldg(pp + cR0), ldg(pp + cR1), L.p, R.p, lmr);
+            interp_scalar(w, lim, clip, eps, ldg(pT + cL1), ldg(pT + cL0), ldg(pT + cR0), ldg(pT + cR1), L.T, R.T, lmr);
             if (NSP > 1) {                      // Lft/Rght start as copies of the cells: their mass fractions
 #pragma unroll
                 for (int i = 0; i < NSP; ++i) { L.massf[i] = ldg(prim + (8 + i) * total + cL0); R.massf[i] = ldg(prim + (8 + i) * total + cR0); }
@@ -383,26 +383,28 @@ __device__ __forceinline__ bool face_flux(const EbParams& P, const EbGas* __rest
                 ok &= scale_mass_fractions<NSP>(L.massf);
                 ok &= scale_mass_fractions<NSP>(R.massf);
             } else {
-                interp_scalar(w, lim, clip, eps, ldg(prim + cL1), rhoL0, rhoR0, ldg(prim + cR1), L.rho, R.rho);
+                interp_scalar(w, lim, clip, eps, ldg(prim + cL1), rhoL0, rhoR0, ldg(prim + cR1), L.rho, R.rho, lmr);
                 L.massf[0] = 1.0; R.massf[0] = 1.0;
             }
             if (ti == EB200_INTERP_RHOP) {
                 const double* pp = prim + 2 * total;
-                interp_scalar(w, lim, clip, eps, ldg(pp + cL1), ldg(pp + cL0), ldg(pp + cR0), ldg(pp + cR1), L.p, R.p);
+                interp_scalar(w, lim, clip, eps, ldg(pp + cL1), ldg(pp + cL0), ldg(pp + cR0), ldg(pp + cR1), L.p, R.p, lmr);
                 okL = thermo_from_rhop<GASM, NSP>(gas, L);
                 okR = thermo_from_rhop<GASM, NSP>(gas, R);
             } else if (ti == EB200_INTERP_RHOT) {
                 const double* pT = prim + 3 * total;
-                interp_scalar(w, lim, clip, eps, ldg(pT + cL1), ldg(pT + cL0), ldg(pT + cR0), ldg(pT + cR1), L.T, R.T);
+                interp_scalar(w, lim, clip, eps, ldg(pT + cL1), ldg(pT + cL0), ldg(pT + cR0), ldg(pT + cR1), L.T, R.T, lmr);
                 okL = thermo_from_rhoT<GASM, NSP>(gas, L);
                 okR = thermo_from_rhoT<GASM, NSP>(gas, R);
             } else {
-                interp_scalar(w, lim, clip, eps, ldg(prim + total + cL1), uL0, uR0, ldg(prim + total + cR1), L.u, R.u);
+                interp_scalar(w, lim, clip, eps, ldg(prim + total + cL1), uL0, uR0, ldg(prim + total + cR1), L.u, R.u, lmr);
                 okL = thermo_from_rhou<GASM, NSP>(gas, L);
                 okR = thermo_from_rhou<GASM, NSP>(gas, R);
             }
         }
-        // on a failed thermo update: fall back to the cell-centre state (onedinterp.d:45-74)
+        // on a failed thermo update: fall back to the cell-centre state (onedinterp.d:45-74); lmr has no try/catch
+        // there (lmr/onedinterp.d:296-360): the exception ends the step
+        if (lmr && !(okL && okR)) ok = false;
         if (!okL) {
             load_prim<NSP>(L, prim, total, cL0);
             L.vx = vL0x; L.vy = vL0y; L.vz = vL0z;        // the cell's velocity, currently in the local frame

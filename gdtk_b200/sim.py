@@ -75,6 +75,9 @@ class Config:
         # Not an Eilmer option: testing knob, never use the uniform-Cartesian fast path.
         self.force_general_path = False
         self.force_generic_kernel = False  # testing knob: never use the tuned flux kernel
+        # "eilmer4" (src/eilmer, the default) or "lmr": Eilmer 5's formulas where they change numbers on this path
+        # (scaled van Albada epsilon, smooth-maximum sound speed in AUSMDV, no thermo fall-back)
+        self.solver_variant = "eilmer4"
         self.no_tma = False                # testing knob: stage tiles with cp.async instead of TMA
         self.no_push = False               # testing knob: all ghost cells are filled by the ghost-cell kernel
         self.block_index = None          # optional {block id: (ib, jb, kb)} left by the case factories
@@ -138,6 +141,9 @@ class Config:
         c.max_invalid_cells = self.max_invalid_cells
         c.strict_fp = int(self.strict_fp)
         c.thermo_interpolator = _abi.THERMO_INTERPOLATORS[self.thermo_interpolator]
+        if self.solver_variant not in ("eilmer4", "lmr"):
+            raise ValueError(f"unknown solver_variant {self.solver_variant!r}")
+        c.solver_variant = 1.0 if self.solver_variant == "lmr" else 0.0
         c.reserved_i[0] = int(self.force_general_path)
         c.reserved_i[1] = int(self.force_generic_kernel)
         c.reserved_i[2] = int(self.no_tma)

@@ -204,7 +204,13 @@ typedef struct eb200_config {
     double ideal_gamma;
     double compression_tolerance;   /* -0.30 (globalconfig.d:1123), PJ shock detector */
     double shear_tolerance;         /* 0.20 (globalconfig.d:1108) */
-    double reserved_d[4];
+    double solver_variant;          /* 0: Eilmer 4 (src/eilmer), every citation in this header; 1: the formulas of Eilmer 5
+                                       (src/lmr) where they change numbers on this path: van Albada's epsilon scaled by the
+                                       local magnitude and cell spacing (lmr/onedinterp.d:147-151), the smooth maximum for
+                                       AUSMDV's common sound speed (lmr/fluxcalc.d:553-561), no fall-back to the cell state
+                                       when a reconstructed state has no thermodynamic closure (lmr/onedinterp.d:296-360:
+                                       the step fails instead).  Single-species gas, generic kernel. */
+    double reserved_d[3];
     /* Thermally perfect gas mixture */
     eb200_species species[EB200_MAX_SPECIES];
 } eb200_config;

@@ -105,6 +105,7 @@ typedef struct {
     int lists_built;
     int shock_detect;        /* do_shock_detect (set by the adaptive flux calculators) */
     int mutate_cell_vel;     /* reproduce e4 onedinterp.d:766-769,983-986 in-place round trips */
+    int lmr;                 /* eb200_config.solver_variant == 1: the formulas of src/lmr where they differ */
     double** undo_saved;     /* FlowStates at the start of the last successful step (orc_undo_step), or NULL */
     int n_stages;
 } Sim;
@@ -535,6 +536,12 @@ static void interp_l2r2_scalar(const Sim* s, const L2R2* w, double qL1, double q
     double sL = 1.0, sR = 1.0;
     if (s->cfg.apply_limiter) {
         double eps = s->cfg.epsilon_van_albada;
+        if (s->lmr) {          /* lmr/onedinterp.d:147-151: "Dimensionalise the smoothing parameter epsilon" */
+            double qqL = fmax(1e-12, fabs(qL0));
+            double qqR = fmax(1e-12, fabs(qR0));
+            double qq = fmax(qqL, qqR);
+            eps = qq * s->cfg.epsilon_van_albada * w->two_over_lenR0_plus_lenL0;
+        }
         sL = (delLminus * del + fabs(delLminus * del) + eps) / (delLminus * delLminus + del * del + eps);
         sR = (del * delRplus + fabs(del * delRplus) + eps) / (del * del + delRplus * delRplus + eps);
     }
@@ -668,8 +675,8 @@ static int interp_stencil(const Sim* s, int mode, FS cells[4], const double len[
     if (ti == EB200_INTERP_PT) {                      /* case InterpolateOption.pt :820-850 */
         interp_l2r2_scalar(s, &w, cL1->gas.p, cL0->gas.p, cR0->gas.p, cR1->gas.p, &Lft->gas.p, &Rght->gas.p, beta);
         interp_l2r2_scalar(s, &w, cL1->gas.T, cL0->gas.T, cR0->gas.T, cR1->gas.T, &Lft->gas.T, &Rght->gas.T, beta);
-        if (doL && gas_update_thermo_from_pT(s, &Lft->gas)) *Lft = *cL0;
-        if (doR && gas_update_thermo_from_pT(s, &Rght->gas)) *Rght = *cR0;
+        if (doL && gas_update_thermo_from_pT(s, &Lft->gas)) { if (s->lmr) return -1; *Lft = *cL0; }     /* lmr/onedinterp.d:296-360: no try/catch */
+        if (doR && gas_update_thermo_from_pT(s, &Rght->gas)) { if (s->lmr) return -1; *Rght = *cR0; }
         if (nsp > 1) {
             for (int i = 0; i < nsp; ++i) {
                 if (doL) Lft->gas.massf[i] = Lft->gas.rho_s[i] / Lft->gas.rho;
@@ -698,17 +705,17 @@ static int interp_stencil(const Sim* s, int mode, FS cells[4], const double len[
     }
     if (ti == EB200_INTERP_RHOP) {
         interp_l2r2_scalar(s, &w, cL1->gas.p, cL0->gas.p, cR0->gas.p, cR1->gas.p, &Lft->gas.p, &Rght->gas.p, beta);
-        if (doL && gas_update_thermo_from_rhop(s, &Lft->gas)) *Lft = *cL0;
-        if (doR && gas_update_thermo_from_rhop(s, &Rght->gas)) *Rght = *cR0;
+        if (doL && gas_update_thermo_from_rhop(s, &Lft->gas)) { if (s->lmr) return -1; *Lft = *cL0; }     /* lmr/onedinterp.d:296-360: no try/catch */
+        if (doR && gas_update_thermo_from_rhop(s, &Rght->gas)) { if (s->lmr) return -1; *Rght = *cR0; }
     } else if (ti == EB200_INTERP_RHOT) {
         interp_l2r2_scalar(s, &w, cL1->gas.T, cL0->gas.T, cR0->gas.T, cR1->gas.T, &Lft->gas.T, &Rght->gas.T, beta);
-        if (doL && gas_update_thermo_from_rhoT(s, &Lft->gas)) *Lft = *cL0;
-        if (doR && gas_update_thermo_from_rhoT(s, &Rght->gas)) *Rght = *cR0;
+        if (doL && gas_update_thermo_from_rhoT(s, &Lft->gas)) { if (s->lmr) return -1; *Lft = *cL0; }     /* lmr/onedinterp.d:296-360: no try/catch */
+        if (doR && gas_update_thermo_from_rhoT(s, &Rght->gas)) { if (s->lmr) return -1; *Rght = *cR0; }
     } else {
         interp_l2r2_scalar(s, &w, cL1->gas.u, cL0->gas.u, cR0->gas.u, cR1->gas.u, &Lft->gas.u, &Rght->gas.u, beta);
         /* mixin(codeForThermoUpdateBoth("rhou")) :45-74: on exception copy the whole cell state */
-        if (doL && gas_update_thermo_from_rhou(s, &Lft->gas)) *Lft = *cL0;
-        if (doR && gas_update_thermo_from_rhou(s, &Rght->gas)) *Rght = *cR0;
+        if (doL && gas_update_thermo_from_rhou(s, &Lft->gas)) { if (s->lmr) return -1; *Lft = *cL0; }     /* lmr/onedinterp.d:296-360: no try/catch */
+        if (doR && gas_update_thermo_from_rhou(s, &Rght->gas)) { if (s->lmr) return -1; *Rght = *cR0; }
     }
 back_to_global:
 #undef interp_l2r2_scalar
@@ -754,6 +761,12 @@ static void ausmdv(const Sim* s, const FS* Lft, const FS* Rght, double* F)
     double alphaL = 2.0 * pLrL / (pLrL + pRrR);
     double alphaR = 2.0 * pRrR / (pLrL + pRrR);
     double am = fmax(aL, aR);
+    if (s->lmr) {              /* lmr/fluxcalc.d:553-561: the smooth maximum of Biswas et al. (KAD 2025-08-18) */
+        double da = aL - aR;
+        double scale = 0.5 * (aL + aR);
+        double eps = 1e-6 * scale + 1e-12;
+        am = 0.5 * (aL + aR) + 0.5 * sqrt(da * da + eps * eps);
+    }
     double ML = uL / am;
     double MR = uR / am;
     double pLplus, uLplus;
@@ -2027,6 +2040,10 @@ int orc_init(const eb200_config* cfg)
     if (cfg->dimensions != 2 && cfg->dimensions != 3) { set_err("dimensions must be 2 or 3"); return -1; }
     s->threeD = (cfg->dimensions == 3);
     s->nsp = cfg->n_species;
+    s->lmr = (cfg->solver_variant != 0.0);
+    if (s->lmr && (s->nsp != 1 || !cfg->interpolate_in_local_frame)) {
+        set_err("solver_variant = lmr: single-species gas with interpolate_in_local_frame only (lmr/onedinterp.d:218-227, 270-292)"); return -1;
+    }
     if (s->nsp < 1 || s->nsp > MAXSP) { set_err("bad n_species"); return -1; }
     if (cfg->gas_model == EB200_GAS_IDEAL && s->nsp != 1) { set_err("ideal gas has one species"); return -1; }
 

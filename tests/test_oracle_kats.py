@@ -341,3 +341,21 @@ def test_one_sided_stencils_reduce_to_the_symmetric_one_on_linear_data(oracle):
         for v in (6, 7):
             assert np.max(np.abs(sim.interior(b.id, P[v]))) < 1.0e-9
     sim.close()
+
+
+def test_cone20_with_the_formulas_of_eilmer5(oracle):
+    """config.solver_variant = "lmr": the scaled van Albada epsilon (lmr/onedinterp.d:147-151), AUSMDV's smooth-maximum
+    sound speed (lmr/fluxcalc.d:553-561) and no thermo fall-back.  Known answer of the lmr example
+    (examples/lmr/2D/sharp-cone-20-degrees/sg-minimal/test_sharp_cone_sg_minimal.py:105): the transient run takes
+    833 +- 5 steps to 5 ms, like Eilmer 4's; and the variant does change numbers (it is not a no-op)."""
+    runs = {}
+    for variant in ("eilmer4", "lmr"):
+        cfg, gm, blocks = cases.cone20(flux_calculator="adaptive_hanel_ausmdv", solver_variant=variant)
+        sim = Simulation(cfg, gm, blocks, lib=oracle)
+        steps = sim.run()
+        runs[variant] = (steps, [sim.interior(b.id, sim.download_flow(b.id)[2]).copy() for b in blocks])
+        sim.close()
+    assert abs(runs["lmr"][0] - 833) < 12
+    diff = max(float(np.max(np.abs(a - b) / np.abs(b))) for a, b in zip(runs["lmr"][1], runs["eilmer4"][1]))
+    print(f"cone20: lmr variant {runs['lmr'][0]} steps, Eilmer 4 {runs['eilmer4'][0]}; largest relative pressure difference {diff:.2e}")
+    assert 1.0e-12 < diff < 0.05

@@ -198,6 +198,15 @@ def test_supersonic_vortex_known_answer_on_the_gpu(product):
     assert abs(L2T - 0.405) < 0.10
 
 
+def test_formulas_of_eilmer5(oracle, product):
+    """config.solver_variant = "lmr" (SURVEY App. B): van Albada's epsilon scaled per face, the smooth-maximum sound
+    speed of AUSMDV, no thermo fall-back; generic kernel on both kinds of block, plain and adaptive calculators."""
+    _compare(cases.box3d, oracle, product, 6, n=16, nb=2, solver_variant="lmr")
+    _compare(cases.box3d, oracle, product, 5, n=12, nb=2, solver_variant="lmr", sheared=True, flux_calculator="adaptive_hanel_ausmdv")
+    _compare(cases.cone20, oracle, product, 100, solver_variant="lmr", flux_calculator="ausmdv")
+    _compare(cases.ffs, oracle, product, 40, nx=120, ny=40, solver_variant="lmr", flux_calculator="hanel")
+
+
 def test_user_defined_ghost_profile_3d(oracle, product):
     """A static UserDefinedBC profile on the inflow plane of the 3D box (FlowStates that vary with y and z, one per
     ghost cell): the table's ordering on both kinds of block, with the ordinary walls (bit-identical in the FMA-free
