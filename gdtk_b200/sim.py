@@ -481,9 +481,11 @@ class Simulation:
         self.n_stages = _abi.N_STAGES[_abi.UPDATE_SCHEMES[config.gasdynamic_update_scheme]]
         self._cfg_struct = config.to_struct(gmodel, rank, device)
         if any(isinstance(bc, WallBC_WithSlip1) for b in self.blocks for bc in b.bcList.values()):
-            # walls without ghost-cell data are served by the general-metric kernel only (include/eb200.h,
-            # EB200_BC_WALL_WITH_SLIP1): every block of the job keeps its metric arrays
+            # walls without ghost-cell data are served by the generic kernel on general-metric blocks only
+            # (include/eb200.h, EB200_BC_WALL_WITH_SLIP1): every block of the job, on every process -- whoever owns the
+            # wall -- keeps its metric arrays and runs that kernel, so that N processes compute what one computes
             self._cfg_struct.reserved_i[0] = 1
+            self._cfg_struct.reserved_i[1] = 1
         self.handle = self.lib.check(self.lib.init(C.byref(self._cfg_struct)), "init")
         self._exchange_cb = None
         self.time = 0.0
@@ -564,14 +566,6 @@ class Simulation:
             m = np.ascontiguousarray(bc.cell_map, dtype=np.int32)
             lib.check(lib.block_set_face_map(h, blk.id, f, m.ctypes.data_as(C.POINTER(C.c_int)), m.size // 3), "block_set_face_map")
         local_ids = {b.id for b in local}
-        # a wall without ghost-cell data anywhere in the job moves every block to the kernel that knows the one-sided
-        # stencils: every process has to hear of it, whoever owns the block
-        for b in self.blocks:
-            if b.id in local_ids:
-                continue
-            for f in range(nfaces):
-                if isinstance(b.bcList.get(_abi.FACE_NAMES[f]), WallBC_WithSlip1):
-                    lib.check(lib.block_set_bc(h, b.id, f, _abi.BC_WALL_WITH_SLIP1, (C.c_double * 1)(), 0, -1, -1, 0), "block_set_bc")
         for b in self.blocks:
             if b.id not in needed:
                 continue

@@ -124,8 +124,10 @@ enum eb200_bc_kind {
      * no left (or right) cells and takes compute_flux_at_left_wall / _right_wall (fluxcalc.d:41-51, 187-385); it and
      * the next face in are reconstructed from the one-sided stencils l0r2 / l2r0 and l1r2 / l2r1
      * (onedinterp.d:117-273, 386-485, 991-1838).  A job with such a wall on any block runs the generic kernel on
-     * every block and must be initialised with eb200_config.reserved_i[0] = 1 (no uniform-Cartesian fast path:
-     * the one-sided code is built for the general-metric kernel only); eb200_commit says so otherwise. */
+     * every block and must be initialised, on every process of the job, with eb200_config.reserved_i[0] = 1 (no
+     * uniform-Cartesian fast path: the one-sided code is built for the general-metric kernel only; eb200_commit
+     * says so otherwise) and reserved_i[1] = 1 (a process that owns no such wall must pick the same kernel as the
+     * others for N processes to reproduce one). */
     EB200_BC_WALL_WITH_SLIP1 = 7,
     /* UserDefinedBC (bc.lua) whose ghostCells() function does not depend on time or on the flow
      * (bc/user_defined_effects.d:237-310 evaluates it at the ghost-cell centres every stage and gets the same

@@ -36,7 +36,9 @@ def _worker():
                                       ("rotated-pair", rotated_pair, dict(), 6),
                                       ("ffs", cases.ffs, dict(nx=60, ny=20), 25),
                                       ("cone20", cases.cone20, dict(), 30),
-                                      ("cone20-adaptive", cases.cone20, dict(flux_calculator="adaptive_hanel_ausmdv"), 60)):
+                                      ("cone20-adaptive", cases.cone20, dict(flux_calculator="adaptive_hanel_ausmdv"), 60),
+                                      # walls without ghost cells and a static user-defined inflow profile, four blocks
+                                      ("vortex", cases.vortex, dict(gfactor=2), 40)):
         cfg, gm, blocks = factory(**kw)
         if name == "box3d":
             owner = octant_owner({v: next(b for b in blocks if b.id == k) for k, v in cfg.block_index.items()}, 2, world)
@@ -84,6 +86,7 @@ def test_two_ranks_match_one_rank_gloo():
     assert "rotated-pair: 2 ranks == 1 rank: True" in r.stdout
     assert "cone20: 2 ranks == 1 rank: True" in r.stdout
     assert "cone20-adaptive: 2 ranks == 1 rank: True" in r.stdout
+    assert "vortex: 2 ranks == 1 rank: True" in r.stdout
 
 
 if __name__ == "__main__" and "--worker" in sys.argv:
