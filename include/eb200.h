@@ -179,7 +179,8 @@ typedef struct eb200_config {
     int interpolate_in_local_frame; /* 1 */
     int apply_entropy_fix;          /* 1 (AUSMDV) */
     int update_scheme;              /* EB200_UPDATE_PC */
-    int max_invalid_cells;          /* 0 */
+    int max_invalid_cells;          /* 0; compared with the invalid cells of ALL local blocks of a stage together (the
+                                       reference counts per block, simcore_gasdynamic_step.d:1442: stricter when > 0) */
     int strict_fp;                  /* 1: kernels built with FMA contraction off, bit-comparable
                                        with the reference's generic x86-64 (no FMA) arithmetic;
                                        0: fused multiply-add allowed (throughput build) */
