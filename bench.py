@@ -51,7 +51,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -63,10 +63,14 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark(self, name):
+        """Wall-clock stamp of the start / end of the timed region (nvidia-smi stamps its lines with local time)."""
+        setattr(self, name, time.time())
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -77,30 +81,43 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, reasons, smax = [], set(), None
+        import datetime
+        rows, smax = [], None
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
         try:
             with open(self.path) as f:
                 for line in f:
                     p = [x.strip() for x in line.split(",")]
-                    if len(p) < 9:
+                    if len(p) < 10:
                         continue
                     try:
-                        sm.append(float(p[1]))
+                        mhz = float(p[1])
                         smax = float(p[2])
                     except ValueError:
                         continue
-                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                        if v.lower().startswith("active"):
-                            reasons.add(name)
+                    try:
+                        stamp = datetime.datetime.strptime(p[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except ValueError:
+                        stamp = None
+                    rs = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9])
+                          if v.lower().startswith("active")}
+                    rows.append((stamp, mhz, rs))
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            hot = sorted(sm)[len(sm) // 2:]          # samples under load
-            out["sm_mhz"] = statistics.median(hot)
+        # the samples taken inside the timed region (the sampler starts before the job is set up, so that it is running
+        # by then); if the stamps cannot be matched, the upper half of all samples (those under load)
+        inside = [r for r in rows if r[0] is not None and t0 is not None and t1 is not None and t0 - 0.02 <= r[0] <= t1 + 0.02]
+        if inside:
+            use, out["window"] = inside, "timed region"
+        else:
+            use = sorted(rows, key=lambda r: r[1])[len(rows) // 2:]
+            out["window"] = "whole run (no sample stamped inside the timed region)"
+        if use:
+            out["sm_mhz"] = statistics.median(r[1] for r in use)
             out["sm_max_mhz"] = smax
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+            out["samples"] = len(use)
+        out["reasons"] = sorted(set().union(*[r[2] for r in use])) if use else []
         return out
 
 
@@ -183,6 +200,9 @@ def make_sim(spec, world, local_rank):
 def run_gpu_workload(args, spec, rank, world, local_rank, with_e2e=False, with_real_loop=False, steps=None):
     import torch
     steps = steps or args.steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # long before the timed region: nvidia-smi needs a moment to come up
     t_setup = time.time()
     sim, name, balg = make_sim(spec, world, local_rank)
     t_setup = time.time() - t_setup
@@ -208,15 +228,14 @@ def run_gpu_workload(args, spec, rank, world, local_rank, with_e2e=False, with_r
     sim.run_fixed(args.warmup, dt)
     sim.flux_kernel_time(reset=True)
     launches0 = sim.kernel_launches()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark("t0")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     sim.run_fixed(steps, dt)
     e1.record(ext)
     e1.synchronize()
+    sampler.mark("t1")
     barrier()
     clocks = sampler.stop() if rank == 0 else {}
     ms = e0.elapsed_time(e1)
