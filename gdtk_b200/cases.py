@@ -218,7 +218,7 @@ class PerturbedState:
 
 
 def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True, seed=1234,
-          gmodel=None, inflow=None, wall_bc=None, perturb=True, west_bc=None, **cfg_kw):
+          gmodel=None, inflow=None, wall_bc=None, perturb=True, west_bc=None, closed=False, **cfg_kw):
     """3D ideal-air box (C3/C4): unit cube, n^3 cells in nb^3 blocks; inflow west, simple
     outflow east, slip walls elsewhere; initial state = inflow + smooth perturbation.
     sheared=True tilts the k-lines by 10 degrees (general-metric path, cf.
@@ -257,6 +257,8 @@ def box3d(n=64, nb=2, flux_calculator="ausmdv", sheared=False, uniform_fast=True
                 bid += 1
     connect_block_array(blocks, 3)
     for (ib, jb, kb), blk in blocks.items():
+        if closed:                       # slip walls all round (the default of a face without a boundary condition)
+            continue
         if ib == 0:
             blk.bcList["west"] = west_bc(gm, inflow) if west_bc is not None else InFlowBC_Supersonic(inflow)
         if ib == nb - 1:

@@ -215,6 +215,49 @@ def test_user_defined_ghost_profile_3d(oracle, product):
     _compare(cases.box3d, oracle, product, 4, n=12, nb=1, west_bc=cases.sheared_inflow_profile, sheared=True)
 
 
+def test_benchmark_size_properties(product):
+    """BASELINE's metric configuration at full size (512^3 cells in 64 blocks of 128^3, where the oracle would take
+    hours), through properties that do not depend on the size:
+      * a closed box (slip walls all round, gas at rest with the density perturbation): total mass and total energy do
+        not drift (the face fluxes telescope across tiles, chunks, blocks and pushed ghost cells);
+      * the benchmark job itself: the FMA-free build -- bit-identical to the oracle wherever the oracle can go -- and the
+        throughput build agree to 1e-10 after three steps."""
+    from gdtk_b200 import FlowState, Simulation
+    gm = cases.ideal_air()
+    rest = FlowState(gm, p=95.84e3, T=1103.0, velx=0.0)
+    cfg, gm, blocks = cases.box3d(n=512, nb=4, closed=True, inflow=rest, gmodel=gm)
+    cfg.strict_fp = False
+    sim = Simulation(cfg, gm, blocks, lib=product)
+
+    def totals():
+        m = e = 0.0
+        for b in sim.local_blocks:
+            U = sim.download_conserved(b.id)
+            m += float(np.sum(sim.interior(b.id, U[0]), dtype=np.longdouble))
+            e += float(np.sum(sim.interior(b.id, U[4]), dtype=np.longdouble))
+        return m, e
+    m0, e0 = totals()
+    dt = 0.5 * sim.compute_dt(False)[0]
+    sim.run_fixed(4, dt)
+    m1, e1 = totals()
+    sim.close()
+    print(f"closed 512^3 box, 4 steps: mass drift {abs(m1 - m0) / m0:.2e}, energy drift {abs(e1 - e0) / e0:.2e}")
+    assert abs(m1 - m0) / m0 < 1.0e-12 and abs(e1 - e0) / e0 < 1.0e-12
+    runs = {}
+    for strict in (False, True):
+        cfg, gm, blocks = cases.box3d(n=512, nb=4)
+        cfg.strict_fp = strict
+        sim = Simulation(cfg, gm, blocks, lib=product)
+        if not runs:
+            dt = 0.5 * sim.compute_dt(False)[0]
+        sim.run_fixed(3, dt)
+        runs[strict] = {b.id: [sim.interior(b.id, a).copy() for a in sim.download_conserved(b.id)] for b in sim.local_blocks}
+        sim.close()
+    g, c = max_rel_diff(runs[False], runs[True]), cellwise_rel_diff(runs[False], runs[True])
+    print(f"512^3 benchmark job, 3 steps: throughput build vs FMA-free build {g:.2e} (field scale), {c:.2e} (cell by cell)")
+    assert g < REL_TOL_U and c < 10.0 * REL_TOL_U
+
+
 def test_block_of_the_benchmark_shape(oracle, product):
     """One 128^3 block -- the benchmark's block size: whole 32 x 16 tiles, the k-chunking of a full-size block, TMA
     staging -- three predictor-corrector steps against the oracle."""
