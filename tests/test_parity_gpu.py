@@ -258,6 +258,33 @@ def test_benchmark_size_properties(product):
     assert g < REL_TOL_U and c < 10.0 * REL_TOL_U
 
 
+@pytest.mark.parametrize("config", ["ffs_4096x1024", "tpg_256"])
+def test_benchmark_size_properties_of_the_other_configurations(product, config):
+    """BASELINE configs[1] (2D forward-facing step, 4096 x 1024, the step face at cell 820 as in bench.py) and configs[4]
+    (thermally perfect 5-species air, 256^3 in 8 blocks of 128^3) at full size: the throughput build against the FMA-free
+    build after a few steps at the CFL step."""
+    from gdtk_b200 import Simulation
+    runs = {}
+    dt = None
+    for strict in (False, True):
+        if config == "ffs_4096x1024":
+            cfg, gm, blocks = cases.ffs(nx=4096, ny=1024, i_step=820)
+            nsteps = 4
+        else:
+            cfg, gm, blocks = cases.tpg_box3d(n=256, nb=2)
+            nsteps = 2
+        cfg.strict_fp = strict
+        sim = Simulation(cfg, gm, blocks, lib=product)
+        if dt is None:
+            dt = 0.5 * sim.compute_dt(False)[0]
+        sim.run_fixed(nsteps, dt)
+        runs[strict] = {b.id: [sim.interior(b.id, a).copy() for a in sim.download_conserved(b.id)] for b in sim.local_blocks}
+        sim.close()
+    g, c = max_rel_diff(runs[False], runs[True]), cellwise_rel_diff(runs[False], runs[True])
+    print(f"{config}: throughput build vs FMA-free build {g:.2e} (field scale), {c:.2e} (cell by cell)")
+    assert g < REL_TOL_U and c < 10.0 * REL_TOL_U
+
+
 def test_block_of_the_benchmark_shape(oracle, product):
     """One 128^3 block -- the benchmark's block size: whole 32 x 16 tiles, the k-chunking of a full-size block, TMA
     staging -- three predictor-corrector steps against the oracle."""
