@@ -592,7 +592,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    numa = bind_near_gpu(local_rank) if world > 1 else None
+    # keep this process (and with it the page-locked host buffers of the e2e figure: first touch) on the CPUs next to
+    # its GPU; the CPU arm below gets the full affinity mask back
+    try:
+        affinity0 = os.sched_getaffinity(0)
+    except Exception:
+        affinity0 = None
+    numa = bind_near_gpu(local_rank)
     if world > 1:
         import torch.distributed as dist
         try:     # halo messages on a high-priority NCCL stream: they run beside the interior tiles
@@ -641,6 +647,11 @@ def main():
         parity = run_parity_check(args, rank, world, local_rank)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if affinity0:
+            try:
+                os.sched_setaffinity(0, affinity0)       # all host cores for the CPU arm
+            except Exception:
+                pass
         cpu = run_cpu_sample(args, args.cpu_seconds)
     if rank == 0:
         line = {
